@@ -1,0 +1,204 @@
+"""ctypes binding of include/gsalign_b200.h (harness side: tests, bench.py, smoke).
+
+The product is the shared library ``gsalign_b200/libgsalign_b200.so`` (CUDA kernels + C ABI) and the
+``bin/GSAlign`` CLI built on it; this module only lets Python call the same entry points a C/C++ host
+would.  There is NO fallback: if the library is missing or no GPU is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsalign_b200.so")
+
+
+class GsaError(RuntimeError):
+    pass
+
+
+class IndexView(C.Structure):
+    _fields_ = [("bwt", C.POINTER(C.c_uint32)), ("bwt_size", C.c_uint64), ("primary", C.c_uint64),
+                ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64), ("sa", C.POINTER(C.c_uint64)),
+                ("n_sa", C.c_uint64), ("sa_intv", C.c_int32), ("pac", C.POINTER(C.c_uint8)),
+                ("l_pac", C.c_int64), ("n_contigs", C.c_int32), ("contig_off", C.POINTER(C.c_int64)),
+                ("contig_len", C.POINTER(C.c_int32))]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("min_seed_len", "sensitive", "max_indel", "min_block_score",
+                                         "min_aln_len", "min_idy", "one_on_one")]
+
+
+class Frag(C.Structure):
+    _fields_ = [("rPos", C.c_int64), ("qPos", C.c_int32), ("qLen", C.c_int32), ("rLen", C.c_int32),
+                ("bSeed", C.c_int32), ("aln_off", C.c_int64), ("aln_len", C.c_int32), ("reserved", C.c_int32)]
+
+
+FRAG_DTYPE = np.dtype([("rPos", "<i8"), ("qPos", "<i4"), ("qLen", "<i4"), ("rLen", "<i4"), ("bSeed", "<i4"),
+                       ("aln_off", "<i8"), ("aln_len", "<i4"), ("reserved", "<i4")])
+BLOCK_DTYPE = np.dtype([("score", "<i4"), ("aln_len", "<i4"), ("bDup", "<i4"), ("n_frags", "<i4"), ("frag_beg", "<i8")])
+
+
+class Alignment(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("blocks", C.c_void_p), ("n_frags", C.c_int64), ("frags", C.c_void_p),
+                ("aln_bytes", C.c_int64), ("aln1", C.c_void_p), ("aln2", C.c_void_p)]
+
+
+class Timing(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "seed_ms", "cluster_ms", "fill_ms", "d2h_ms", "host_ms")] + \
+               [(n, C.c_int64) for n in ("n_seeds", "n_dp", "dp_cells", "n_frags", "launches")]
+
+
+EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
+           "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
+           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch"]
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise GsaError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.gsa_last_error.restype = C.c_char_p
+    lib.gsa_dump_blocks.restype = C.c_int64
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _as_array(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.empty(0, dtype=dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+class Aligner:
+    """One context per GPU; mirrors the per-contig loop of GenomeComparison (reference src/GSAlign.cpp:473)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.gsa_create(C.c_int(device), C.byref(self.ctx))
+        if rc != 0:
+            raise GsaError(f"gsa_create(device={device}) failed with {rc}: no usable B200; there is no CPU fallback")
+        self._keep = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.gsa_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise GsaError(f"gsalign_b200 error {rc}: {self.lib.gsa_last_error(self.ctx).decode()}")
+
+    def upload_index(self, bi):
+        v = IndexView()
+        v.bwt = _p(bi.bwt, C.c_uint32); v.bwt_size = bi.bwt.shape[0]; v.primary = bi.primary
+        for i in range(5):
+            v.L2[i] = int(bi.L2[i])
+        v.seq_len = bi.seq_len; v.sa = _p(bi.sa, C.c_uint64); v.n_sa = bi.sa.shape[0]; v.sa_intv = bi.sa_intv
+        v.pac = _p(bi.pac, C.c_uint8); v.l_pac = bi.l_pac; v.n_contigs = len(bi.names)
+        v.contig_off = _p(bi.contig_off, C.c_int64); v.contig_len = _p(bi.contig_len, C.c_int32)
+        self._chk(self.lib.gsa_index_upload(self.ctx, C.byref(v)))
+
+    def set_params(self, **kw):
+        p = Params()
+        self.lib.gsa_default_params(C.byref(p))
+        for k, val in kw.items():
+            setattr(p, k, val)
+        self._chk(self.lib.gsa_set_params(self.ctx, C.byref(p)))
+
+    def contig_begin(self, seq):
+        """seq: bytes or uint8 ndarray (host)."""
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        self._keep = a
+        self._chk(self.lib.gsa_contig_begin(self.ctx, a.ctypes.data_as(C.c_char_p), C.c_uint32(a.shape[0])))
+
+    def contig_begin_device(self, dev_ptr: int, n: int):
+        self._chk(self.lib.gsa_contig_begin_device(self.ctx, C.c_void_p(dev_ptr), C.c_uint32(n)))
+
+    def seed(self) -> int:
+        n = C.c_int64()
+        self._chk(self.lib.gsa_seed(self.ctx, C.byref(n)))
+        return n.value
+
+    def fetch_seeds(self, n):
+        q = np.empty(n, dtype=np.int32); r = np.empty(n, dtype=np.int64); l = np.empty(n, dtype=np.int32)
+        self._chk(self.lib.gsa_fetch_seeds(self.ctx, _p(q, C.c_int32), _p(r, C.c_int64), _p(l, C.c_int32)))
+        return q, r, l
+
+    def cluster(self) -> int:
+        n = C.c_int32()
+        self._chk(self.lib.gsa_cluster(self.ctx, C.byref(n)))
+        return n.value
+
+    def dump_blocks(self, stage: int) -> np.ndarray:
+        w = self.lib.gsa_dump_blocks(self.ctx, C.c_int32(stage), None)
+        if w < 0:
+            self._chk(int(w))
+        out = np.empty(w, dtype=np.int64)
+        w2 = self.lib.gsa_dump_blocks(self.ctx, C.c_int32(stage), _p(out, C.c_int64))
+        if w2 < 0:
+            self._chk(int(w2))
+        return out
+
+    def _alignment(self, al: Alignment):
+        blocks = _as_array(al.blocks, al.n_blocks, BLOCK_DTYPE).copy()
+        frags = _as_array(al.frags, al.n_frags, FRAG_DTYPE).copy()
+        a1 = _as_array(al.aln1, al.aln_bytes, np.dtype("u1")).copy()
+        a2 = _as_array(al.aln2, al.aln_bytes, np.dtype("u1")).copy()
+        return blocks, frags, a1, a2
+
+    def fill(self):
+        al = Alignment()
+        self._chk(self.lib.gsa_fill(self.ctx, C.byref(al)))
+        return self._alignment(al)
+
+    def align_contig(self, seq):
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        self._keep = a
+        al = Alignment()
+        self._chk(self.lib.gsa_align_contig(self.ctx, a.ctypes.data_as(C.c_char_p), C.c_uint32(a.shape[0]), C.byref(al)))
+        return self._alignment(al)
+
+    def align_contig_raw(self, a: np.ndarray) -> Alignment:
+        """No copies of the result (bench path): returns the struct pointing into the library's pinned buffers."""
+        al = Alignment()
+        self._chk(self.lib.gsa_align_contig(self.ctx, a.ctypes.data_as(C.c_char_p), C.c_uint32(a.shape[0]), C.byref(al)))
+        return al
+
+    def timing(self) -> Timing:
+        t = Timing()
+        self._chk(self.lib.gsa_get_timing(self.ctx, C.byref(t)))
+        return t
+
+    def dp_batch(self, refs, qrys):
+        """refs/qrys: lists of bytes.  Returns (list of (row1,row2)), kernel_ms."""
+        n = len(refs)
+        ro = np.zeros(n + 1, dtype=np.int64); qo = np.zeros(n + 1, dtype=np.int64)
+        ro[1:] = np.cumsum([len(x) for x in refs]); qo[1:] = np.cumsum([len(x) for x in qrys])
+        rb = np.frombuffer(b"".join(refs) + b"\0", dtype=np.uint8); qb = np.frombuffer(b"".join(qrys) + b"\0", dtype=np.uint8)
+        tot = int(ro[-1] + qo[-1]) + 1
+        o1 = np.zeros(tot, dtype=np.uint8); o2 = np.zeros(tot, dtype=np.uint8); ol = np.zeros(max(n, 1), dtype=np.int32)
+        ms = C.c_float()
+        self._chk(self.lib.gsa_dp_batch(self.ctx, C.c_int32(n), rb.ctypes.data_as(C.c_char_p), _p(ro, C.c_int64),
+                                        qb.ctypes.data_as(C.c_char_p), _p(qo, C.c_int64), o1.ctypes.data_as(C.c_char_p),
+                                        o2.ctypes.data_as(C.c_char_p), _p(ol, C.c_int32), C.byref(ms)))
+        res = []
+        for i in range(n):
+            off = int(ro[i] + qo[i]); L = int(ol[i])
+            res.append((o1[off:off + L].tobytes(), o2[off:off + L].tobytes()))
+        return res, ms.value

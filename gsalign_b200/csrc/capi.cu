@@ -1,0 +1,218 @@
+// capi.cu -- the extern "C" entry points of include/gsalign_b200.h.
+#include "gsa_internal.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <chrono>
+
+int gsa_fail(gsa_ctx *ctx, int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+	if (ctx) ctx->err = buf;
+	return code;
+}
+
+int gsa_ensure(gsa_ctx *ctx, DevBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap && b.p) return GSA_OK;
+	size_t want = bytes + bytes / 4 + 256; // grow-only, with slack so that similar contigs do not reallocate
+	if (b.p) { cudaError_t e = cudaFree(b.p); b.p = nullptr; b.cap = 0; if (e != cudaSuccess) return gsa_fail(ctx, GSA_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e)); }
+	cudaError_t e = cudaMalloc(&b.p, want);
+	if (e != cudaSuccess) { b.p = nullptr; return gsa_fail(ctx, GSA_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); }
+	b.cap = want;
+	return GSA_OK;
+}
+
+int gsa_ensure_host(gsa_ctx *ctx, HostBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap && b.p) return GSA_OK;
+	size_t want = bytes + bytes / 4 + 256;
+	if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+	cudaError_t e = cudaMallocHost(&b.p, want);
+	if (e != cudaSuccess) { b.p = nullptr; return gsa_fail(ctx, GSA_ERR_NOMEM, "cudaMallocHost(%zu): %s", want, cudaGetErrorString(e)); }
+	b.cap = want;
+	return GSA_OK;
+}
+
+extern "C" {
+
+void gsa_default_params(gsa_params *p)
+{ // reference src/main.cpp:203-215
+	p->min_seed_len = 15; p->sensitive = 0; p->max_indel = 25; p->min_block_score = 200;
+	p->min_aln_len = 200; p->min_idy = 70; p->one_on_one = 0;
+}
+
+int gsa_create(int device, gsa_ctx **out)
+{
+	if (!out) return GSA_ERR_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+		fprintf(stderr, "gsalign_b200: no usable CUDA device %d (%s); there is no CPU fallback\n", device, e == cudaSuccess ? "bad ordinal" : cudaGetErrorString(e));
+		return GSA_ERR_CUDA;
+	}
+	gsa_ctx *ctx = new gsa_ctx();
+	ctx->device = device;
+	gsa_default_params(&ctx->prm);
+	memset(&ctx->tm, 0, sizeof(ctx->tm));
+	memset(&ctx->ix, 0, sizeof(ctx->ix));
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
+	for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+	if (gsa_ensure_host(ctx, ctx->h_small, 1 << 20) != GSA_OK) { delete ctx; return GSA_ERR_NOMEM; }
+	*out = ctx;
+	return GSA_OK;
+}
+
+void gsa_destroy(gsa_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	DevBuf *bufs[] = {&ctx->d_occ, &ctx->d_txt, &ctx->d_sa, &ctx->d_ktab, &ctx->d_cend, &ctx->d_seq, &ctx->d_qpk, &ctx->d_qinv,
+	                  &ctx->d_counter, &ctx->d_sq, &ctx->d_sr, &ctx->d_sl, &ctx->d_cub, &ctx->d_cq, &ctx->d_cr, &ctx->d_cl, &ctx->d_cb,
+	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum};
+	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+	for (DevBuf &b : ctx->d_tmp) if (b.p) cudaFree(b.p);
+	HostBuf *hb[] = {&ctx->h_small, &ctx->h_stage, &ctx->h_frag, &ctx->h_aln1, &ctx->h_aln2, &ctx->h_blocks};
+	for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
+	for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char *gsa_last_error(const gsa_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gsa_index_upload(gsa_ctx *ctx, const gsa_index_view *view)
+{
+	if (!ctx) return GSA_ERR_ARG;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	return gsa_impl_index_upload(ctx, view);
+}
+
+int gsa_set_params(gsa_ctx *ctx, const gsa_params *p)
+{
+	if (!ctx || !p) return GSA_ERR_ARG;
+	if (p->min_seed_len < 10 || p->min_seed_len > 30) return gsa_fail(ctx, GSA_ERR_ARG, "min_seed_len must be 10..30 (reference src/main.cpp:257)");
+	if (p->max_indel < 10 || p->max_indel > 100) return gsa_fail(ctx, GSA_ERR_ARG, "max_indel must be 10..100 (reference src/main.cpp:266)");
+	ctx->prm = *p;
+	return GSA_OK;
+}
+
+static int contig_reset(gsa_ctx *ctx, uint32_t len)
+{
+	if (!ctx->have_index) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_contig_begin: no index uploaded");
+	if (len >= 0x7FFFFF00u) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_contig_begin: contig longer than 2^31 (positions are int in the reference)");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	ctx->qlen = len; ctx->have_contig = false; ctx->have_seeds = false; ctx->have_cluster = false;
+	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0;
+	memset(&ctx->tm, 0, sizeof(ctx->tm));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_seq, (size_t)len + 64));
+	return GSA_OK;
+}
+
+int gsa_contig_begin(gsa_ctx *ctx, const char *seq, uint32_t len)
+{
+	if (!ctx || (!seq && len)) return GSA_ERR_ARG;
+	GSA_TRY(contig_reset(ctx, len));
+	ctx->h_seq = seq;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_seq.p, seq, len, cudaMemcpyHostToDevice, ctx->stream));
+	GSA_TRY(gsa_impl_pack_query(ctx));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+	ctx->have_contig = true;
+	return GSA_OK;
+}
+
+int gsa_contig_begin_device(gsa_ctx *ctx, const void *dev_seq, uint32_t len)
+{
+	if (!ctx || (!dev_seq && len)) return GSA_ERR_ARG;
+	GSA_TRY(contig_reset(ctx, len));
+	ctx->h_seq = nullptr;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_seq.p, dev_seq, len, cudaMemcpyDeviceToDevice, ctx->stream));
+	GSA_TRY(gsa_impl_pack_query(ctx));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+	ctx->have_contig = true;
+	return GSA_OK;
+}
+
+int gsa_seed(gsa_ctx *ctx, int64_t *n_seeds)
+{
+	if (!ctx) return GSA_ERR_ARG;
+	if (!ctx->have_contig) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_seed: call gsa_contig_begin first");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+	GSA_TRY(gsa_impl_seed(ctx));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+	ctx->tm.n_seeds = ctx->n_seeds;
+	if (n_seeds) *n_seeds = ctx->n_seeds;
+	return GSA_OK;
+}
+
+int gsa_fetch_seeds(gsa_ctx *ctx, int32_t *q, int64_t *r, int32_t *l)
+{
+	if (!ctx || !ctx->have_seeds) return GSA_ERR_ARG;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	size_t n = (size_t)ctx->n_seeds;
+	if (n == 0) return GSA_OK;
+	CUDA_TRY(ctx, cudaMemcpy(q, ctx->d_sq.p, n * 4, cudaMemcpyDeviceToHost));
+	CUDA_TRY(ctx, cudaMemcpy(r, ctx->d_sr.p, n * 8, cudaMemcpyDeviceToHost));
+	CUDA_TRY(ctx, cudaMemcpy(l, ctx->d_sl.p, n * 4, cudaMemcpyDeviceToHost));
+	return GSA_OK;
+}
+
+int gsa_cluster(gsa_ctx *ctx, int32_t *n_blocks)
+{
+	if (!ctx) return GSA_ERR_ARG;
+	if (!ctx->have_seeds) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_cluster: call gsa_seed first");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+	GSA_TRY(gsa_impl_cluster(ctx));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+	ctx->have_cluster = true;
+	if (n_blocks) *n_blocks = (int32_t)ctx->final_blocks.size();
+	return GSA_OK;
+}
+
+int gsa_fill(gsa_ctx *ctx, gsa_alignment *out)
+{
+	if (!ctx || !out) return GSA_ERR_ARG;
+	if (!ctx->have_cluster) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_fill: call gsa_cluster first");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+	GSA_TRY(gsa_impl_fill(ctx, out));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+	CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[7]));
+	cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
+	cudaEventElapsedTime(&ctx->tm.seed_ms, ctx->ev[2], ctx->ev[3]);
+	cudaEventElapsedTime(&ctx->tm.cluster_ms, ctx->ev[4], ctx->ev[5]);
+	cudaEventElapsedTime(&ctx->tm.fill_ms, ctx->ev[6], ctx->ev[7]);
+	return GSA_OK;
+}
+
+int gsa_align_contig(gsa_ctx *ctx, const char *seq, uint32_t len, gsa_alignment *out)
+{
+	GSA_TRY(gsa_contig_begin(ctx, seq, len));
+	GSA_TRY(gsa_seed(ctx, nullptr));
+	GSA_TRY(gsa_cluster(ctx, nullptr));
+	return gsa_fill(ctx, out);
+}
+
+int gsa_get_timing(const gsa_ctx *ctx, gsa_timing *out)
+{
+	if (!ctx || !out) return GSA_ERR_ARG;
+	*out = ctx->tm;
+	return GSA_OK;
+}
+
+int gsa_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
+                 const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms)
+{
+	if (!ctx || n_pairs < 0) return GSA_ERR_ARG;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	return gsa_impl_dp_batch(ctx, n_pairs, ref, ref_off, qry, qry_off, out1, out2, out_len, kernel_ms);
+}
+
+} // extern "C"

@@ -1,0 +1,79 @@
+// fm.cuh -- device-side primitives on the HBM index layout (see DevIndex in gsa_internal.cuh).
+#pragma once
+#include "gsa_internal.cuh"
+
+// nst_nt4_table (reference src/BWT_Index/bntseq.c:40-57): A/a 0, C/c 1, G/g 2, T/t 3, else 4
+__device__ __forceinline__ int gsa_nt4(unsigned char ch)
+{
+	unsigned char u = ch & 0xDF; // fold case (only letters reach here for valid input; others fall to 4)
+	return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4;
+}
+
+// number of symbols == c among the first m (1..64) symbols of a rank block's symbol quad
+__device__ __forceinline__ uint32_t gsa_block_count(uint4 s, int c, int m)
+{
+	unsigned long long hi = ((unsigned long long)s.x << 32) | s.y, lo = ((unsigned long long)s.z << 32) | s.w;
+	unsigned long long pat = 0x5555555555555555ull * (unsigned long long)c;
+	hi ^= pat; lo ^= pat;                                   // matching symbols become 00
+	hi = ~(hi | (hi >> 1)) & 0x5555555555555555ull;         // one bit per matching symbol
+	lo = ~(lo | (lo >> 1)) & 0x5555555555555555ull;
+	if (m <= 32) return __popcll(hi & (~0ull << (64 - 2 * m)));
+	return __popcll(hi) + __popcll(lo & (~0ull << (128 - 2 * m)));
+}
+
+// Occ(c, r): occurrences of c among the BWT characters of rows 0..r (inclusive), '$' row excluded.
+// One 32-byte sector: two 128-bit loads from the same sector.
+__device__ __forceinline__ uint32_t gsa_occ(const DevIndex &ix, int c, uint32_t r)
+{
+	const uint4 *blk = ix.occ + 2 * (size_t)(r >> 6);
+	uint4 cnt = __ldg(blk), sym = __ldg(blk + 1);
+	uint32_t base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
+	return base + gsa_block_count(sym, c, (int)(r & 63) + 1) - (uint32_t)(c == 0 && r >= ix.primary);
+}
+
+// Occ(c, r1) and Occ(c, r2) for r1 <= r2; shares the block when both rows fall in the same one
+__device__ __forceinline__ void gsa_occ2(const DevIndex &ix, int c, uint32_t r1, uint32_t r2, uint32_t &o1, uint32_t &o2)
+{
+	const uint4 *b1 = ix.occ + 2 * (size_t)(r1 >> 6);
+	uint4 cnt = __ldg(b1), sym = __ldg(b1 + 1);
+	uint32_t base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
+	o1 = base + gsa_block_count(sym, c, (int)(r1 & 63) + 1) - (uint32_t)(c == 0 && r1 >= ix.primary);
+	if ((r1 >> 6) != (r2 >> 6)) {
+		const uint4 *b2 = ix.occ + 2 * (size_t)(r2 >> 6);
+		cnt = __ldg(b2); sym = __ldg(b2 + 1);
+		base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
+	}
+	o2 = base + gsa_block_count(sym, c, (int)(r2 & 63) + 1) - (uint32_t)(c == 0 && r2 >= ix.primary);
+}
+
+// BWT character of row r (0..3; the '$' row reads as 0 -- callers special-case primary)
+__device__ __forceinline__ int gsa_bwt_char(const DevIndex &ix, uint32_t r)
+{
+	const uint32_t *w = (const uint32_t *)(ix.occ + 2 * (size_t)(r >> 6) + 1);
+	return (int)(__ldg(w + ((r & 63) >> 4)) >> ((~r & 15) << 1)) & 3;
+}
+
+// base i of a 2-bit MSB-first packed stream
+__device__ __forceinline__ int gsa_pk_base(const uint32_t *pk, uint32_t i)
+{
+	return (int)(__ldg(pk + (i >> 4)) >> ((~i & 15) << 1)) & 3;
+}
+
+// 16 bases starting at base i (MSB first); the stream must be padded by one word
+__device__ __forceinline__ uint32_t gsa_pk_window(const uint32_t *pk, uint32_t i)
+{
+	uint32_t w0 = __ldg(pk + (i >> 4)), w1 = __ldg(pk + (i >> 4) + 1);
+	return __funnelshift_l(w1, w0, (i & 15) << 1);
+}
+
+// 32 flag bits starting at bit i of an MSB-first bitmap (padded by one word)
+__device__ __forceinline__ uint32_t gsa_bit_window(const uint32_t *bm, uint32_t i)
+{
+	uint32_t w0 = __ldg(bm + (i >> 5)), w1 = __ldg(bm + (i >> 5) + 1);
+	return __funnelshift_l(w1, w0, i & 31);
+}
+
+__device__ __forceinline__ char gsa_text_char(const DevIndex &ix, int64_t pos)
+{
+	return "ACGT"[gsa_pk_base(ix.txt, (uint32_t)pos)];
+}

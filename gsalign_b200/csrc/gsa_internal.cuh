@@ -1,0 +1,137 @@
+// gsa_internal.cuh -- context, device buffers and the on-device index layout shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/gsalign_b200.h"
+
+#define GSA_SEED_CHUNK 10000   // SeedExplorationChunk, reference src/GSAlign.cpp:5 (observable: MEMs are cut at chunk ends)
+#define GSA_MAX_SEED_FREQ 100  // MaxSeedFreq, reference src/bwt_search.cpp:3
+#define GSA_MAX_SEED_GAP 5000  // MaxSeedGap, reference src/structure.h:23
+#define GSA_KTAB_MAX_K 12      // k-mer prefix table depth (never above MinSeedLength, see seed.cu)
+
+// ----------------------------------------------------------------------------------------------
+// Device index.  rows 0..n of the sorted suffix matrix of T$ (T = F . revcomp(F), |T| = n = 2N).
+//   occ   one 32-byte block per 64 rows: {u32 cnt[4]; u32 sym[4]}.  sym holds the BWT characters of the
+//         block's rows, 2 bit each, MSB first (row 64b at bits 31..30 of sym[0]); the row whose BWT
+//         character is '$' (primary) stores 0 and is corrected at query time.  cnt[c] = number of c among
+//         rows [0, 64b) INCLUDING that placeholder.  One rank query = one 32-byte sector.
+//   txt   T itself, 2 bit per base, MSB first in u32 words (16 bases per word), padded with 2 words.
+//   sa    the FULL suffix array, u32 per row (n < 2^32 in this build): sa[row] = start of the suffix.
+//   ktab  for every k-mer w (k = ktab_k, code = bases big-endian): the row interval {lo, size} of
+//         revcomp(w); size 0 = w does not occur in T.
+// ----------------------------------------------------------------------------------------------
+struct DevIndex {
+	const uint4 *occ;
+	const uint32_t *txt;
+	const uint32_t *sa;
+	const uint2 *ktab;
+	uint32_t L2[5];
+	uint32_t primary;
+	uint32_t n;        // 2N
+	int ktab_k;
+};
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct HostBuf { // pinned
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+// one contig-end table entry of ChrLocMap (reference src/bwt_index.cpp:247-252)
+struct ContigEnd { int64_t end; int32_t idx; int32_t pad; };
+
+struct BlockHdr { // host-side view of one candidate alignment block (a range of the device seed array)
+	int32_t score;
+	int32_t bDup;
+	int64_t beg, end;  // range in the post-overlap seed arrays
+	int32_t qf, ql, lenl; // first qPos, last qPos, last len
+	int64_t rf, rl;       // first rPos, last rPos
+};
+
+struct gsa_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[8] = {};
+	std::string err;
+	gsa_params prm;
+	gsa_timing tm;
+
+	// index
+	bool have_index = false;
+	DevIndex ix;
+	int64_t N = 0;                 // GenomeSize
+	DevBuf d_occ, d_txt, d_sa, d_ktab, d_cend;
+	std::vector<ContigEnd> cend;   // sorted by end (forward and reverse ends of every contig)
+	std::vector<int64_t> contig_off; std::vector<int32_t> contig_len;
+
+	// query contig
+	uint32_t qlen = 0;
+	bool have_contig = false, have_seeds = false, have_cluster = false;
+	DevBuf d_seq, d_qpk, d_qinv;   // raw chars, 2-bit packed, invalid-base bitmap
+	const char *h_seq = nullptr;   // borrowed host pointer (may be null for device-resident contigs)
+
+	// K1 output / K2 working set
+	int64_t n_seeds = 0;
+	DevBuf d_counter;              // small block of device counters
+	DevBuf d_sq, d_sr, d_sl;       // seeds: qPos (i32), rPos (i64), len (i32), sorted by (PosDiff,qPos) after gsa_seed
+	DevBuf d_tmp[24];              // scratch arrays for K2/K3 (sized on demand)
+	DevBuf d_cub;                  // cub temp storage
+	HostBuf h_small;               // pinned scratch for counters / piece tables
+	HostBuf h_stage;               // pinned staging for dumps
+
+	// K2 state kept for dumps and K3
+	int64_t n_cseeds = 0;          // seeds after RemoveOverlaps (device arrays cq/cr/cl)
+	DevBuf d_cq, d_cr, d_cl, d_cb; // qPos, rPos, len, block id
+	std::vector<BlockHdr> blocks_stage[4]; // host block lists at the dump stages 0..3
+	std::vector<int32_t> st0_q, st0_l; std::vector<int64_t> st0_r; // stage-0 seeds (kept only when dumps are enabled)
+	std::vector<int64_t> st0_beg;
+	bool keep_dumps = true;
+	std::vector<BlockHdr> final_blocks;   // after dedup, reference order
+
+	// fragments (after FillAlnBlockGaps) and K3 output
+	int64_t n_frags = 0;
+	DevBuf d_frag;                 // gsa_frag[n_frags]
+	DevBuf d_fblk;                 // block index per fragment
+	DevBuf d_aln1, d_aln2;         // row pools
+	DevBuf d_bsum;                 // per block {aln_len, score}
+	HostBuf h_frag, h_aln1, h_aln2, h_blocks;
+	std::vector<gsa_block> out_blocks;
+};
+
+int gsa_fail(gsa_ctx *ctx, int code, const char *fmt, ...);
+int gsa_ensure(gsa_ctx *ctx, DevBuf &b, size_t bytes);
+int gsa_ensure_host(gsa_ctx *ctx, HostBuf &b, size_t bytes);
+
+#define CUDA_TRY(ctx, call)                                                                          \
+	do {                                                                                             \
+		cudaError_t _e = (call);                                                                     \
+		if (_e != cudaSuccess)                                                                       \
+			return gsa_fail((ctx), GSA_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+	} while (0)
+
+#define GSA_TRY(call)                  \
+	do {                               \
+		int _r = (call);               \
+		if (_r != GSA_OK) return _r;   \
+	} while (0)
+
+#define KERNEL_CHECK(ctx) do { (ctx)->tm.launches++; CUDA_TRY((ctx), cudaGetLastError()); } while (0)
+
+static inline unsigned gsa_grid(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// phase entry points implemented per translation unit
+int gsa_impl_index_upload(gsa_ctx *ctx, const gsa_index_view *v);
+int gsa_impl_build_ktab(gsa_ctx *ctx, int k);
+int gsa_impl_pack_query(gsa_ctx *ctx);
+int gsa_impl_seed(gsa_ctx *ctx);
+int gsa_impl_cluster(gsa_ctx *ctx);
+int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out);
+int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
+                      const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms);

@@ -1,0 +1,157 @@
+/* gsalign_b200.h -- C ABI of the B200-native seed -> cluster/chain -> gapped-fill path.
+ *
+ * The reference (hsinnan75/GSAlign) has no plugin/FFI interface; its drop-in surface is the
+ * `bin/GSAlign` executable and its files.  This header therefore mirrors the reference's INTERNAL
+ * seams for the hot path -- one entry point per phase GenomeComparison() runs per query contig
+ * (src/GSAlign.cpp:473-552) -- so that a maintainer can replace those phases call by call (see
+ * INTEGRATION.md).  Plain C types only; no exceptions cross this boundary; every function returns
+ * 0 on success and a negative gsa_status otherwise (gsa_last_error() has the text).
+ *
+ * Ownership: the caller owns every pointer it passes in (borrowed for the duration of the call).
+ * The library owns device memory and the pinned host buffers behind every pointer it hands out;
+ * those stay valid until the next gsa_contig_begin*() on the same context or gsa_destroy().
+ * Threading: one gsa_ctx per GPU, driven by one host thread at a time.
+ */
+#ifndef GSALIGN_B200_H
+#define GSALIGN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsa_ctx gsa_ctx;
+
+enum gsa_status {
+	GSA_OK = 0,
+	GSA_ERR_ARG = -1,      /* bad argument / call order */
+	GSA_ERR_CUDA = -2,     /* CUDA runtime error (no CPU fallback exists) */
+	GSA_ERR_LIMIT = -3,    /* input exceeds a documented limit of this build */
+	GSA_ERR_NOMEM = -4
+};
+
+/* The BWA-format index exactly as the reference holds it after bwa_idx_load()
+ * (bwt_t / bntseq_t, src/structure.h:28-66; loaders src/bwt_index.cpp:15-159). */
+typedef struct {
+	const uint32_t *bwt;       /* .bwt payload after the 5 x u64 header (Occ-interleaved words) */
+	uint64_t bwt_size;         /* number of 32-bit words */
+	uint64_t primary;          /* bwt_t::primary */
+	uint64_t L2[5];            /* bwt_t::L2 */
+	uint64_t seq_len;          /* bwt_t::seq_len = 2N */
+	const uint64_t *sa;        /* bwt_t::sa, n_sa entries, sa[0] = (uint64_t)-1 */
+	uint64_t n_sa;
+	int32_t sa_intv;           /* bwt_t::sa_intv (32) */
+	const uint8_t *pac;        /* bwaidx_t::pac: forward strand, 2 bit/base, MSB first */
+	int64_t l_pac;             /* bntseq_t::l_pac = N */
+	int32_t n_contigs;         /* bntseq_t::n_seqs */
+	const int64_t *contig_off; /* bntann1_t::offset */
+	const int32_t *contig_len; /* bntann1_t::len */
+} gsa_index_view;
+
+/* The globals the hot path reads (src/main.cpp:203-215,239-291). */
+typedef struct {
+	int32_t min_seed_len;      /* MinSeedLength     -slen  [15]; forced to 10 by -sen (src/main.cpp:323) */
+	int32_t sensitive;         /* bSensitive        -sen   [0] */
+	int32_t max_indel;         /* MaxIndelSize      -ind   [25] */
+	int32_t min_block_score;   /* MinAlnBlockScore  -clr   [200] */
+	int32_t min_aln_len;       /* MinAlnLength      -alen  [200] */
+	int32_t min_idy;           /* MinSeqIdy         -idy   [70] */
+	int32_t one_on_one;        /* OneOnOneMode      -one   [0] */
+} gsa_params;
+
+/* FragPair_t (src/structure.h:103-113) without the strings. */
+typedef struct {
+	int64_t rPos;
+	int32_t qPos;
+	int32_t qLen;
+	int32_t rLen;
+	int32_t bSeed;             /* 1 = exact seed, 0 = gap fragment between two seeds */
+	int64_t aln_off;           /* gap fragments: offset of the two aligned rows in gsa_alignment::aln1/aln2 */
+	int32_t aln_len;           /* gap fragments: number of alignment columns; seeds: qLen */
+	int32_t reserved;
+} gsa_frag;
+
+/* AlnBlock_t (src/structure.h:115-122); coor is left to the emitter (GenCoordinateInfo is host logic). */
+typedef struct {
+	int32_t score;             /* AlnBlock_t::score after GenerateFragAlignment (identical columns) */
+	int32_t aln_len;           /* AlnBlock_t::aln_len */
+	int32_t bDup;              /* AlnBlock_t::bDup */
+	int32_t n_frags;
+	int64_t frag_beg;          /* first fragment in gsa_alignment::frags */
+} gsa_block;
+
+/* Everything the emitters (OutputMAF / OutputAlignment / VariantIdentification) need for one query
+ * contig: AlnBlockVec after src/GSAlign.cpp:540, in the reference's order. */
+typedef struct {
+	int32_t n_blocks;
+	const gsa_block *blocks;
+	int64_t n_frags;
+	const gsa_frag *frags;
+	int64_t aln_bytes;
+	const char *aln1;          /* reference rows of all gap fragments ('-' = gap), not NUL-separated */
+	const char *aln2;          /* query rows */
+} gsa_alignment;
+
+/* Per-phase device time of the last contig, milliseconds (CUDA events on the context's stream). */
+typedef struct {
+	float h2d_ms, seed_ms, cluster_ms, fill_ms, d2h_ms, host_ms;
+	int64_t n_seeds, n_dp, dp_cells, n_frags;
+	int64_t launches;          /* kernels launched by this library for the contig */
+} gsa_timing;
+
+/* --- lifecycle ------------------------------------------------------------------------------- */
+int gsa_create(int device, gsa_ctx **out);
+void gsa_destroy(gsa_ctx *ctx);
+const char *gsa_last_error(const gsa_ctx *ctx);
+
+/* Replaces bwa_idx_load() + RestoreReferenceInfo() for the device side (src/bwt_index.cpp:147-159,
+ * 229-264): re-lays the index out in HBM (32-byte rank blocks, 2-bit text, full suffix array,
+ * k-mer prefix table).  The view may be freed after the call returns. */
+int gsa_index_upload(gsa_ctx *ctx, const gsa_index_view *view);
+int gsa_set_params(gsa_ctx *ctx, const gsa_params *prm);
+void gsa_default_params(gsa_params *prm);
+
+/* --- per query contig (the body of the loop at src/GSAlign.cpp:483-548) ----------------------- */
+/* seq: the contig exactly as LoadQueryFile() stores it (any case, IUPAC allowed), host memory. */
+int gsa_contig_begin(gsa_ctx *ctx, const char *seq, uint32_t len);
+/* same, but seq is a DEVICE pointer (inputs already resident in HBM) */
+int gsa_contig_begin_device(gsa_ctx *ctx, const void *dev_seq, uint32_t len);
+
+/* K1  IdentifyLocalMEM + BWT_Search (src/GSAlign.cpp:51-107, src/bwt_search.cpp:141-185):
+ * all seeds of the contig, sorted by (PosDiff, qPos).  n_seeds may be NULL. */
+int gsa_seed(gsa_ctx *ctx, int64_t *n_seeds);
+
+/* K2  SeedGrouping .. CheckAlnBlockSpanMultiSeqs, the block-level dedup and FillAlnBlockGaps
+ * (src/GSAlign.cpp:495-514): candidate blocks, then the final fragment lists.  n_blocks may be NULL. */
+int gsa_cluster(gsa_ctx *ctx, int32_t *n_blocks);
+
+/* K3  GenerateFragAlignment + ksw2_alignment and the identity filter (src/GSAlign.cpp:523-540,
+ * src/ProcessCandidateAlignment.cpp:290-351, src/ksw2_alignment.cpp:251-273): copies the result to
+ * pinned host memory and fills *out. */
+int gsa_fill(gsa_ctx *ctx, gsa_alignment *out);
+
+/* The three phases back to back on a host buffer: the call GenomeComparison() would make per contig. */
+int gsa_align_contig(gsa_ctx *ctx, const char *seq, uint32_t len, gsa_alignment *out);
+
+int gsa_get_timing(const gsa_ctx *ctx, gsa_timing *out);
+
+/* --- dump hooks for per-kernel parity tests (the seams of SURVEY.md appendix E) ----------------- */
+/* seeds after gsa_seed(), sorted by (PosDiff, qPos); arrays must hold n_seeds entries */
+int gsa_fetch_seeds(gsa_ctx *ctx, int32_t *qPos, int64_t *rPos, int32_t *len);
+/* blocks after a stage of gsa_cluster(): 0 = SeedGroupAnalysis/AddAlnBlock, 1 = RemoveOverlaps,
+ * 2 = gap + contig-span splits, 3 = dedup + FillAlnBlockGaps.  Stream layout:
+ * [nblocks, {score, aln_len, bDup, nfrag, {bSeed,qPos,rPos,qLen,rLen} * nfrag} * nblocks].
+ * Pass out = NULL to get the length in int64 words. */
+int64_t gsa_dump_blocks(gsa_ctx *ctx, int32_t stage, int64_t *out);
+
+/* Stand-alone batch of global alignments through K3's DP kernel (ksw2_alignment semantics):
+ * pair i aligns ref[ref_off[i] .. ref_off[i+1]) with qry[qry_off[i] .. qry_off[i+1]); rows are written
+ * to out1/out2 at out_off[i] = ref_off[i] + qry_off[i], lengths to out_len.  Host pointers. */
+int gsa_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
+                 const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
