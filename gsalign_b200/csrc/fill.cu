@@ -1,3 +1,384 @@
-#include "gsa_internal.cuh"
-int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out) { (void)out; return gsa_fail(ctx, GSA_ERR_ARG, "fill: not built yet"); }
-int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t, const char *, const int64_t *, const char *, const int64_t *, char *, char *, int32_t *, float *) { return gsa_fail(ctx, GSA_ERR_ARG, "not built yet"); }
+// fill.cu -- K3: gapped fill of the fragments between seeds.
+//
+// Replaces GenerateFragAlignment (reference src/ProcessCandidateAlignment.cpp:290-351) and
+// ksw2_alignment / ksw_extz2_sse / ksw_backtrack (src/ksw2_alignment.cpp:25-273).
+//   * dispatch per non-seed fragment: pure gap rows, ungapped copy when qLen == rLen and <= 5 mismatches
+//     (query-N positions skipped), otherwise a GLOBAL affine-gap alignment over the full matrix
+//     (the reference passes w = -1, so no band is bit-exact).
+//   * DP recurrence (absolute scores, validated against the reference by the oracle tests): rows over the
+//     query fragment, columns over the reference fragment; match +1, mismatch -1, any non-ACGT 0;
+//     E(i,j) = max(H(i-1,j)-3, E(i-1,j)-1), F(i,j) = max(H(i,j-1)-3, F(i,j-1)-1), ties open;
+//     H = max(diag+s, E, F) preferring diag, then E, then F; scores fit int16 (|H| <= 2+m+n).
+//   * anti-diagonal wavefront: one CTA per problem, the three live diagonals of H/E/F live in shared memory
+//     as int16 and one direction byte per cell is written diagonal-major (coalesced) to HBM.
+//   * traceback walks the direction bytes backwards exactly like ksw_backtrack (continuation flags,
+//     leftover rows/columns become one gap) and the CTA reverses the rows in place.
+// Also accumulates AlnBlock_t::aln_len / score per block and applies nothing else: the identity filter and
+// the final block order are O(#blocks) host logic (see gsa_impl_fill at the bottom).
+#include "fm.cuh"
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <algorithm>
+
+#define DP_NEG (-30000)
+#define DP_MAX_DIM 8000
+
+struct DpProblem {
+	const char *ref_chars; // explicit reference fragment (gsa_dp_batch) or nullptr -> read the 2-bit text at rpos
+	const char *qry_chars;
+	int64_t rpos;
+	int64_t flag_off;      // into the direction-byte pool
+	int64_t out_off;       // into the row pools
+	int32_t m, n;          // m = reference fragment length (columns), n = query fragment length (rows)
+	int32_t frag;          // fragment index (pipeline) or pair index (batch)
+	int32_t pad;
+};
+
+// fragment type codes
+enum { FT_SEED = 0, FT_DEL = 1, FT_INS = 2, FT_COPY = 3, FT_DP = 4 };
+
+// ---- classification ----------------------------------------------------------------------------------
+// One thread per fragment: type, mismatch count for equal-length fragments (CheckFragPairMismatch,
+// src/ProcessCandidateAlignment.cpp:49-61), upper bound of its row length, DP cell count.
+__global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char *seq, DevIndex ix, uint8_t *type, int32_t *mism,
+                                int64_t *row_len, int64_t *flag_len, uint8_t *is_dp)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nfr) return;
+	gsa_frag f = frag[t];
+	uint8_t ty = FT_SEED; int64_t rl = 0, fl = 0; int mm = 0;
+	if (!f.bSeed) {
+		if (f.qLen == 0) { ty = FT_DEL; rl = f.rLen; }
+		else if (f.rLen == 0) { ty = FT_INS; rl = f.qLen; }
+		else {
+			ty = FT_DP;
+			if (f.qLen == f.rLen) {
+				for (int k = 0; k < f.qLen && mm <= 5; k++) {
+					int b = gsa_nt4(seq[f.qPos + k]);
+					if (b != 4 && b != gsa_pk_base(ix.txt, (uint32_t)(f.rPos + k))) mm++;
+				}
+				if (mm <= 5) ty = FT_COPY;
+			}
+			if (ty == FT_COPY) rl = f.qLen;
+			else { rl = (int64_t)f.qLen + f.rLen; int w = min(f.qLen, f.rLen); fl = (int64_t)(f.qLen + f.rLen - 1) * w; }
+		}
+	}
+	type[t] = ty; mism[t] = mm; row_len[t] = rl; flag_len[t] = fl; is_dp[t] = ty == FT_DP;
+}
+
+// rows of the non-DP fragment types + per-block sums (src/ProcessCandidateAlignment.cpp:303-331)
+__global__ void k_frag_simple(gsa_frag *frag, int64_t nfr, const int32_t *fblk, const uint8_t *type, const int32_t *mism, const int64_t *row_off,
+                              const unsigned char *seq, DevIndex ix, char *aln1, char *aln2, unsigned int *bsum)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nfr) return;
+	gsa_frag f = frag[t];
+	int ty = type[t], b = fblk[t];
+	int64_t o = row_off[t];
+	unsigned int alen = 0, sc = 0;
+	if (ty == FT_SEED) { alen = (unsigned)f.qLen; sc = (unsigned)f.qLen; }
+	else if (ty == FT_DEL) {
+		for (int k = 0; k < f.rLen; k++) { aln1[o + k] = gsa_text_char(ix, f.rPos + k); aln2[o + k] = '-'; }
+		alen = (unsigned)f.rLen; frag[t].aln_off = o; frag[t].aln_len = f.rLen;
+	} else if (ty == FT_INS) {
+		for (int k = 0; k < f.qLen; k++) { aln1[o + k] = '-'; aln2[o + k] = (char)seq[f.qPos + k]; }
+		alen = (unsigned)f.qLen; frag[t].aln_off = o; frag[t].aln_len = f.qLen;
+	} else if (ty == FT_COPY) {
+		for (int k = 0; k < f.qLen; k++) { aln1[o + k] = gsa_text_char(ix, f.rPos + k); aln2[o + k] = (char)seq[f.qPos + k]; }
+		alen = (unsigned)f.qLen; sc = (unsigned)(f.qLen - mism[t]); frag[t].aln_off = o; frag[t].aln_len = f.qLen;
+	} else return; // DP fragments are accounted by the DP kernel
+	atomicAdd(bsum + 2 * b, alen); atomicAdd(bsum + 2 * b + 1, sc);
+}
+
+__global__ void k_dp_problems(const int32_t *dp_idx, int64_t ndp, const gsa_frag *frag, const int64_t *row_off, const int64_t *flag_off,
+                              const unsigned char *seq, DpProblem *prob)
+{
+	int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= ndp) return;
+	int32_t t = dp_idx[k];
+	gsa_frag f = frag[t];
+	DpProblem p; p.ref_chars = nullptr; p.qry_chars = (const char *)seq + f.qPos; p.rpos = f.rPos; p.flag_off = flag_off[t]; p.out_off = row_off[t];
+	p.m = f.rLen; p.n = f.qLen; p.frag = t; p.pad = 0;
+	prob[k] = p;
+}
+
+// ---- the DP kernel -----------------------------------------------------------------------------------------
+// Shared memory (dynamic): codes of both fragments (bytes) and 7 int16 arrays over the query rows:
+// H on diagonals d-1 and d-2 and the one being written, E and F on d-1 and the one being written.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_dp(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *flags, char *aln1, char *aln2, int32_t *out_len, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum, int rows_cap)
+{
+	extern __shared__ int16_t smem[];
+	int pi = blockIdx.x;
+	if (pi >= nprob) return;
+	const DpProblem P = prob[pi];
+	const int m = P.m, n = P.n, tid = threadIdx.x;
+	int16_t *H0 = smem, *H1 = H0 + rows_cap, *H2 = H1 + rows_cap, *E0 = H2 + rows_cap, *E1 = E0 + rows_cap, *F0 = E1 + rows_cap, *F1 = F0 + rows_cap;
+	uint8_t *qc = (uint8_t *)(F1 + rows_cap), *rc = qc + rows_cap; // rc holds m codes (cols_cap == rows_cap)
+	for (int i = tid; i < n; i += THREADS) qc[i] = (uint8_t)gsa_nt4((unsigned char)P.qry_chars[i]);
+	for (int j = tid; j < m; j += THREADS) rc[j] = P.ref_chars ? (uint8_t)gsa_nt4((unsigned char)P.ref_chars[j]) : (uint8_t)gsa_pk_base(ix.txt, (uint32_t)(P.rpos + j));
+	if (THREADS == 32) __syncwarp(); else __syncthreads();
+	const int w = min(m, n);
+	uint8_t *fl = flags + P.flag_off;
+	// Hd1 = diagonal d-1, Hd2 = diagonal d-2, Hn = diagonal d (being written); same for E/F
+	int16_t *Hd2 = H0, *Hd1 = H1, *Hn = H2, *Ed1 = E0, *En = E1, *Fd1 = F0, *Fn = F1;
+	for (int d = 0; d < m + n - 1; d++) {
+		int i_lo = max(0, d - m + 1), i_hi = min(n - 1, d);
+		uint8_t *fd = fl + (int64_t)d * w - i_lo;
+		for (int i = i_lo + tid; i <= i_hi; i += THREADS) {
+			int j = d - i;
+			int a = qc[i], b = rc[j];
+			int s = (a > 3 || b > 3) ? 0 : (a == b ? 1 : -1);
+			int hdiag, hup, eup, hleft, fleft;
+			if (i == 0) { hup = -(2 + (j + 1)); eup = DP_NEG; hdiag = j == 0 ? 0 : -(2 + j); }
+			else { hup = Hd1[i - 1]; eup = Ed1[i - 1]; hdiag = j == 0 ? -(2 + i) : Hd2[i - 1]; }
+			if (j == 0) { hleft = -(2 + (i + 1)); fleft = DP_NEG; }
+			else { hleft = Hd1[i]; fleft = Fd1[i]; }
+			int eo = hup - 3, ee = eup - 1, fo = hleft - 3, fe = fleft - 1;
+			int ye = ee > eo, yf = fe > fo;      // strict: a tie opens a new gap
+			int e = ye ? ee : eo, f = yf ? fe : fo;
+			int h = hdiag + s, dir = 0;
+			if (e > h) { h = e; dir = 1; }        // E only if strictly greater than diag
+			if (f > h) { h = f; dir = 2; }        // F only if strictly greater than both
+			Hn[i] = (int16_t)h; En[i] = (int16_t)e; Fn[i] = (int16_t)f;
+			fd[i] = (uint8_t)(dir | (ye << 3) | (yf << 4));
+		}
+		if (THREADS == 32) __syncwarp(); else __syncthreads();
+		int16_t *t = Hd2; Hd2 = Hd1; Hd1 = Hn; Hn = t;
+		t = Ed1; Ed1 = En; En = t;
+		t = Fd1; Fd1 = Fn; Fn = t;
+	}
+	__threadfence_block();
+	// ---- traceback (ksw_backtrack, src/ksw2_alignment.cpp:25-68), rows are produced back to front
+	__shared__ int sL, sSame;
+	char *o1 = aln1 + P.out_off, *o2 = aln2 + P.out_off;
+	if (tid == 0) {
+		int i = n - 1, j = m - 1, state = 0, cont = 0, L = 0;
+		while (i >= 0 && j >= 0) {
+			int d = i + j, i_lo = max(0, d - m + 1);
+			int t = fl[(int64_t)d * w + (i - i_lo)];
+			if (state == 0 || !cont) state = t & 3;
+			char c1, c2;
+			if (state == 0) { c1 = P.ref_chars ? P.ref_chars[j] : "ACGT"[rc[j]]; c2 = P.qry_chars[i]; i--; j--; }
+			else if (state == 1) { c1 = '-'; c2 = P.qry_chars[i]; cont = (t >> 3) & 1; i--; }
+			else { c1 = P.ref_chars ? P.ref_chars[j] : "ACGT"[rc[j]]; c2 = '-'; cont = (t >> 4) & 1; j--; }
+			o1[L] = c1; o2[L] = c2; L++;
+		}
+		for (; i >= 0; i--, L++) { o1[L] = '-'; o2[L] = P.qry_chars[i]; }
+		for (; j >= 0; j--, L++) { o1[L] = P.ref_chars ? P.ref_chars[j] : "ACGT"[rc[j]]; o2[L] = '-'; }
+		sL = L; sSame = 0;
+	}
+	__syncthreads();
+	const int L = sL;
+	int same = 0;
+	for (int k = tid; k < L / 2; k += THREADS) {
+		char a = o1[k], b = o1[L - 1 - k]; o1[k] = b; o1[L - 1 - k] = a;
+		a = o2[k]; b = o2[L - 1 - k]; o2[k] = b; o2[L - 1 - k] = a;
+	}
+	__syncthreads();
+	// CountIdenticalPairs (src/ProcessCandidateAlignment.cpp:38-47): nt4 classes, so '-' == N == 4
+	for (int k = tid; k < L; k += THREADS) same += gsa_nt4((unsigned char)o1[k]) == gsa_nt4((unsigned char)o2[k]);
+	if (same) atomicAdd(&sSame, same);
+	__syncthreads();
+	if (tid == 0) {
+		if (out_len) out_len[P.frag] = L;
+		if (frag) {
+			frag[P.frag].aln_off = P.out_off; frag[P.frag].aln_len = L;
+			int b = fblk[P.frag];
+			atomicAdd(bsum + 2 * b, (unsigned)L); atomicAdd(bsum + 2 * b + 1, (unsigned)sSame);
+		}
+	}
+}
+
+static size_t dp_smem_bytes(int rows_cap) { return (size_t)rows_cap * (7 * sizeof(int16_t) + 2); }
+
+// launches the DP over problems [0,nprob) whose max(m,n) <= dim_cap
+template <int THREADS>
+static int launch_dp(gsa_ctx *ctx, const DpProblem *prob, int nprob, int dim_cap, uint8_t *flags, char *a1, char *a2, int32_t *out_len, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+{
+	if (nprob <= 0) return GSA_OK;
+	int rows_cap = (dim_cap + 15) & ~15;
+	size_t smem = dp_smem_bytes(rows_cap);
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_dp<THREADS><<<nprob, THREADS, smem, ctx->stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, frag, fblk, bsum, rows_cap);
+	KERNEL_CHECK(ctx);
+	return GSA_OK;
+}
+
+// problems are binned by max(m,n) so that small ones get small shared memory (many CTAs per SM)
+static int run_dp_binned(gsa_ctx *ctx, std::vector<DpProblem> &hp, DpProblem *d_prob, uint8_t *flags, char *a1, char *a2, int32_t *out_len, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+{
+	std::stable_sort(hp.begin(), hp.end(), [](const DpProblem &a, const DpProblem &b) { return std::max(a.m, a.n) < std::max(b.m, b.n); });
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_prob, hp.data(), hp.size() * sizeof(DpProblem), cudaMemcpyHostToDevice, ctx->stream));
+	const int caps[] = {32, 128, 512, 2048, DP_MAX_DIM};
+	size_t beg = 0;
+	for (int c = 0; c < 5; c++) {
+		size_t end = beg;
+		while (end < hp.size() && std::max(hp[end].m, hp[end].n) <= caps[c]) end++;
+		int cnt = (int)(end - beg);
+		if (cnt > 0) {
+			if (c == 0) GSA_TRY(launch_dp<32>(ctx, d_prob + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
+			else if (c == 1) GSA_TRY(launch_dp<64>(ctx, d_prob + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
+			else GSA_TRY(launch_dp<256>(ctx, d_prob + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
+		}
+		beg = end;
+	}
+	if (beg != hp.size()) return gsa_fail(ctx, GSA_ERR_LIMIT, "DP fragment longer than %d", DP_MAX_DIM);
+	return GSA_OK;
+}
+
+struct Ws3 {
+	gsa_ctx *ctx; int next = 0; int rc = GSA_OK;
+	explicit Ws3(gsa_ctx *c) : ctx(c) {}
+	template <typename T> T *get(int64_t n)
+	{
+		if (next >= 64) { rc = gsa_fail(ctx, GSA_ERR_NOMEM, "fill: out of scratch slots"); return nullptr; }
+		DevBuf &b = ctx->d_tmp[next++];
+		int r = gsa_ensure(ctx, b, (size_t)(n > 0 ? n : 1) * sizeof(T) + 64);
+		if (r != GSA_OK) { rc = r; return nullptr; }
+		return (T *)b.p;
+	}
+};
+
+static int scan_ex64(gsa_ctx *ctx, const int64_t *in, int64_t *out, int64_t n)
+{
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream);
+	GSA_TRY(gsa_ensure(ctx, ctx->d_cub, bytes));
+	CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, bytes, in, out, (int)n, ctx->stream));
+	ctx->tm.launches++;
+	return GSA_OK;
+}
+
+int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
+{
+	memset(out, 0, sizeof(*out));
+	ctx->out_blocks.clear();
+	int nblk = (int)ctx->final_blocks.size();
+	int64_t nfr = ctx->n_frags;
+	ctx->tm.n_frags = nfr;
+	if (nblk == 0 || nfr == 0) return GSA_OK;
+	Ws3 ws(ctx);
+	gsa_frag *frag = (gsa_frag *)ctx->d_frag.p; const int32_t *fblk = (const int32_t *)ctx->d_fblk.p;
+	const unsigned char *seq = (const unsigned char *)ctx->d_seq.p;
+	uint8_t *type = ws.get<uint8_t>(nfr), *is_dp = ws.get<uint8_t>(nfr);
+	int32_t *mism = ws.get<int32_t>(nfr), *dp_idx = ws.get<int32_t>(nfr);
+	int64_t *row_len = ws.get<int64_t>(nfr + 1), *flag_len = ws.get<int64_t>(nfr + 1), *row_off = ws.get<int64_t>(nfr + 1), *flag_off = ws.get<int64_t>(nfr + 1);
+	if (ws.rc) return ws.rc;
+	GSA_TRY(gsa_ensure(ctx, ctx->d_bsum, (size_t)nblk * 8));
+	unsigned int *bsum = (unsigned int *)ctx->d_bsum.p;
+	int32_t *d_ndp = (int32_t *)ctx->d_counter.p + 32;
+	CUDA_TRY(ctx, cudaMemsetAsync(bsum, 0, (size_t)nblk * 8, ctx->stream));
+	k_frag_classify<<<gsa_grid(nfr, 128), 128, 0, ctx->stream>>>(frag, nfr, seq, ctx->ix, type, mism, row_len, flag_len, is_dp);
+	KERNEL_CHECK(ctx);
+	CUDA_TRY(ctx, cudaMemsetAsync(row_len + nfr, 0, 8, ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(flag_len + nfr, 0, 8, ctx->stream));
+	GSA_TRY(scan_ex64(ctx, row_len, row_off, nfr + 1));
+	GSA_TRY(scan_ex64(ctx, flag_len, flag_off, nfr + 1));
+	{
+		size_t bytes = 0;
+		thrust::counting_iterator<int32_t> it(0);
+		cub::DeviceSelect::Flagged(nullptr, bytes, it, is_dp, dp_idx, d_ndp, (int)nfr, ctx->stream);
+		GSA_TRY(gsa_ensure(ctx, ctx->d_cub, bytes));
+		CUDA_TRY(ctx, cub::DeviceSelect::Flagged(ctx->d_cub.p, bytes, it, is_dp, dp_idx, d_ndp, (int)nfr, ctx->stream));
+		ctx->tm.launches += 2;
+	}
+	int64_t *hs = (int64_t *)ctx->h_small.p;
+	CUDA_TRY(ctx, cudaMemcpyAsync(hs, row_off + nfr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(hs + 1, flag_off + nfr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(hs + 2, d_ndp, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	int64_t row_bytes = hs[0], flag_bytes = hs[1], ndp = *(int32_t *)(hs + 2);
+	GSA_TRY(gsa_ensure(ctx, ctx->d_aln1, (size_t)row_bytes + 16));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_aln2, (size_t)row_bytes + 16));
+	char *a1 = (char *)ctx->d_aln1.p, *a2 = (char *)ctx->d_aln2.p;
+	k_frag_simple<<<gsa_grid(nfr, 128), 128, 0, ctx->stream>>>(frag, nfr, fblk, type, mism, row_off, seq, ctx->ix, a1, a2, bsum);
+	KERNEL_CHECK(ctx);
+	ctx->tm.n_dp = ndp; ctx->tm.dp_cells = 0;
+	if (ndp > 0) {
+		DpProblem *d_prob = ws.get<DpProblem>(ndp);
+		uint8_t *flags = ws.get<uint8_t>(flag_bytes);
+		if (ws.rc) return ws.rc;
+		k_dp_problems<<<gsa_grid(ndp, 128), 128, 0, ctx->stream>>>(dp_idx, ndp, frag, row_off, flag_off, seq, d_prob);
+		KERNEL_CHECK(ctx);
+		std::vector<DpProblem> hp((size_t)ndp);
+		CUDA_TRY(ctx, cudaMemcpyAsync(hp.data(), d_prob, (size_t)ndp * sizeof(DpProblem), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		for (const DpProblem &p : hp) ctx->tm.dp_cells += (int64_t)p.m * p.n;
+		GSA_TRY(run_dp_binned(ctx, hp, d_prob, flags, a1, a2, nullptr, frag, fblk, bsum));
+	}
+	// ---- results to pinned host memory ---------------------------------------------------------------------
+	GSA_TRY(gsa_ensure_host(ctx, ctx->h_frag, (size_t)nfr * sizeof(gsa_frag)));
+	GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln1, (size_t)row_bytes + 16));
+	GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln2, (size_t)row_bytes + 16));
+	GSA_TRY(gsa_ensure_host(ctx, ctx->h_blocks, (size_t)nblk * 8));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_frag.p, frag, (size_t)nfr * sizeof(gsa_frag), cudaMemcpyDeviceToHost, ctx->stream));
+	if (row_bytes) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln1.p, a1, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln2.p, a2, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_blocks.p, bsum, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	// ---- identity filter + final order (src/GSAlign.cpp:529-540): O(#blocks), same std::sort as the reference
+	const unsigned int *hb = (const unsigned int *)ctx->h_blocks.p;
+	std::vector<BlockHdr> vec = ctx->final_blocks;
+	for (int k = 0; k < nblk; k++) {
+		vec[k].aln_len = (int32_t)hb[2 * k]; vec[k].score = (int32_t)hb[2 * k + 1];
+		if ((int)(100 * (1.0 * vec[k].score / vec[k].aln_len)) < ctx->prm.min_idy) vec[k].score = 0;
+	}
+	gsa_host_remove_bad(vec);
+	ctx->out_blocks.resize(vec.size());
+	for (size_t k = 0; k < vec.size(); k++) {
+		gsa_block &b = ctx->out_blocks[k];
+		b.score = vec[k].score; b.aln_len = vec[k].aln_len; b.bDup = vec[k].bDup; b.n_frags = vec[k].n_frags; b.frag_beg = vec[k].frag_beg;
+	}
+	out->n_blocks = (int32_t)ctx->out_blocks.size(); out->blocks = ctx->out_blocks.data();
+	out->n_frags = nfr; out->frags = (const gsa_frag *)ctx->h_frag.p;
+	out->aln_bytes = row_bytes; out->aln1 = (const char *)ctx->h_aln1.p; out->aln2 = (const char *)ctx->h_aln2.p;
+	return GSA_OK;
+}
+
+// ---- stand-alone DP batch (dump hook / DP stress bench) -----------------------------------------------------
+int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
+                      const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms)
+{
+	if (kernel_ms) *kernel_ms = 0;
+	if (n_pairs == 0) return GSA_OK;
+	if (!ref || !qry || !ref_off || !qry_off || !out1 || !out2 || !out_len) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dp_batch: null argument");
+	Ws3 ws(ctx);
+	int64_t rb = ref_off[n_pairs], qb = qry_off[n_pairs];
+	char *d_ref = ws.get<char>(rb + 1), *d_qry = ws.get<char>(qb + 1), *d_o1 = ws.get<char>(rb + qb + 1), *d_o2 = ws.get<char>(rb + qb + 1);
+	int32_t *d_len = ws.get<int32_t>(n_pairs);
+	DpProblem *d_prob = ws.get<DpProblem>(n_pairs);
+	if (ws.rc) return ws.rc;
+	std::vector<DpProblem> hp((size_t)n_pairs);
+	int64_t fbytes = 0;
+	for (int i = 0; i < n_pairs; i++) {
+		DpProblem &p = hp[i];
+		p.m = (int32_t)(ref_off[i + 1] - ref_off[i]); p.n = (int32_t)(qry_off[i + 1] - qry_off[i]);
+		if (p.m <= 0 || p.n <= 0) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dp_batch: empty fragment in pair %d", i);
+		p.ref_chars = d_ref + ref_off[i]; p.qry_chars = d_qry + qry_off[i]; p.rpos = 0; p.flag_off = fbytes; p.out_off = ref_off[i] + qry_off[i];
+		p.frag = i; p.pad = 0;
+		fbytes += (int64_t)(p.m + p.n - 1) * std::min(p.m, p.n);
+	}
+	uint8_t *flags = ws.get<uint8_t>(fbytes);
+	if (ws.rc) return ws.rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_ref, ref, (size_t)rb, cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_qry, qry, (size_t)qb, cudaMemcpyHostToDevice, ctx->stream));
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	cudaEventRecord(e0, ctx->stream);
+	int rc = run_dp_binned(ctx, hp, d_prob, flags, d_o1, d_o2, d_len, nullptr, nullptr, nullptr);
+	cudaEventRecord(e1, ctx->stream);
+	if (rc == GSA_OK) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(out1, d_o1, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(out2, d_o2, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(out_len, d_len, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	return rc;
+}

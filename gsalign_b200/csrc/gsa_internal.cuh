@@ -53,6 +53,13 @@ struct BlockHdr { // host-side view of one candidate alignment block (a range of
 	int64_t beg, end;  // range in the post-overlap seed arrays
 	int32_t qf, ql, lenl; // first qPos, last qPos, last len
 	int64_t rf, rl;       // first rPos, last rPos
+	int64_t frag_beg; int32_t n_frags; int32_t aln_len; // filled by the normal-pair / fill phases
+};
+
+// one maximal run of seeds between break points (device -> host, O(#pieces))
+struct Piece {
+	int64_t beg, end, sumlen, rf, rl;
+	int32_t qf, ql, lenl, pad;
 };
 
 struct gsa_ctx {
@@ -81,7 +88,7 @@ struct gsa_ctx {
 	int64_t n_seeds = 0;
 	DevBuf d_counter;              // small block of device counters
 	DevBuf d_sq, d_sr, d_sl;       // seeds: qPos (i32), rPos (i64), len (i32), sorted by (PosDiff,qPos) after gsa_seed
-	DevBuf d_tmp[24];              // scratch arrays for K2/K3 (sized on demand)
+	DevBuf d_tmp[64];              // scratch arrays for K2/K3 (sized on demand)
 	DevBuf d_cub;                  // cub temp storage
 	HostBuf h_small;               // pinned scratch for counters / piece tables
 	HostBuf h_stage;               // pinned staging for dumps
@@ -89,10 +96,10 @@ struct gsa_ctx {
 	// K2 state kept for dumps and K3
 	int64_t n_cseeds = 0;          // seeds after RemoveOverlaps (device arrays cq/cr/cl)
 	DevBuf d_cq, d_cr, d_cl, d_cb; // qPos, rPos, len, block id
-	std::vector<BlockHdr> blocks_stage[4]; // host block lists at the dump stages 0..3
-	std::vector<int32_t> st0_q, st0_l; std::vector<int64_t> st0_r; // stage-0 seeds (kept only when dumps are enabled)
-	std::vector<int64_t> st0_beg;
-	bool keep_dumps = true;
+	std::vector<BlockHdr> blocks_stage[3]; // host block lists at dump stages 0..2 (stage 3 = final_blocks)
+	DevBuf d_s0q, d_s0r, d_s0l;    // stage-0 seed arrays (pre-overlap), kept only when dumps are enabled
+	int64_t n_s0 = 0;
+	bool keep_dumps = false;
 	std::vector<BlockHdr> final_blocks;   // after dedup, reference order
 
 	// fragments (after FillAlnBlockGaps) and K3 output
@@ -132,6 +139,11 @@ int gsa_impl_build_ktab(gsa_ctx *ctx, int k);
 int gsa_impl_pack_query(gsa_ctx *ctx);
 int gsa_impl_seed(gsa_ctx *ctx);
 int gsa_impl_cluster(gsa_ctx *ctx);
+// host block logic (block_logic.cpp): exact restatement of the reference's O(#blocks) serial phases
+void gsa_host_split(const gsa_ctx *ctx, std::vector<BlockHdr> &vec, const std::vector<Piece> &p1, const std::vector<Piece> &p2);
+void gsa_host_dedup(const gsa_ctx *ctx, std::vector<BlockHdr> &vec);
+void gsa_host_remove_bad(std::vector<BlockHdr> &vec);
+int gsa_host_chr_idx(const gsa_ctx *ctx, int64_t rpos, int64_t *end_out);
 int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out);
 int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
                       const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms);

@@ -136,6 +136,9 @@ int gsa_align_contig(gsa_ctx *ctx, const char *seq, uint32_t len, gsa_alignment 
 
 int gsa_get_timing(const gsa_ctx *ctx, gsa_timing *out);
 
+/* keep (1) or drop (0, default) the intermediate block lists gsa_dump_blocks() serves */
+int gsa_set_dump(gsa_ctx *ctx, int enable);
+
 /* --- dump hooks for per-kernel parity tests (the seams of SURVEY.md appendix E) ----------------- */
 /* seeds after gsa_seed(), sorted by (PosDiff, qPos); arrays must hold n_seeds entries */
 int gsa_fetch_seeds(gsa_ctx *ctx, int32_t *qPos, int64_t *rPos, int32_t *len);

@@ -1,0 +1,158 @@
+"""K2 + K3 parity through the C ABI: every seam of the cluster/chain/fill path against the UNMODIFIED
+reference (oracle/_ref/libgsref.so driven by tests/ref_worker.py in a fresh process) and against the
+oracle restatement."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_reference(prefix, query_path, out_path, **prm):
+    if not os.path.exists(os.path.join(orc.REF_DIR, "libgsref.so")):
+        pytest.skip("oracle/_ref/libgsref.so not built")
+    args = [sys.executable, os.path.join(HERE, "ref_worker.py"), prefix, query_path, out_path] + [f"{k}={v}" for k, v in prm.items()]
+    subprocess.run(args, check=True)
+    with open(out_path, "rb") as f:
+        return pickle.load(f)
+
+
+def blocks_key(b):
+    return (b[0], b[3])
+
+
+def check_contig(aligner, seq, ref):
+    """ref: one entry of ref_worker's result."""
+    from gsalign_b200 import capi
+    aligner.contig_begin(seq)
+    n = aligner.seed()
+    q, r, l = aligner.fetch_seeds(n)
+    rq, rr, rl = ref["seeds"]
+    assert np.array_equal(q, rq) and np.array_equal(r, rr) and np.array_equal(l, rl)
+    aligner.cluster()
+    for stage in (0, 1, 2):
+        mine = orc.parse_blocks(aligner.dump_blocks(stage))
+        theirs = ref["stages"][stage]
+        assert len(mine) == len(theirs), f"stage {stage}: {len(mine)} vs {len(theirs)} blocks"
+        if stage < 2:  # push order is defined at -t 1; after the splits the std::sort tie order applies too
+            assert mine == theirs, f"stage {stage}"
+        assert sorted(mine, key=blocks_key) == sorted(theirs, key=blocks_key), f"stage {stage}"
+    assert orc.parse_blocks(aligner.dump_blocks(2)) == ref["stages"][2]
+    s3 = orc.parse_blocks(aligner.dump_blocks(3))
+    assert s3 == ref["stages"][3], "stage 3 (dedup + normal pairs)"
+    blocks, frags, a1, a2 = aligner.fill()
+    final = ref["stages"][5]
+    assert len(blocks) == len(final)
+    # the reference's aln strings are in stage-4 order (pre identity filter); index them by fragment key
+    ref_aln = {}
+    k = 0
+    for b in ref["stages"][4]:
+        for f in b[3]:
+            if f[0] == 0:
+                ref_aln[(f[1], f[2], f[3], f[4])] = (ref["aln"][k], ref["aln"][k + 1]); k += 2
+    for bi, b in enumerate(blocks):
+        score, aln_len, dup, fr = final[bi]
+        assert (int(b["score"]), int(b["aln_len"]), int(b["bDup"]), int(b["n_frags"])) == (score, aln_len, dup, len(fr))
+        mine = frags[int(b["frag_beg"]): int(b["frag_beg"]) + int(b["n_frags"])]
+        for f, g in zip(mine, fr):
+            assert (int(f["bSeed"]), int(f["qPos"]), int(f["rPos"]), int(f["qLen"]), int(f["rLen"])) == g
+            if not f["bSeed"]:
+                o, L = int(f["aln_off"]), int(f["aln_len"])
+                assert (a1[o:o + L].tobytes(), a2[o:o + L].tobytes()) == ref_aln[g[1:]], g
+    return len(blocks)
+
+
+@pytest.fixture(scope="module")
+def ecoli_ref(ecoli, workdir):
+    return run_reference(ecoli["prefix"], ecoli["query_path"], os.path.join(workdir, "ecoli_ref.pkl"))
+
+
+def test_ecoli_all_seams(ecoli, ecoli_ref):
+    from gsalign_b200 import capi
+    a = capi.Aligner(0)
+    a.upload_index(ecoli["index"])
+    a.lib.gsa_set_dump(a.ctx, 1)
+    assert check_contig(a, ecoli["query"], ecoli_ref[0]) == 1
+    a.close()
+
+
+def make_rearranged(workdir, seed=7, n=600_000):
+    """3 reference contigs with an exact 6 kb duplication; 2 query contigs built from mutated, reversed,
+    translocated pieces with N runs, lower case and a 700 bp unrelated insertion."""
+    from gsalign_b200 import synth
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    codes = [rng.integers(0, 4, size=n // 3, dtype=np.uint8) for _ in range(3)]
+    codes[1][50_000:56_000] = codes[0][20_000:26_000]           # duplication across contigs
+    codes[2][10_000:13_000] = codes[2][100_000:103_000]         # duplication inside a contig
+    ref = [(f"c{i + 1}", acgt[c]) for i, c in enumerate(codes)]
+    mut = lambda c: acgt[synth.mutate(c, rng, 0.01, 0.001)]
+    p1 = mut(codes[0][5_000:150_000])
+    p2 = synth.revcomp_ascii(mut(codes[1][30_000:120_000]))
+    p3 = mut(codes[2][0:60_000]).copy()
+    p3[20_000:20_040] = ord("N")
+    p3[30_000:30_200] = np.frombuffer(bytes(p3[30_000:30_200]).lower(), dtype=np.uint8)
+    junk = acgt[rng.integers(0, 4, size=700, dtype=np.uint8)]
+    p4a, p4b = mut(codes[0][150_000:170_000]), mut(codes[0][170_700:199_000])
+    q1 = np.concatenate([p1, p2, p3])
+    q2 = np.concatenate([p4a, junk, p4b, synth.revcomp_ascii(mut(codes[2][120_000:199_000])), mut(codes[1][50_000:56_000])])
+    d = os.path.join(workdir, "rearr")
+    os.makedirs(d, exist_ok=True)
+    synth.write_fasta(os.path.join(d, "ref.fa"), ref)
+    synth.write_fasta(os.path.join(d, "qry.fa"), [("q1", q1), ("q2 some comment", q2)])
+    return d
+
+
+@pytest.mark.parametrize("prm", [dict(), dict(min_seed_len=10, sensitive=1, min_block_score=50)])
+def test_rearranged_all_seams(workdir, prm):
+    from conftest import build_index
+    from gsalign_b200 import bwaidx, capi, synth
+    d = make_rearranged(workdir)
+    build_index(os.path.join(d, "ref.fa"), os.path.join(d, "ref"))
+    tag = "sen" if prm else "def"
+    ref = run_reference(os.path.join(d, "ref"), os.path.join(d, "qry.fa"), os.path.join(d, f"ref_{tag}.pkl"), **prm)
+    a = capi.Aligner(0)
+    a.upload_index(bwaidx.load(os.path.join(d, "ref")))
+    a.lib.gsa_set_dump(a.ctx, 1)
+    cprm = dict(prm)
+    a.set_params(**cprm)
+    nb = 0
+    for (name, seq), rc in zip(synth.read_fasta(os.path.join(d, "qry.fa")), ref):
+        nb += check_contig(a, seq.tobytes(), rc)
+    assert nb >= 5
+    a.close()
+
+
+def test_dp_batch_vs_oracle(oracle):
+    """adversarial DP cases straight through the DP kernel (gsa_dp_batch) vs the oracle's ksw2 restatement"""
+    import random
+    from gsalign_b200 import capi
+    random.seed(3)
+    refs, qrys = [], []
+    for t in range(600):
+        m = random.choice([1, 2, 3, 7, 31, 32, 33, 64, 100, 129, 300]); n = max(1, m + random.randint(-5, 5))
+        a = "".join(random.choice("ACGT") for _ in range(m))
+        if t % 3 == 0:
+            b = "".join(random.choice("ACGT") for _ in range(n))           # unrelated
+        else:
+            b = "".join((random.choice("ACGTNn") if random.random() < 0.08 else ch) for ch in a)
+            if len(b) > 4 and t % 3 == 1:
+                c = random.randrange(len(b)); b = b[:c] + b[c + random.randint(1, 3):]
+            b = b or "A"
+        if t % 7 == 0:
+            a = a.lower()
+        refs.append(a.encode()); qrys.append(b.encode())
+    refs += [b"A" * 500, b"ACGT" * 300, b"A", b"AAAAAAAAAA"]
+    qrys += [b"A" * 480, b"ACGT" * 290 + b"TT", b"ACGTACGTAC", b"A"]
+    al = capi.Aligner(0)
+    res, ms = al.dp_batch(refs, qrys)
+    for a, b, (x, y) in zip(refs, qrys, res):
+        assert (x, y) == oracle.dp_align(a, b), (a, b)
+    al.close()

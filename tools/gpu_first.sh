@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests/test_gpu_seed.py -m gpu -x -q 2>&1 | tail -20
+python -m pytest tests -m gpu -x -q 2>&1 | tail -30
