@@ -49,12 +49,13 @@ class Alignment(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "seed_ms", "cluster_ms", "fill_ms", "d2h_ms", "host_ms")] + \
-               [(n, C.c_int64) for n in ("n_seeds", "n_dp", "dp_cells", "n_frags", "launches")]
+               [(n, C.c_int64) for n in ("n_seeds", "n_dp", "dp_cells", "n_frags", "launches")] + \
+               [(n, C.c_float) for n in ("k_seed_ms", "k_dp_ms", "total_ms")]
 
 
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
-           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch"]
+           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump"]
 
 
 def load_library() -> C.CDLL:
@@ -120,6 +121,12 @@ class Aligner:
         for k, val in kw.items():
             setattr(p, k, val)
         self._chk(self.lib.gsa_set_params(self.ctx, C.byref(p)))
+
+    def set_stream(self, cuda_stream: int):
+        self._chk(self.lib.gsa_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+
+    def set_dump(self, enable: bool):
+        self._chk(self.lib.gsa_set_dump(self.ctx, C.c_int(1 if enable else 0)))
 
     def contig_begin(self, seq):
         """seq: bytes or uint8 ndarray (host)."""

@@ -58,7 +58,7 @@ int gsa_create(int device, gsa_ctx **out)
 	memset(&ctx->tm, 0, sizeof(ctx->tm));
 	memset(&ctx->ix, 0, sizeof(ctx->ix));
 	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
-	for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+	for (int i = 0; i < 12; i++) cudaEventCreate(&ctx->ev[i]);
 	if (gsa_ensure_host(ctx, ctx->h_small, 1 << 20) != GSA_OK) { delete ctx; return GSA_ERR_NOMEM; }
 	*out = ctx;
 	return GSA_OK;
@@ -76,8 +76,8 @@ void gsa_destroy(gsa_ctx *ctx)
 	for (DevBuf &b : ctx->d_tmp) if (b.p) cudaFree(b.p);
 	HostBuf *hb[] = {&ctx->h_small, &ctx->h_stage, &ctx->h_frag, &ctx->h_aln1, &ctx->h_aln2, &ctx->h_blocks};
 	for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
-	for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	for (int i = 0; i < 12; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
 
@@ -88,6 +88,16 @@ int gsa_index_upload(gsa_ctx *ctx, const gsa_index_view *view)
 	if (!ctx) return GSA_ERR_ARG;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	return gsa_impl_index_upload(ctx, view);
+}
+
+int gsa_set_stream(gsa_ctx *ctx, void *cuda_stream)
+{
+	if (!ctx) return GSA_ERR_ARG;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+	ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false;
+	return GSA_OK;
 }
 
 int gsa_set_params(gsa_ctx *ctx, const gsa_params *p)
@@ -105,7 +115,7 @@ static int contig_reset(gsa_ctx *ctx, uint32_t len)
 	if (len >= 0x7FFFFF00u) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_contig_begin: contig longer than 2^31 (positions are int in the reference)");
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	ctx->qlen = len; ctx->have_contig = false; ctx->have_seeds = false; ctx->have_cluster = false;
-	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0;
+	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->dp_timed = false;
 	memset(&ctx->tm, 0, sizeof(ctx->tm));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_seq, (size_t)len + 64));
 	return GSA_OK;
@@ -189,6 +199,9 @@ int gsa_fill(gsa_ctx *ctx, gsa_alignment *out)
 	cudaEventElapsedTime(&ctx->tm.seed_ms, ctx->ev[2], ctx->ev[3]);
 	cudaEventElapsedTime(&ctx->tm.cluster_ms, ctx->ev[4], ctx->ev[5]);
 	cudaEventElapsedTime(&ctx->tm.fill_ms, ctx->ev[6], ctx->ev[7]);
+	cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[7]);
+	if (ctx->qlen > 0) cudaEventElapsedTime(&ctx->tm.k_seed_ms, ctx->ev[8], ctx->ev[9]);
+	if (ctx->dp_timed) cudaEventElapsedTime(&ctx->tm.k_dp_ms, ctx->ev[10], ctx->ev[11]);
 	return GSA_OK;
 }
 

@@ -307,7 +307,10 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 		CUDA_TRY(ctx, cudaMemcpyAsync(hp.data(), d_prob, (size_t)ndp * sizeof(DpProblem), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		for (const DpProblem &p : hp) ctx->tm.dp_cells += (int64_t)p.m * p.n;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
 		GSA_TRY(run_dp_binned(ctx, hp, d_prob, flags, a1, a2, nullptr, frag, fblk, bsum));
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
+		ctx->dp_timed = true;
 	}
 	// ---- results to pinned host memory ---------------------------------------------------------------------
 	GSA_TRY(gsa_ensure_host(ctx, ctx->h_frag, (size_t)nfr * sizeof(gsa_frag)));

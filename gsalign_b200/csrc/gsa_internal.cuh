@@ -65,7 +65,8 @@ struct Piece {
 struct gsa_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[8] = {};
+	cudaEvent_t ev[12] = {};        // 0/1 h2d, 2/3 seed, 4/5 cluster, 6/7 fill, 8/9 k_seed, 10/11 k_dp
+	bool own_stream = true; bool dp_timed = false;
 	std::string err;
 	gsa_params prm;
 	gsa_timing tm;

@@ -64,67 +64,148 @@ struct SeedOut {
 	unsigned long long capacity;
 };
 
+struct SeedArgs {
+	const uint32_t *qpk, *qinv;
+	uint32_t qlen, nchunks;
+	int min_seed_len, sensitive;
+};
+
 __device__ __forceinline__ void emit_seed(const SeedOut &o, unsigned long long slot, int32_t q, int64_t r, int32_t len)
 {
 	if (slot < o.capacity) { o.q[slot] = q; o.r[slot] = r; o.len[slot] = len; }
 }
 
-__global__ void __launch_bounds__(64)
-k_seed(DevIndex ix, const uint32_t *__restrict__ qpk, const uint32_t *__restrict__ qinv, uint32_t qlen, uint32_t nchunks,
-       int min_seed_len, int sensitive, SeedOut out)
+// One search (BWT_Search semantics) from `start` inside a chunk ending at `stop`; the first K bases are known to be
+// ACGT and inside the chunk.  Returns the match length; lo/size = row interval of revcomp(match); rpos = start of the
+// match in T when it is unique.
+__device__ __forceinline__ int seed_search(const DevIndex &ix, const uint32_t *__restrict__ qpk, const uint32_t *__restrict__ qinv,
+                                           uint32_t start, uint32_t stop, int K, uint32_t &lo, uint32_t &size, uint32_t &rpos)
 {
-	uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
-	if (chunk >= nchunks) return;
+	// 1. prefix table
+	uint32_t code = gsa_pk_window(qpk, start) >> (32 - 2 * K);
+	uint2 iv = __ldg(ix.ktab + code);
+	lo = iv.x; size = iv.y;
+	if (size == 0) return 0;
+	uint32_t pos = start + K;
+	// 2. backward search while the interval holds several rows
+	while (size > 1 && pos < stop) {
+		if ((__ldg(qinv + (pos >> 5)) >> (~pos & 31)) & 1) break;
+		int c = 3 - gsa_pk_base(qpk, pos);
+		uint32_t o1, o2;
+		gsa_occ2(ix, c, lo - 1, lo + size - 1, o1, o2);
+		if (o2 == o1) break;
+		lo = ix.L2[c] + o1 + 1; size = o2 - o1; pos++;
+	}
+	// 3/4. unique: locate once, then compare the 2-bit query against the 2-bit text
+	if (size == 1) {
+		uint32_t m = pos - start;
+		uint32_t p = ix.n - __ldg(ix.sa + lo) - m;  // start of the match in T
+		rpos = p;
+		uint32_t tpos = p + m;
+		while (pos < stop && tpos < ix.n) {
+			uint32_t x = gsa_pk_window(qpk, pos) ^ gsa_pk_window(ix.txt, tpos);
+			uint32_t iw = gsa_bit_window(qinv, pos);
+			int ext = min(min(__clz(x) >> 1, __clz(iw)), 16);   // first mismatch / first non-ACGT
+			uint32_t lim = min(stop - pos, ix.n - tpos);
+			if ((uint32_t)ext >= lim) { pos += lim; break; }
+			pos += ext; tpos += ext;
+			if (ext < 16) break;
+		}
+	}
+	return (int)(pos - start);
+}
+
+#define SEED_SUB 313            // ceil(10000 / 32): one lane per sub-chunk
+#define SEED_VIS_WORDS 10       // 313 bits
+#define SEED_WARPS 4
+
+__device__ __forceinline__ void vis_mark(uint32_t *vis, uint32_t a, uint32_t b)
+{ // set bits [a, b) (LSB-first inside a word)
+	for (uint32_t w = a >> 5; w <= ((b - 1) >> 5) && a < b; w++) {
+		uint32_t lo = max(a, w << 5) & 31, hi = min(b, (w + 1) << 5) - (w << 5); // bits [lo, hi) of word w
+		vis[w] |= (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1)) & ~((1u << lo) - 1);
+	}
+}
+
+// Walks the chunk's search chain from `start` until it leaves [.., limit); returns the first chain start >= limit.
+//   MODE 0: speculative pass -- records every visited start of [base, limit) in vis
+//   MODE 1: repair pass      -- stops as soon as it lands on a start the speculative pass visited (returns UINT_MAX then)
+//   MODE 2: emitting pass    -- writes the seeds
+// Misses advance by one position, so a run of guaranteed misses (k-mer cut by a non-ACGT base or by the chunk end)
+// is a run of consecutive visited starts.
+template <int MODE>
+__device__ __forceinline__ uint32_t seed_walk(const DevIndex &ix, const SeedArgs &A, uint32_t start, uint32_t base, uint32_t limit, uint32_t stop,
+                                              uint32_t *vis, const SeedOut &out)
+{
 	const int K = ix.ktab_k;
-	uint32_t start = chunk * GSA_SEED_CHUNK, stop = start + GSA_SEED_CHUNK;
-	if (stop > qlen) stop = qlen;
-	while (start + K <= stop) { // a search with fewer than K (<= MinSeedLength) bases left is a guaranteed miss
-		// --- 1. prefix table --------------------------------------------------------------------------
-		uint32_t invw = gsa_bit_window(qinv, start);
-		int bad = __clz(invw);                 // offset of the first non-ACGT base at or after start
-		if (bad < K) { start += bad + 1; continue; } // every search starting in [start, start+bad] misses
-		uint32_t code = gsa_pk_window(qpk, start) >> (32 - 2 * K);
-		uint2 iv = __ldg(ix.ktab + code);
-		uint32_t lo = iv.x, size = iv.y;
-		if (size == 0) { start++; continue; }
-		uint32_t pos = start + K;
-		// --- 2. backward search while the interval holds several rows ---------------------------------
-		while (size > 1 && pos < stop) {
-			if ((__ldg(qinv + (pos >> 5)) >> (~pos & 31)) & 1) break;
-			int c = 3 - gsa_pk_base(qpk, pos);
-			uint32_t o1, o2;
-			gsa_occ2(ix, c, lo - 1, lo + size - 1, o1, o2);
-			if (o2 == o1) break;
-			lo = ix.L2[c] + o1 + 1; size = o2 - o1; pos++;
+	while (start < limit) {
+		if (MODE == 1 && ((vis[(start - base) >> 5] >> ((start - base) & 31)) & 1)) return 0xFFFFFFFFu;
+		if (start + K > stop) { // fewer than K (<= MinSeedLength) bases left in the chunk: misses all the way
+			if (MODE == 0) vis_mark(vis, start - base, limit - base);
+			return limit;
 		}
-		// --- 3/4. unique: locate once, then compare against the text -----------------------------------
-		int64_t rpos = -1;
-		if (size == 1) {
-			uint32_t m = pos - start;
-			uint32_t p = ix.n - __ldg(ix.sa + lo) - m;  // start of the match in T
-			rpos = p;
-			uint32_t tpos = p + m;
-			while (pos < stop && tpos < ix.n) {
-				uint32_t x = gsa_pk_window(qpk, pos) ^ gsa_pk_window(ix.txt, tpos);
-				uint32_t iw = gsa_bit_window(qinv, pos);
-				int ext = min(__clz(x) >> 1, __clz(iw));   // first mismatch / first non-ACGT
-				ext = min(ext, 16);
-				uint32_t lim = min(stop - pos, ix.n - tpos);
-				if ((uint32_t)ext >= lim) { pos += lim; break; }
-				pos += ext; tpos += ext;
-				if (ext < 16) break;
+		int bad = __clz(gsa_bit_window(A.qinv, start)); // offset of the first non-ACGT base at or after start
+		if (bad < K) { // every search starting in [start, start+bad] misses
+			uint32_t ns = min(start + bad + 1, limit);
+			if (MODE == 0) vis_mark(vis, start - base, ns - base);
+			if (MODE == 1) { // any visited start inside the run merges the chains
+				for (uint32_t s2 = start + 1; s2 < ns; s2++) if ((vis[(s2 - base) >> 5] >> ((s2 - base) & 31)) & 1) return 0xFFFFFFFFu;
 			}
+			start = ns;
+			continue;
 		}
-		int len = (int)(pos - start);
-		if (len >= min_seed_len && size <= GSA_MAX_SEED_FREQ) {
-			unsigned long long slot = atomicAdd(out.count, (unsigned long long)size);
-			if (size == 1) emit_seed(out, slot, (int32_t)start, rpos, len);
-			else
-				for (uint32_t i = 0; i < size; i++)
-					emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - __ldg(ix.sa + lo + i) - (uint32_t)len), len);
-			start += sensitive ? 5 : (uint32_t)len + 1;
+		if (MODE == 0) vis[(start - base) >> 5] |= 1u << ((start - base) & 31);
+		uint32_t lo, size, rpos = 0;
+		int len = seed_search(ix, A.qpk, A.qinv, start, stop, K, lo, size, rpos);
+		if (len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ) {
+			if (MODE == 2) {
+				unsigned long long slot = atomicAdd(out.count, (unsigned long long)size);
+				if (size == 1) emit_seed(out, slot, (int32_t)start, (int64_t)rpos, len);
+				else
+					for (uint32_t i = 0; i < size; i++)
+						emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - __ldg(ix.sa + lo + i) - (uint32_t)len), len);
+			}
+			start += A.sensitive ? 5 : (uint32_t)len + 1;
 		} else start++;
 	}
+	return start;
+}
+
+// One warp per 10 kb chunk, one lane per 313-bp sub-chunk.  The chain of search starts inside a chunk is serial
+// (reference src/GSAlign.cpp:70-93), but chains started anywhere re-synchronise at the next mismatch, so:
+//   pass A  every lane walks its sub-chunk speculatively from the sub-chunk's first base and records the visited starts;
+//   resolve lane by lane, the true entry point of sub-chunk j (= exit of the true chain from sub-chunk j-1) is looked
+//           up in lane j's visited set; if it is not there the lane repairs by walking from the true entry until it
+//           merges with its speculative chain (rare: needs a spurious seed spanning the entry);
+//   pass B  every lane re-walks from its true entry and emits.  Results are exactly the serial chain's.
+__global__ void __launch_bounds__(32 * SEED_WARPS)
+k_seed(DevIndex ix, SeedArgs A, SeedOut out)
+{
+	__shared__ uint32_t s_vis[SEED_WARPS][32][SEED_VIS_WORDS];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t chunk = blockIdx.x * SEED_WARPS + wib;
+	if (chunk >= A.nchunks) return;
+	uint32_t cs = chunk * GSA_SEED_CHUNK, stop = min(cs + GSA_SEED_CHUNK, A.qlen);
+	uint32_t base = min(cs + lane * SEED_SUB, stop), limit = min(base + SEED_SUB, stop);
+	uint32_t *vis = s_vis[wib][lane];
+#pragma unroll
+	for (int w = 0; w < SEED_VIS_WORDS; w++) vis[w] = 0;
+	uint32_t spec_exit = seed_walk<0>(ix, A, base, base, limit, stop, vis, out);
+	__syncwarp();
+	// resolve the true entry of every sub-chunk
+	uint32_t entry = cs, my_entry = cs;
+	for (int j = 0; j < 32; j++) {
+		uint32_t ex = entry;
+		if (lane == j) {
+			my_entry = entry;
+			if (entry < limit) {
+				if ((vis[(entry - base) >> 5] >> ((entry - base) & 31)) & 1) ex = spec_exit;
+				else { ex = seed_walk<1>(ix, A, entry, base, limit, stop, vis, out); if (ex == 0xFFFFFFFFu) ex = spec_exit; }
+			}
+		}
+		entry = __shfl_sync(0xffffffffu, ex, j);
+	}
+	if (my_entry < limit) seed_walk<2>(ix, A, my_entry, base, limit, stop, vis, out);
 }
 
 // sort key: ((PosDiff + 2^31) << 31) | qPos -- a strict total order on seeds, identical to CompByPosDiff
@@ -165,9 +246,12 @@ int gsa_impl_seed(gsa_ctx *ctx)
 		SeedOut so; so.q = (int32_t *)ctx->d_tmp[0].p; so.r = (int64_t *)ctx->d_tmp[1].p; so.len = (int32_t *)ctx->d_tmp[2].p;
 		so.count = d_count; so.capacity = cap;
 		if (nchunks > 0) {
-			k_seed<<<gsa_grid(nchunks, 64), 64, 0, ctx->stream>>>(ctx->ix, (const uint32_t *)ctx->d_qpk.p, (const uint32_t *)ctx->d_qinv.p,
-			                                                     ctx->qlen, nchunks, ctx->prm.min_seed_len, ctx->prm.sensitive, so);
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
+			SeedArgs sa; sa.qpk = (const uint32_t *)ctx->d_qpk.p; sa.qinv = (const uint32_t *)ctx->d_qinv.p; sa.qlen = ctx->qlen; sa.nchunks = nchunks;
+			sa.min_seed_len = ctx->prm.min_seed_len; sa.sensitive = ctx->prm.sensitive;
+			k_seed<<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so);
 			KERNEL_CHECK(ctx);
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
 		}
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small.p, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

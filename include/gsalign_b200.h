@@ -98,6 +98,9 @@ typedef struct {
 	float h2d_ms, seed_ms, cluster_ms, fill_ms, d2h_ms, host_ms;
 	int64_t n_seeds, n_dp, dp_cells, n_frags;
 	int64_t launches;          /* kernels launched by this library for the contig */
+	float k_seed_ms;           /* the fm_seed kernel alone (K1's dominant launch) */
+	float k_dp_ms;             /* the DP kernels alone (K3) */
+	float total_ms;            /* first to last event of the contig on the context's stream */
 } gsa_timing;
 
 /* --- lifecycle ------------------------------------------------------------------------------- */
@@ -110,6 +113,8 @@ const char *gsa_last_error(const gsa_ctx *ctx);
  * k-mer prefix table).  The view may be freed after the call returns. */
 int gsa_index_upload(gsa_ctx *ctx, const gsa_index_view *view);
 int gsa_set_params(gsa_ctx *ctx, const gsa_params *prm);
+/* run on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g. to time with the caller's events */
+int gsa_set_stream(gsa_ctx *ctx, void *cuda_stream);
 void gsa_default_params(gsa_params *prm);
 
 /* --- per query contig (the body of the loop at src/GSAlign.cpp:483-548) ----------------------- */
