@@ -1,0 +1,77 @@
+// host.h -- host side of bin/GSAlign: index/FASTA I/O and the MAF / ALN / VCF emitters.
+// Mirrors the reference's CLI surface (src/main.cpp), loaders (src/bwt_index.cpp) and emitters
+// (src/tools.cpp, src/SeqVariant.cpp) so that the files it writes are byte-identical; all of the
+// seed -> cluster -> fill work goes through the C ABI in include/gsalign_b200.h.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../../include/gsalign_b200.h"
+
+struct HostIndex {                 // bwaidx_t as loaded by bwa_idx_load (reference src/bwt_index.cpp:147-159)
+	std::vector<uint32_t> bwt;
+	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0;
+	std::vector<uint64_t> sa;
+	int sa_intv = 32;
+	std::vector<uint8_t> pac;
+	int64_t l_pac = 0;
+	std::vector<std::string> names; // ChromosomeVec[i].name
+	std::vector<int64_t> offset;    // FowardLocation
+	std::vector<int32_t> len;
+	// ChrLocMap (reference src/bwt_index.cpp:247-252): inclusive contig ends on both strands, sorted
+	std::vector<std::pair<int64_t, int> > chr_loc;
+	bool load(const std::string &prefix, std::string &err);
+	void view(gsa_index_view *v) const;
+	int64_t genome() const { return l_pac; }
+	int64_t reverse_location(int i) const { return 2 * l_pac - (offset[i] + len[i]); }
+	// RefSequence[pos] (reference src/bwt_index.cpp:193-212): forward base or its complement on the mirrored half
+	char text(int64_t pos) const
+	{
+		int64_t f = pos < l_pac ? pos : 2 * l_pac - 1 - pos;
+		int b = pac[(size_t)(f >> 2)] >> ((~f & 3) << 1) & 3;
+		return "ACGT"[pos < l_pac ? b : 3 - b];
+	}
+	// ChrLocMap.lower_bound(pos)
+	const std::pair<int64_t, int> &loc(int64_t pos) const;
+};
+
+struct QueryChr { std::string name, seq; };  // QueryChr_t, reference src/structure.h:134-138
+
+bool check_input_file(const char *path);                                   // CheckInputFile, src/main.cpp:49-64
+bool load_query_file(const char *path, std::vector<QueryChr> &out);        // LoadQueryFile,  src/main.cpp:82-114
+std::string trim_chromosome_name(std::string name);                        // TrimChromosomeName, src/main.cpp:35-47
+
+struct Coordinate { bool bDir; int gPos; int ChromosomeIdx; };            // Coordinate_t
+Coordinate gen_coordinate(const HostIndex &ix, int64_t rPos);              // GenCoordinateInfo, src/tools.cpp:120-140
+
+struct Variant { int pos, chr_idx, query_idx; std::string ref_frag, alt_frag; int type; }; // Variant_t
+
+struct Options {                   // the globals of src/main.cpp:10-12,203-215
+	int threads = 8, out_format = 1, n_gpus = 1;
+	bool sensitive = false, show_plot = false, debug = false, vcf = true, allow_dup = true, one_on_one = false;
+	int min_seed_len = 15, min_block_score = 200, min_aln_len = 200, min_idy = 70, max_indel = 25;
+	const char *ref_fa = nullptr, *index_prefix = nullptr, *query = nullptr, *out_prefix = nullptr, *gnuplot = nullptr;
+	std::string maf, aln, vcf_name;
+};
+
+// One contig's result, detached from the library's pinned buffers (needed when several GPUs run ahead of the emitter)
+struct ContigResult {
+	std::vector<gsa_block> blocks;
+	std::vector<gsa_frag> frags;
+	std::string aln1, aln2;
+	void assign(const gsa_alignment &a);
+};
+
+struct EmitState {                 // running totals of GenomeComparison (src/GSAlign.cpp:14-15)
+	int64_t total_aln_len = 0, total_matches = 0, local_aln_num = 0, dup_num = 0;
+	int iSNV = 0, iInsertion = 0, iDeletion = 0;
+	std::vector<Variant> variants;
+};
+
+// OutputMAF / OutputAlignment (src/tools.cpp:149-286); they trim a block that runs past its contig end
+// (iExtension) by MUTATING the result, exactly like the reference does before VariantIdentification runs
+void output_maf(const Options &o, const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, ContigResult &r);
+void output_aln(const Options &o, const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, ContigResult &r);
+void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, const ContigResult &r, EmitState &st); // src/SeqVariant.cpp:12-119
+void output_variants(const Options &o, const HostIndex &ix, EmitState &st);                                                      // src/SeqVariant.cpp:121-143

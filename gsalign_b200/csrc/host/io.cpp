@@ -1,0 +1,141 @@
+// io.cpp -- BWA-format index reader and query FASTA reader of bin/GSAlign.
+#include <string.h>
+#include <algorithm>
+#include <fstream>
+#include "host.h"
+
+static bool read_file(const std::string &path, std::vector<uint8_t> &out)
+{
+	FILE *fp = fopen(path.c_str(), "rb");
+	if (!fp) return false;
+	fseek(fp, 0, SEEK_END);
+	long n = ftell(fp);
+	fseek(fp, 0, SEEK_SET);
+	out.resize((size_t)n);
+	size_t got = n > 0 ? fread(out.data(), 1, (size_t)n, fp) : 0;
+	fclose(fp);
+	return got == (size_t)n;
+}
+
+// bwt_restore_bwt / bwt_restore_sa / bns_restore_core (reference src/bwt_index.cpp:15-121)
+bool HostIndex::load(const std::string &prefix, std::string &err)
+{
+	std::vector<uint8_t> raw;
+	if (!read_file(prefix + ".bwt", raw) || raw.size() < 40) { err = "cannot read " + prefix + ".bwt"; return false; }
+	const uint64_t *h = (const uint64_t *)raw.data();
+	primary = h[0]; L2[0] = 0; for (int i = 1; i < 5; i++) L2[i] = h[i];
+	seq_len = L2[4];
+	bwt.resize((raw.size() - 40) / 4);
+	memcpy(bwt.data(), raw.data() + 40, bwt.size() * 4);
+	if (!read_file(prefix + ".sa", raw) || raw.size() < 56) { err = "cannot read " + prefix + ".sa"; return false; }
+	h = (const uint64_t *)raw.data();
+	sa_intv = (int)h[5];                       // hazard H13: the reference reads this u64 into an int
+	if (sa_intv <= 0) { err = "bad sa_intv in " + prefix + ".sa"; return false; }
+	uint64_t n_sa = (seq_len + (uint64_t)sa_intv) / (uint64_t)sa_intv;
+	if (raw.size() < 56 + (n_sa - 1) * 8) { err = prefix + ".sa is truncated"; return false; }
+	sa.resize(n_sa);
+	sa[0] = (uint64_t)-1;
+	memcpy(sa.data() + 1, raw.data() + 56, (n_sa - 1) * 8);
+	FILE *fp = fopen((prefix + ".ann").c_str(), "r");
+	if (!fp) { err = "cannot read " + prefix + ".ann"; return false; }
+	long long xx; int n_seqs; unsigned seed;
+	if (fscanf(fp, "%lld%d%u", &xx, &n_seqs, &seed) != 3) { fclose(fp); err = "bad .ann header"; return false; }
+	l_pac = xx;
+	names.clear(); offset.clear(); len.clear();
+	char str[10240];
+	for (int i = 0; i < n_seqs; i++) {
+		unsigned gi; int c, l, namb;
+		if (fscanf(fp, "%u%10239s", &gi, str) != 2) { fclose(fp); err = "bad .ann record"; return false; }
+		names.push_back(str);
+		while ((c = fgetc(fp)) != '\n' && c != EOF) {}
+		if (fscanf(fp, "%lld%d%d", &xx, &l, &namb) != 3) { fclose(fp); err = "bad .ann record"; return false; }
+		offset.push_back(xx); len.push_back(l);
+	}
+	fclose(fp);
+	if (!read_file(prefix + ".pac", raw) || (int64_t)raw.size() < l_pac / 4 + 1) { err = "cannot read " + prefix + ".pac"; return false; }
+	pac.assign(raw.begin(), raw.begin() + (size_t)(l_pac / 4 + 1));
+	// RestoreReferenceInfo (reference src/bwt_index.cpp:229-253): locations are cumulative lengths
+	chr_loc.clear();
+	int64_t total = 0;
+	for (int i = 0; i < n_seqs; i++) {
+		offset[i] = total; total += len[i];
+		chr_loc.push_back(std::make_pair(offset[i] + len[i] - 1, i));
+		chr_loc.push_back(std::make_pair(2 * l_pac - total + len[i] - 1, i));
+	}
+	std::sort(chr_loc.begin(), chr_loc.end());
+	if (seq_len != 2 * (uint64_t)l_pac) { err = "index inconsistent: seq_len != 2*l_pac"; return false; }
+	return true;
+}
+
+void HostIndex::view(gsa_index_view *v) const
+{
+	v->bwt = bwt.data(); v->bwt_size = bwt.size(); v->primary = primary;
+	for (int i = 0; i < 5; i++) v->L2[i] = L2[i];
+	v->seq_len = seq_len; v->sa = sa.data(); v->n_sa = sa.size(); v->sa_intv = sa_intv;
+	v->pac = pac.data(); v->l_pac = l_pac; v->n_contigs = (int32_t)names.size();
+	v->contig_off = offset.data(); v->contig_len = len.data();
+}
+
+const std::pair<int64_t, int> &HostIndex::loc(int64_t pos) const
+{
+	size_t lo = 0, hi = chr_loc.size();
+	while (lo < hi) { size_t m = (lo + hi) / 2; if (chr_loc[m].first < pos) lo = m + 1; else hi = m; }
+	return chr_loc[lo < chr_loc.size() ? lo : chr_loc.size() - 1];
+}
+
+Coordinate gen_coordinate(const HostIndex &ix, int64_t rPos)
+{
+	Coordinate c;
+	const std::pair<int64_t, int> &it = ix.loc(rPos);
+	c.ChromosomeIdx = it.second;
+	if (rPos < ix.genome()) { c.bDir = true; c.gPos = (int)(rPos + 1 - ix.offset[it.second]); }
+	else { c.bDir = false; c.gPos = (int)(it.first - rPos + 1); }
+	return c;
+}
+
+std::string trim_chromosome_name(std::string name)
+{
+	size_t i, n = name.length();
+	for (i = 0; i < n; i++) {
+		if (name[i] == '|') name[i] = '-';
+		else if (name[i] == ' ' || name[i] == '#' || name[i] == ':' || name[i] == '=' || name[i] == '\t') break;
+	}
+	return name.substr(0, i);
+}
+
+bool check_input_file(const char *path)
+{
+	std::ifstream f(path);
+	if (!f.is_open()) return false;
+	std::string s;
+	std::getline(f, s);
+	return !s.empty() && s[0] == '>';
+}
+
+bool load_query_file(const char *path, std::vector<QueryChr> &out)
+{
+	std::ifstream f(path);
+	if (!f.is_open()) return false;
+	std::string s;
+	int idx = -1;
+	while (!f.eof()) {
+		std::getline(f, s);
+		if (s.empty()) continue;
+		if (s[0] == '>') {
+			out.push_back(QueryChr()); idx++;
+			out[idx].name = trim_chromosome_name(s.substr(1));
+		} else {
+			if (s[s.size() - 1] == '\r') s.resize(s.size() - 1);   // CheckQuerySeq, src/main.cpp:66-80
+			for (size_t i = 0; i < s.size(); i++)
+				if (!isalpha((unsigned char)s[i])) {
+					printf("%s\n", s.c_str());
+					fprintf(stderr, "The query sequence contains non-alphabet characters!\n");
+					return false;
+				}
+			if (idx < 0) return false;
+			out[idx].seq.append(s);
+		}
+	}
+	fprintf(stderr, "\tLoad the query sequences (%d %s)\n", (int)out.size(), out.size() > 1 ? "chromosomes" : "chromosome");
+	return !out.empty();
+}

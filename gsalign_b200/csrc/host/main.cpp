@@ -1,0 +1,200 @@
+// main.cpp -- bin/GSAlign: the reference's command line (src/main.cpp:14-33,198-334) on top of the
+// B200 seed -> cluster -> fill path.  Same flags, same defaults, same files, exit code 0 always.
+// The per-contig loop of GenomeComparison (src/GSAlign.cpp:473-552) becomes: gsa_align_contig() on a GPU,
+// then the emitters on the host.  Query contigs are independent, so with -gpus N they are dealt to N
+// GPUs (longest first); records are emitted in contig order whatever GPU produced them.
+#include <ctype.h>
+#include <string.h>
+#include <time.h>
+#include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include "host.h"
+
+extern "C" int gsa_build_index_files(const char *fasta, const char *prefix, int device); // index_build.cu
+
+static void usage(const char *prog, const Options &o)
+{
+	fprintf(stderr, "\n");
+	fprintf(stderr, "GenAlign v%s (B200 build)\n", "1.0.22");
+	fprintf(stderr, "Usage: %s [-i IndexFile Prefix / -r Reference file] -q QueryFile[Fasta]\n\n", prog);
+	fprintf(stderr, "Options: -t     INT     number of threads [%d]\n", o.threads);
+	fprintf(stderr, "         -o     STR     Set the prefix of the output files [output]\n");
+	fprintf(stderr, "         -fmt   INT     Set the output format 1:maf, 2:aln [%d]\n", o.out_format);
+	fprintf(stderr, "         -idy   INT     Set the minimal sequence identity (0-100) of a local alignment [%d]\n", o.min_idy);
+	fprintf(stderr, "         -slen  INT     Set the minimal seed length [%d]\n", o.min_seed_len);
+	fprintf(stderr, "         -alen  INT     Set the minimal alignment length [%d]\n", o.min_aln_len);
+	fprintf(stderr, "         -ind   INT     Set the maximal indel size [%d]\n", o.max_indel);
+	fprintf(stderr, "         -clr   INT     Set the minimal cluster size [%d]\n", o.min_block_score);
+	fprintf(stderr, "         -unique        Output unique alignment only [false]\n");
+	fprintf(stderr, "         -sen           Sensitive mode [False]\n");
+	fprintf(stderr, "         -dp            Output Dot-plots\n");
+	fprintf(stderr, "         -one           set one on one aligment mode[false]\n");
+	fprintf(stderr, "         -gp    STR     Specify the path of gnuplot\n");
+	fprintf(stderr, "         -gpus  INT     number of B200s to spread the query contigs over [1]\n");
+	fprintf(stderr, "\n");
+}
+
+static bool check_output_prefix(const char *p)
+{ // CheckOutputPrefix, src/main.cpp:116-138
+	if (strcmp(p, "/dev/null") == 0) return true;
+	for (size_t i = 0, n = strlen(p); i < n; i++) {
+		int c = (int)p[i];
+		if (!isprint((unsigned char)p[i]) || (c >= 32 && c <= 44) || (c >= 58 && c <= 64) || (c >= 123 && c <= 127)) {
+			fprintf(stderr, "FatalError: Please specify a valid prefix name\n");
+			return false;
+		}
+	}
+	return true;
+}
+
+static bool index_files_present(const std::string &prefix)
+{ // CheckBWAIndexFiles, src/GetData.cpp:8-24 (.bwt/.sa are not checked there either)
+	const char *ext[] = {".ann", ".amb", ".pac"};
+	for (const char *e : ext) { FILE *f = fopen((prefix + e).c_str(), "r"); if (!f) return false; fclose(f); }
+	return true;
+}
+
+struct Worker {
+	gsa_ctx *ctx = nullptr;
+	std::thread th;
+};
+
+int main(int argc, char *argv[])
+{
+	Options o;
+	if (argc == 1 || strcmp(argv[1], "-h") == 0) { usage(argv[0], o); return 0; }
+	if (strcmp(argv[1], "update") == 0) { fprintf(stderr, "self-update is not supported by this build\n"); return 0; }
+	if (strcmp(argv[1], "index") == 0) {
+		if (argc == 4) { if (gsa_build_index_files(argv[2], argv[3], 0) != 0) fprintf(stderr, "index construction failed\n"); }
+		else fprintf(stderr, "usage: %s index ref.fa prefix\n", argv[0]);
+		return 0;
+	}
+	for (int i = 1; i < argc; i++) {
+		std::string p = argv[i];
+		if (p == "-i") o.index_prefix = argv[++i];
+		else if (p == "-r" && i + 1 < argc) o.ref_fa = argv[++i];
+		else if (p == "-q" && i + 1 < argc) o.query = argv[++i];
+		else if (p == "-t" && i + 1 < argc) { if ((o.threads = atoi(argv[++i])) < 0) { fprintf(stderr, "Warning! Thread number should be greater than 0!\n"); o.threads = 16; } }
+		else if (p == "-slen" && i + 1 < argc) { o.min_seed_len = atoi(argv[++i]); if (o.min_seed_len < 10 || o.min_seed_len > 30) { fprintf(stderr, "Warning! minimal seed length is between 10~20!\n"); return 0; } }
+		else if (p == "-ind" && i + 1 < argc) { o.max_indel = atoi(argv[++i]); if (o.max_indel < 10 || o.max_indel > 100) { fprintf(stderr, "Warning! maximal indel size is between 10~100!\n"); return 0; } }
+		else if (p == "-sen" || p == "-sensitive") { o.sensitive = true; o.min_aln_len = 200; o.min_block_score = 50; }
+		else if (p == "-unique") o.allow_dup = false;
+		else if (p == "-no_vcf") o.vcf = false;
+		else if (p == "-one") o.one_on_one = true;
+		else if (p == "-idy" && i + 1 < argc) o.min_idy = atoi(argv[++i]);
+		else if (p == "-alen" && i + 1 < argc) o.min_aln_len = atoi(argv[++i]);
+		else if (p == "-clr" && i + 1 < argc) o.min_block_score = atoi(argv[++i]);
+		else if (p == "-dp") o.show_plot = true;
+		else if (p == "-gp" && i + 1 < argc) o.gnuplot = argv[++i];
+		else if (p == "-fmt" && i + 1 < argc) o.out_format = atoi(argv[++i]);
+		else if (p == "-o") o.out_prefix = argv[++i];
+		else if (p == "-d" || p == "-debug") o.debug = true;
+		else if (p == "-obr") ++i;
+		else if (p == "-gpus" && i + 1 < argc) o.n_gpus = std::max(1, atoi(argv[++i]));
+		else fprintf(stderr, "Warning! Unknow parameter: %s\n", argv[i]);
+	}
+	if ((!o.index_prefix && !o.ref_fa) || !o.query) { usage(argv[0], o); return 0; }
+	if (!o.out_prefix) o.out_prefix = "output";
+	else if (!check_output_prefix(o.out_prefix)) return 0;
+
+	time_t t_start = time(NULL);
+	fprintf(stderr, "Step1. Load the two genome sequences...\n");
+	std::vector<QueryChr> query;
+	if (!check_input_file(o.query) || !load_query_file(o.query, query)) { fprintf(stderr, "Please check the query file: %s\n", o.query); return 0; }
+
+	HostIndex ix;
+	std::string err, prefix;
+	if (o.index_prefix && index_files_present(o.index_prefix)) prefix = o.index_prefix;
+	else if (o.ref_fa && check_input_file(o.ref_fa)) {
+		prefix = o.ref_fa;
+		size_t p = prefix.find_last_of('.');
+		if (p != std::string::npos && p > 0) prefix.resize(p);
+		if (gsa_build_index_files(o.ref_fa, prefix.c_str(), 0) != 0) { fprintf(stderr, "\n\nError! Please check your input!\n"); return 0; }
+	} else { fprintf(stderr, "Please specify a valid reference genome\n"); return 0; }
+	if (!ix.load(prefix, err)) { fprintf(stderr, "\n\nError! Please check your input! (%s)\n", err.c_str()); return 0; }
+	fprintf(stderr, "\tLoad the reference sequences (%d %s)\n", (int)ix.names.size(), ix.names.size() > 1 ? "chromosomes" : "chromosome");
+	if (o.sensitive) o.min_seed_len = 10; // src/main.cpp:323
+	if (o.show_plot) fprintf(stderr, "Warning! dot-plots need gnuplot and are not produced by this build\n");
+	std::string op = o.out_prefix;
+	if (o.out_format == 1) o.maf = op + ".maf";
+	if (o.out_format == 2) o.aln = op + ".aln";
+	o.vcf_name = op + ".vcf";
+
+	// ---- one context per GPU, index replicated in each GPU's HBM ------------------------------------------------
+	gsa_params prm; gsa_default_params(&prm);
+	prm.min_seed_len = o.min_seed_len; prm.sensitive = o.sensitive; prm.max_indel = o.max_indel; prm.min_block_score = o.min_block_score;
+	prm.min_aln_len = o.min_aln_len; prm.min_idy = o.min_idy; prm.one_on_one = o.one_on_one;
+	gsa_index_view view; ix.view(&view);
+	int ngpu = std::min<int>(o.n_gpus, (int)query.size());
+	std::vector<gsa_ctx *> ctx((size_t)ngpu, nullptr);
+	for (int g = 0; g < ngpu; g++) {
+		if (gsa_create(g, &ctx[g]) != 0) { fprintf(stderr, "FatalError: cannot open CUDA device %d (this build has no CPU path)\n", g); return 0; }
+		if (gsa_set_params(ctx[g], &prm) != 0 || gsa_index_upload(ctx[g], &view) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g])); return 0; }
+	}
+
+	// ---- GenomeComparison ------------------------------------------------------------------------------------------------
+	fprintf(stderr, "Step2. Sequence analysis for all query chromosomes\n");
+	int nq = (int)query.size();
+	std::vector<ContigResult> results((size_t)nq);
+	std::vector<int> done((size_t)nq, 0);
+	std::mutex mu; std::condition_variable cv;
+	// longest-processing-time dealing of contigs to GPUs
+	std::vector<int> order((size_t)nq); for (int i = 0; i < nq; i++) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return query[a].seq.size() > query[b].seq.size(); });
+	std::vector<std::vector<int> > work((size_t)ngpu); std::vector<size_t> load((size_t)ngpu, 0);
+	for (int qi : order) { int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); work[g].push_back(qi); load[g] += query[qi].seq.size(); }
+	for (auto &w : work) std::sort(w.begin(), w.end()); // each GPU walks its share in contig order so that the emitter is never starved
+	bool failed = false;
+	auto run_gpu = [&](int g) {
+		for (int qi : work[g]) {
+			gsa_alignment al;
+			int rc = gsa_align_contig(ctx[g], query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al);
+			std::unique_lock<std::mutex> lk(mu);
+			if (rc != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g])); failed = true; }
+			else results[qi].assign(al);
+			done[qi] = 1;
+			cv.notify_all();
+		}
+	};
+	std::vector<std::thread> threads;
+	if (ngpu > 1) for (int g = 0; g < ngpu; g++) threads.emplace_back(run_gpu, g);
+
+	EmitState st;
+	for (int qi = 0; qi < nq; qi++) {
+		fprintf(stderr, "\tProcess query chromsomoe: %s...\n", query[qi].name.c_str());
+		ContigResult &r = results[(size_t)qi];
+		if (ngpu > 1) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[qi] != 0; }); }
+		else {
+			gsa_alignment al;
+			if (gsa_align_contig(ctx[0], query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[0])); failed = true; break; }
+			r.assign(al);
+		}
+		if (failed) break;
+		int n = 0; int64_t aln_score = 0, aln_len = 0;
+		for (const gsa_block &b : r.blocks) { // src/GSAlign.cpp:529-539 (the identity filter itself ran inside gsa_fill)
+			if (b.bDup) st.dup_num++;
+			n++; aln_len += b.aln_len; aln_score += b.score;
+			st.local_aln_num++; st.total_aln_len += b.aln_len; st.total_matches += b.score;
+		}
+		if (n == 0) { r = ContigResult(); continue; }
+		fprintf(stderr, "\t\tProduce %d local alignments (length = %lld), ANI=%.2f%%\n", n, (long long)aln_len, 100 * (1.0 * aln_score / aln_len));
+		if (o.out_format == 1) { fprintf(stderr, "\t\tOutput alignments for query sequence (%s)\n", o.maf.c_str()); output_maf(o, ix, query, qi, r); }
+		if (o.out_format == 2) { fprintf(stderr, "\t\tOutput alignments for query sequence (%s)\n", o.aln.c_str()); output_aln(o, ix, query, qi, r); }
+		if (o.vcf) { fprintf(stderr, "\t\tIdentify sequence variants for query sequence...\n"); variant_identification(ix, query, qi, r, st); }
+		fprintf(stderr, "\n");
+		r = ContigResult();
+	}
+	for (auto &t : threads) t.join();
+	if (st.local_aln_num > 0)
+		fprintf(stderr, "\tAlignment#=%d (total alignment length=%lld) ANI=%.2f%%, unique alignment#=%d\n", (int)st.local_aln_num, (long long)st.total_aln_len,
+		        100 * (1.0 * st.total_matches / st.total_aln_len), (int)(st.local_aln_num - st.dup_num));
+	fprintf(stderr, "\tIt took %lld seconds for genome sequence alignment.\n", (long long)(time(NULL) - t_start));
+	if (o.vcf && !failed) {
+		fprintf(stderr, "\nGSAlign identifies %d SNVs, %d insertions, and %d deletions [%s].\n\n", st.iSNV, st.iInsertion, st.iDeletion, o.vcf_name.c_str());
+		output_variants(o, ix, st);
+	}
+	for (gsa_ctx *c : ctx) gsa_destroy(c);
+	return 0;
+}

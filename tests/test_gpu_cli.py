@@ -1,0 +1,115 @@
+"""End-to-end drop-in parity: bin/GSAlign (this repo) vs the unmodified reference binary (oracle/_ref/GSAlign)
+on the same inputs -- .maf / .aln / .vcf must be byte-identical -- and bin/gsa_index vs the reference indexer."""
+import filecmp
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "bin", "GSAlign")
+OUR_INDEX = os.path.join(ROOT, "bin", "gsa_index")
+REF = os.path.join(ROOT, "oracle", "_ref", "GSAlign")
+REF_INDEX = os.path.join(ROOT, "oracle", "_ref", "bwt_index")
+
+# md5 of the reference's output for `-i test/ecoli -q test/ecoli.mut` (reproduced by
+# oracle/_ref/GSAlign in this container) -- pins config C1 even where the reference binary is absent
+ECOLI_MD5 = {"maf": "ad1155c7b94076ba964f87c1651f3112", "vcf": "9cc41a67335be201f2f559bc5ecbb0b1"}
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def run(exe, cwd, args):
+    subprocess.run([exe] + args, cwd=cwd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+def test_ecoli_golden_md5(ecoli, workdir):
+    """config C1, exactly the reference's run_test.sh command line (the VCF header embeds the -i string)"""
+    cwd = os.path.dirname(ecoli["dir"])
+    run(OURS, cwd, ["-t", "1", "-i", "test/ecoli", "-q", "test/ecoli.mut", "-o", "test/ours"])
+    assert md5(os.path.join(ecoli["dir"], "ours.maf")) == ECOLI_MD5["maf"]
+    assert md5(os.path.join(ecoli["dir"], "ours.vcf")) == ECOLI_MD5["vcf"]
+
+
+@pytest.mark.parametrize("flags", [[], ["-sen"], ["-fmt", "2"], ["-unique", "-idy", "90"], ["-slen", "20", "-ind", "50", "-clr", "300", "-alen", "500"],
+                                   ["-one"], ["-no_vcf"]])
+def test_rearranged_cli_bytes(workdir, flags):
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/GSAlign not built")
+    from conftest import build_index
+    from test_gpu_pipeline import make_rearranged
+    d = make_rearranged(workdir)
+    if not os.path.exists(os.path.join(d, "ref.sa")):
+        build_index(os.path.join(d, "ref.fa"), os.path.join(d, "ref"))
+    tag = "_".join(f.strip("-") for f in flags) or "default"
+    for exe, name in ((REF, "r_" + tag), (OURS, "o_" + tag)):
+        for ext in ("maf", "aln", "vcf"):
+            p = os.path.join(d, f"{name}.{ext}")
+            if os.path.exists(p):
+                os.remove(p)
+        run(exe, d, ["-t", "1", "-i", "ref", "-q", "qry.fa", "-o", name] + flags)
+    exts = ["aln"] if "-fmt" in flags else ["maf"]
+    if "-no_vcf" not in flags:
+        exts.append("vcf")
+    for ext in exts:
+        a, b = os.path.join(d, f"r_{tag}.{ext}"), os.path.join(d, f"o_{tag}.{ext}")
+        assert os.path.getsize(a) > 100
+        assert filecmp.cmp(a, b, shallow=False), f"{ext} differs for flags {flags}"
+    if "-no_vcf" in flags:
+        assert not os.path.exists(os.path.join(d, f"o_{tag}.vcf"))
+
+
+def test_multi_gpu_flag_same_bytes(workdir):
+    """-gpus N deals contigs to GPUs; output must not depend on it (N is clamped to the devices/contigs present)"""
+    from conftest import build_index
+    from test_gpu_pipeline import make_rearranged
+    import torch
+    d = make_rearranged(workdir)
+    if not os.path.exists(os.path.join(d, "ref.sa")):
+        build_index(os.path.join(d, "ref.fa"), os.path.join(d, "ref"))
+    n = min(2, torch.cuda.device_count())
+    run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "g1"])
+    run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "g2", "-gpus", str(n)])
+    for ext in ("maf", "vcf"):
+        assert filecmp.cmp(os.path.join(d, f"g1.{ext}"), os.path.join(d, f"g2.{ext}"), shallow=False)
+
+
+def _index_equal(d, fasta):
+    run(REF_INDEX, d, [fasta, "ri"])
+    run(OUR_INDEX, d, [fasta, "oi"])
+    for ext in ("pac", "ann", "amb", "bwt", "sa"):
+        assert filecmp.cmp(os.path.join(d, "ri." + ext), os.path.join(d, "oi." + ext), shallow=False), ext
+
+
+def test_index_builder_bytes_ecoli(ecoli):
+    if not os.path.exists(REF_INDEX):
+        pytest.skip("oracle/_ref/bwt_index not built")
+    _index_equal(ecoli["dir"], "ecoli.fa")
+
+
+def test_index_builder_bytes_adversarial(workdir):
+    """N runs, IUPAC codes, lower case, comments, CRLF, long exact repeats, tiny contigs"""
+    if not os.path.exists(REF_INDEX):
+        pytest.skip("oracle/_ref/bwt_index not built")
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    a = acgt[rng.integers(0, 4, size=70_001, dtype=np.uint8)].copy()
+    a[1000:1300] = ord("N"); a[2000:2003] = np.frombuffer(b"RYK", dtype=np.uint8); a[5000:5100] = ord("n"); a[5100:5150] = ord("N")
+    a[30_000:36_000] = a[10_000:16_000]                    # 6 kb exact repeat
+    b = np.frombuffer(bytes(acgt[rng.integers(0, 4, size=4_096, dtype=np.uint8)]).lower(), dtype=np.uint8)
+    c = np.frombuffer(b"ACGTNACGT", dtype=np.uint8)
+    e = np.frombuffer(b"A" * 3000 + b"AC" * 1500, dtype=np.uint8)  # low-complexity: deep doubling
+    d = os.path.join(workdir, "idx")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "adv.fa"), "wb") as f:
+        for name, s, eol in (("s1 first contig", a, b"\n"), ("s2", b, b"\r\n"), ("s3\tx y", c, b"\n"), ("s4", e, b"\n")):
+            f.write(b">" + name.encode() + eol)
+            for i in range(0, len(s), 61):
+                f.write(bytes(s[i:i + 61]) + eol)
+            f.write(b"\n")
+    _index_equal(d, "adv.fa")
