@@ -1,0 +1,127 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol that
+include/gsalign_b200.h declares; it refuses to run without a device (no CPU fallback); host-side helpers."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "gsalign_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsa_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gsalign_b200 import capi
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/gsalign_b200.h but not exported"
+    assert sorted(capi.EXPORTS) == [n for n in names if n in capi.EXPORTS]
+
+
+def test_no_cpu_fallback():
+    """without a GPU gsa_create must fail (loudly), never fall back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gsalign_b200 import capi
+    with pytest.raises(capi.GsaError):
+        capi.Aligner(0)
+
+
+def test_product_never_touches_the_oracle():
+    """nothing under gsalign_b200/ or include/ may reference oracle/ (test infrastructure only)"""
+    bad = []
+    for base in ("gsalign_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in dp:
+                continue
+            for f in files:
+                if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"gsa_oracle|liboracle|libgsref|orc_[a-z]+\(", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_synth_generator_is_deterministic():
+    from gsalign_b200 import synth
+    r1, q1 = synth.make_pair(40_000, 2, 0.01, 0.001, 4)
+    r2, q2 = synth.make_pair(40_000, 2, 0.01, 0.001, 4)
+    assert all(np.array_equal(a[1], b[1]) for a, b in zip(r1 + q1, r2 + q2))
+    assert [n for n, _ in r1] == ["chr1", "chr2"] and [n for n, _ in q1] == ["qchr1", "qchr2"]
+    assert not np.array_equal(r1[0][1][:2000], q1[0][1][:2000])
+    rs, qs = synth.make_pair(40_000, 2, 0.01, 0.0, 4)           # SNV only: same length, ~1 % substitutions
+    assert 0.003 < np.mean(rs[0][1] != qs[0][1]) < 0.03
+    assert abs(len(q1[0][1]) - 20_000) < 200
+
+
+def test_bwaidx_loader_roundtrip(ecoli):
+    from gsalign_b200 import bwaidx
+    bi = ecoli["index"]
+    assert bi.seq_len == 2 * bi.l_pac == 2 * 4639675 and bi.sa_intv == 32
+    assert bi.bwt.shape[0] * 4 + 40 == os.path.getsize(ecoli["prefix"] + ".bwt")
+    assert int(bi.L2[4]) == bi.seq_len and bi.names == ["NC_000913"]
+    t = bwaidx.text(bi)
+    assert t.shape[0] == bi.seq_len and np.array_equal(t[:50], 3 - t[::-1][:50])
+    # T is its own reverse complement: base counts of A/T and C/G agree with L2
+    cnt = np.bincount(t, minlength=4)
+    assert [int(bi.L2[i + 1] - bi.L2[i]) for i in range(4)] == cnt.tolist()
+
+
+def test_lpt_sharding():
+    from gsalign_b200.shard import lpt_assign
+    lens = [125] * 24
+    parts = lpt_assign(lens, 8)
+    assert sorted(sum(parts, [])) == list(range(24)) and all(len(p) == 3 for p in parts)
+    parts = lpt_assign([100, 1, 1, 1, 50, 49], 2)
+    assert sorted(sum(parts, [])) == list(range(6))
+    loads = [sum([100, 1, 1, 1, 50, 49][i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= 2
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsalign_b200.shard import lpt_assign
+    lens = [300, 200, 120, 90, 80, 10]
+    mine = lpt_assign(lens, world)[rank]
+    # what bench.py does at N > 1: per-rank time -> MAX over ranks, units -> SUM over ranks
+    t = torch.tensor([float(sum(lens[i] for i in mine))], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    u = torch.tensor([len(mine)], dtype=torch.int64)
+    dist.all_reduce(u)
+    got = [None] * world
+    dist.all_gather_object(got, mine)          # the record gather of SURVEY.md 8e, on host objects
+    q.put((rank, float(t[0]), int(u[0]), got))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_reduction():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    assert all(r[1] == res[0][1] and r[2] == 6 for r in res)
+    assert sorted(res[0][3][0] + res[0][3][1]) == list(range(6))
+    assert res[0][1] == 400.0

@@ -1,0 +1,45 @@
+"""Turns gpurun_out/{launches_*.csv, prof_*.ncu-rep, bench_*.json} into tracked summaries under profiles/.
+usage: python tools/summarize_profile.py <round-tag>"""
+import collections, csv, glob, json, os, re, subprocess, sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+os.makedirs("profiles", exist_ok=True)
+out = [f"# profiles/{tag}: ncu launch lists, full captures and bench lines (B200, sm_100a)\n"]
+for path in sorted(glob.glob("gpurun_out/launches_*.csv")):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(lambda: [0, 0.0]); tot = 0.0
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]
+        v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v * 1e6 if u == "s" else v
+        name = re.sub(r"\(.*", "", re.sub(r"<.*", "", row["Kernel Name"]))[:50]
+        agg[name][0] += 1; agg[name][1] += v; tot += v
+    out.append(f"\n## launch list {os.path.basename(path)} (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare SHARES)\n")
+    out.append("| kernel | launches | total us | share |\n|---|---|---|---|")
+    for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:22]:
+        out.append(f"| {k} | {c} | {t:.1f} | {100 * t / tot:.1f}% |")
+    out.append(f"| **all** | {sum(c for c, _ in agg.values())} | {tot:.1f} | 100% |")
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "sm__inst_executed_pipe_alu.sum", "smsp__inst_executed_op_shared_ld.sum"]
+for path in sorted(glob.glob("gpurun_out/prof_*.ncu-rep")):
+    r = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(r.splitlines()))
+    if len(rows) < 3:
+        continue
+    hdr = rows[0]
+    out.append(f"\n## full capture {os.path.basename(path)} (`ncu --set full --clock-control none --import-source on`)\n")
+    out.append("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(rows) - 2)) + " |\n|---|---|" + "---|" * (len(rows) - 2))
+    ki = hdr.index("Kernel Name")
+    out.append("| kernel | | " + " | ".join(re.sub(r"\(.*", "", row[ki])[:40] for row in rows[2:]) + " |")
+    for w in WANT:
+        if w in hdr:
+            i = hdr.index(w)
+            out.append(f"| {w} | {rows[1][i]} | " + " | ".join(row[i] for row in rows[2:]) + " |")
+for path in sorted(glob.glob("gpurun_out/bench_*.json")):
+    txt = open(path).read().strip()
+    if txt:
+        out.append(f"\n## {os.path.basename(path)}\n\n```json\n{txt}\n```")
+open(f"profiles/{tag}_summary.md", "w").write("\n".join(out) + "\n")
+print("wrote", f"profiles/{tag}_summary.md")
