@@ -1,0 +1,198 @@
+// dpx.cu -- K3's DP kernel: global affine-gap alignment as a register-resident anti-diagonal wavefront on packed
+// int16 pairs (DPX: VIADD.16x2, VIMNMX.S16x2 with predicate outputs).
+//
+// Same recurrence, tie rules and traceback as fill.cu's scalar kernel (ksw_extz2_sse / ksw_backtrack semantics,
+// reference src/ksw2_alignment.cpp:25-249; restated in SURVEY.md 8a A9), for fragment pairs made of ACGT only:
+//     E'(i,j) = max(H(i-1,j), E'(i-1,j) - 1)        E' = E + 3 (gap open 2 + extend 1 folded into H)
+//     F'(i,j) = max(H(i,j-1), F'(i,j-1) - 1)
+//     H(i,j)  = max(H(i-1,j-1) + s, E' - 3, F' - 3)  diag first, E only if strictly greater, F only if greater than both
+// Work split: the query rows are cut into strips of 64; a warp sweeps a strip along its anti-diagonals with lane p
+// holding rows 2p (low half-word) and 2p+1 (high half-word), so both halves of a register sit on the same
+// anti-diagonal.  Per step a lane needs H and E' of the row above (one packed __shfl_up; lane 0 reads the last row of the
+// strip above from shared memory, lane 31 writes its own there for the strip below) and one 16-bit shared-memory
+// load of the two reference bases.  Cells before column 0 are fixed points of the recurrence (sentinel base scores -1
+// against everything: H(i-1,-1) - 1 = H(i,-1)), cells past the last column are garbage nobody reads, so there is no
+// per-step bounds logic.  The match score comes out of one PRMT used as an 8-entry table on q XOR r.
+// Four decision bits per cell (E>diag, F>both, E extended, F extended) are the VIMNMX predicates, collected over 8 steps
+// into one word per row and written as 256-byte warp rows (shared memory for small problems, HBM otherwise).
+// Strips of one problem run on W warps as a pipeline: strip s+1 trails strip s by 72 steps, synchronised by a
+// per-strip progress counter in shared memory.
+#include "dpx.cuh"
+#include "fm.cuh"
+
+#define DPX_FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+// prmt.b32 in its default mode: selector nibble bit 3 replicates the sign of the selected byte (__byte_perm only
+// documents the low three bits)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
+
+// max per half-word; ORs `bit` into f_lo / f_hi where b won strictly (a < b).  ptxas folds the max + setp pair into
+// one VIMNMX.S16x2 with two predicate outputs and predicates the two ORs on them.
+__device__ __forceinline__ uint32_t vmax_flag(uint32_t a, uint32_t b, uint32_t &f_lo, uint32_t &f_hi, uint32_t bit)
+{
+	uint32_t v;
+	asm("{.reg .pred pu, pv;\n\t"
+	    ".reg .s16 rs0, rs1, rs2, rs3;\n\t"
+	    "max.s16x2 %0, %3, %4;\n\t"
+	    "mov.b32 {rs0, rs1}, %0;\n\t"
+	    "mov.b32 {rs2, rs3}, %3;\n\t"
+	    "setp.eq.s16 pv, rs0, rs2;\n\t"
+	    "setp.eq.s16 pu, rs1, rs3;\n\t"
+	    "@!pv or.b32 %1, %1, %5;\n\t"
+	    "@!pu or.b32 %2, %2, %5;}\n\t"
+	    : "=r"(v), "+r"(f_lo), "+r"(f_hi) : "r"(a), "r"(b), "r"(bit));
+	return v;
+}
+
+template <int W, bool SMEMF>
+__global__ void __launch_bounds__(32 * W)
+k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1, char *aln2, int32_t *out_len, gsa_frag *frag,
+      const int32_t *fblk, unsigned int *bsum)
+{
+	extern __shared__ uint32_t dsm[];
+	const int pi = blockIdx.x;
+	if (pi >= nprob) return;
+	const DpProblem P = prob[pi];
+	const int m = P.m, n = P.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const DpxLayout L = dpx_layout(m, n, SMEMF);
+	uint32_t *bhe = dsm + (L.off_bhe >> 2) + 64;                                   // bhe[j] = {H(i0-1,j), E'(i0-1,j)}
+	uint16_t *a16 = (uint16_t *)((char *)dsm + L.off_a16) + 64;                    // a16[k] = selector halves for columns k, k-1
+	volatile int *prog = (volatile int *)((char *)dsm + L.off_prog);
+	unsigned char *qch = (unsigned char *)dsm + L.off_qch, *rch = (unsigned char *)dsm + L.off_rch;
+	uint32_t *fl = SMEMF ? dsm + (L.off_flags >> 2) : (uint32_t *)(gflags + P.flag_off);
+	const int G = L.G, cols = 8 * G + 8;
+
+	// ---- stage both fragments, the reference selector array and the row above strip 0 --------------------------
+	for (int i = tid; i < n; i += 32 * W) qch[i] = (unsigned char)P.qry_chars[i];
+	for (int j = tid; j < m; j += 32 * W) rch[j] = P.ref_chars ? (unsigned char)P.ref_chars[j] : (unsigned char)gsa_text_char(ix, P.rpos + j);
+	if (W == 1) __syncwarp(); else __syncthreads();
+	for (int k = -64 + tid; k < cols; k += 32 * W) {
+		int c0 = (k >= 0 && k < m) ? gsa_nt4(rch[k]) : 4, c1 = (k >= 1 && k <= m) ? gsa_nt4(rch[k - 1]) : 4;
+		a16[k] = (uint16_t)(c0 | 0x80 | (c1 << 8) | 0x8000);
+		bhe[k] = pack16(-(3 + k), DP_NEG);
+	}
+	for (int k = tid; k < L.nstrips; k += 32 * W) prog[k] = 0;
+	if (W == 1) __syncwarp(); else __syncthreads();
+
+	const uint32_t M1 = 0xFFFFFFFFu, M3 = 0xFFFDFFFDu, TA = 0x02020204u, TB = 0x02020202u;
+	for (int s = warp; s < L.nstrips; s += W) {
+		const int i0 = s << 6, r0 = i0 + 2 * lane, r1 = r0 + 1;
+		const int R = min(64, n - i0), Gs = (m + R - 1 + 7) >> 3;
+		uint32_t Hl = pack16(-(3 + r0), -(3 + r1));                 // H(i,-1)
+		uint32_t El = pack16(DP_NEG, DP_NEG), Fl = El;
+		uint32_t Dg = pack16(r0 == 0 ? 0 : -(2 + r0), -(2 + r1));   // H(i-1,-1)
+		const uint32_t qw = (uint32_t)(r0 < n ? gsa_nt4(qch[r0]) : 0) | ((uint32_t)(r1 < n ? gsa_nt4(qch[r1]) : 0) << 8);
+		const uint16_t *ap = a16 - 2 * lane;
+		uint2 *fs = (uint2 *)fl + (size_t)s * G * 32 + lane;
+		for (int g = 0; g < Gs; g++) {
+			if (W > 1 && s > 0) {
+				if (lane == 0) { int need = min(g + 9, G); while (prog[s - 1] < need) { } }
+				__syncwarp();
+				__threadfence_block();
+			}
+			const int d0 = g << 3;
+			uint32_t f0 = 0, f1 = 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				const int d = d0 + k;
+				uint32_t rv = __shfl_up_sync(DPX_FULL, __byte_perm(Hl, El, 0x7632), 1);
+				if (lane == 0) rv = bhe[d];
+				uint32_t up = __byte_perm(rv, Hl, 0x5410), eu = __byte_perm(rv, El, 0x5432);
+				uint32_t s3 = prmt(TA, TB, qw ^ (uint32_t)ap[d]);
+				uint32_t E = vmax_flag(up, __vadd2(eu, M1), f0, f1, 4u << (4 * k));        // bit 2: E extended
+				uint32_t F = vmax_flag(Hl, __vadd2(Fl, M1), f0, f1, 8u << (4 * k));        // bit 3: F extended
+				uint32_t h = vmax_flag(__vadd2(Dg, s3), E, f0, f1, 1u << (4 * k));         // bit 0: E beats the diagonal
+				h = vmax_flag(h, F, f0, f1, 2u << (4 * k));                                // bit 1: F beats both
+				Dg = up; Hl = __vadd2(h, M3); El = E; Fl = F;
+				if (lane == 31) bhe[d - 63] = __byte_perm(Hl, El, 0x7632);
+			}
+			fs[(size_t)g * 32] = make_uint2(f0, f1);
+			if (W > 1 && lane == 31) { __threadfence_block(); prog[s] = g + 1; }
+		}
+		if (W > 1 && lane == 31) { __threadfence_block(); prog[s] = G; } // a short last strip still releases its (absent) follower
+	}
+	if (W == 1) __syncwarp(); else __syncthreads();
+
+	// ---- traceback (ksw_backtrack, src/ksw2_alignment.cpp:25-68); rows are produced back to front ------------------
+	__shared__ int sL, sSame;
+	char *o1 = aln1 + P.out_off, *o2 = aln2 + P.out_off;
+	char *t1 = SMEMF ? (char *)dsm + L.off_st : o1, *t2 = SMEMF ? t1 + ((m + n + 3) & ~3) : o2;
+	if (tid == 0) {
+		int i = n - 1, j = m - 1, state = 0, cont = 0, len = 0;
+		while (i >= 0 && j >= 0) {
+			int ii = i & 63, d = j + ii;
+			uint32_t w = fl[(((size_t)(i >> 6) * G + (d >> 3)) * 32 + (ii >> 1)) * 2 + (ii & 1)];
+			int t = (w >> ((d & 7) << 2)) & 15;
+			if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
+			char c1, c2;
+			if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
+			else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
+			else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
+			t1[len] = c1; t2[len] = c2; len++;
+		}
+		for (; i >= 0; i--, len++) { t1[len] = '-'; t2[len] = (char)qch[i]; }
+		for (; j >= 0; j--, len++) { t1[len] = (char)rch[j]; t2[len] = '-'; }
+		sL = len; sSame = 0;
+	}
+	if (W == 1) __syncwarp(); else __syncthreads();
+	const int len = sL;
+	int same = 0;
+	if (SMEMF) {
+		for (int k = tid; k < len; k += 32 * W) {
+			char a = t1[len - 1 - k], b = t2[len - 1 - k];
+			o1[k] = a; o2[k] = b;
+			same += gsa_nt4((unsigned char)a) == gsa_nt4((unsigned char)b); // CountIdenticalPairs: '-' is class 4, never equal to ACGT
+		}
+	} else {
+		for (int k = tid; k < len / 2; k += 32 * W) {
+			char a = o1[k], b = o1[len - 1 - k]; o1[k] = b; o1[len - 1 - k] = a;
+			a = o2[k]; b = o2[len - 1 - k]; o2[k] = b; o2[len - 1 - k] = a;
+		}
+		__syncthreads();
+		for (int k = tid; k < len; k += 32 * W) same += gsa_nt4((unsigned char)o1[k]) == gsa_nt4((unsigned char)o2[k]);
+	}
+	for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(DPX_FULL, same, o);
+	if (W > 1) {
+		if (lane == 0 && same) atomicAdd(&sSame, same);
+		__syncthreads();
+		same = sSame;
+	}
+	if (tid == 0) {
+		if (out_len) out_len[P.frag] = len;
+		if (frag) {
+			frag[P.frag].aln_off = P.out_off; frag[P.frag].aln_len = len;
+			int b = fblk[P.frag];
+			atomicAdd(bsum + 2 * b, (unsigned)len); atomicAdd(bsum + 2 * b + 1, (unsigned)same);
+		}
+	}
+}
+
+template <int W, bool SMEMF>
+static int launch_dpx(gsa_ctx *ctx, size_t smem, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
+                      gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+{
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<W, SMEMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_dpx<W, SMEMF><<<nprob, 32 * W, smem, ctx->stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, frag, fblk, bsum);
+	KERNEL_CHECK(ctx);
+	return GSA_OK;
+}
+
+int gsa_dpx_launch(gsa_ctx *ctx, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
+                   gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+{
+	if (nprob <= 0) return GSA_OK;
+	switch (cls) {
+	case DPX_CLS_S4: return launch_dpx<1, true>(ctx, DPX_SMEM_S4, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_S12: return launch_dpx<1, true>(ctx, DPX_SMEM_S12, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_S48: return launch_dpx<4, true>(ctx, DPX_SMEM_S48, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_G: return launch_dpx<8, false>(ctx, dpx_layout(max_m, max_n, false).total, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	}
+	return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dpx_launch: bad class %d", cls);
+}

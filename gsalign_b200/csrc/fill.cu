@@ -15,25 +15,12 @@
 //     leftover rows/columns become one gap) and the CTA reverses the rows in place.
 // Also accumulates AlnBlock_t::aln_len / score per block and applies nothing else: the identity filter and
 // the final block order are O(#blocks) host logic (see gsa_impl_fill at the bottom).
+#include "dpx.cuh"
 #include "fm.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
-
-#define DP_NEG (-30000)
-#define DP_MAX_DIM 8000
-
-struct DpProblem {
-	const char *ref_chars; // explicit reference fragment (gsa_dp_batch) or nullptr -> read the 2-bit text at rpos
-	const char *qry_chars;
-	int64_t rpos;
-	int64_t flag_off;      // into the direction-byte pool
-	int64_t out_off;       // into the row pools
-	int32_t m, n;          // m = reference fragment length (columns), n = query fragment length (rows)
-	int32_t frag;          // fragment index (pipeline) or pair index (batch)
-	int32_t pad;
-};
 
 // fragment type codes
 enum { FT_SEED = 0, FT_DEL = 1, FT_INS = 2, FT_COPY = 3, FT_DP = 4 };
@@ -41,13 +28,13 @@ enum { FT_SEED = 0, FT_DEL = 1, FT_INS = 2, FT_COPY = 3, FT_DP = 4 };
 // ---- classification ----------------------------------------------------------------------------------
 // One thread per fragment: type, mismatch count for equal-length fragments (CheckFragPairMismatch,
 // src/ProcessCandidateAlignment.cpp:49-61), upper bound of its row length, DP cell count.
-__global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char *seq, DevIndex ix, uint8_t *type, int32_t *mism,
-                                int64_t *row_len, int64_t *flag_len, uint8_t *is_dp)
+__global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char *seq, const uint32_t *qinv, DevIndex ix, uint8_t *type, int32_t *mism,
+                                int64_t *row_len, int64_t *flag_len, uint8_t *is_dp, uint8_t *dp_cls)
 {
 	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= nfr) return;
 	gsa_frag f = frag[t];
-	uint8_t ty = FT_SEED; int64_t rl = 0, fl = 0; int mm = 0;
+	uint8_t ty = FT_SEED, cls = 0; int64_t rl = 0, fl = 0; int mm = 0;
 	if (!f.bSeed) {
 		if (f.qLen == 0) { ty = FT_DEL; rl = f.rLen; }
 		else if (f.rLen == 0) { ty = FT_INS; rl = f.qLen; }
@@ -61,10 +48,16 @@ __global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char
 				if (mm <= 5) ty = FT_COPY;
 			}
 			if (ty == FT_COPY) rl = f.qLen;
-			else { rl = (int64_t)f.qLen + f.rLen; int w = min(f.qLen, f.rLen); fl = (int64_t)(f.qLen + f.rLen - 1) * w; }
+			else {
+				rl = (int64_t)f.qLen + f.rLen;
+				bool other = false; // any non-ACGT query base in the fragment (the 2-bit reference text holds none)
+				for (uint32_t p = (uint32_t)f.qPos, e = p + (uint32_t)f.qLen; p < e && !other; p += 32) other = (gsa_bit_window(qinv, p) >> (32 - min(32u, e - p))) != 0;
+				cls = (uint8_t)dpx_class(f.rLen, f.qLen, other);
+				fl = dpx_flag_bytes(f.rLen, f.qLen, cls);
+			}
 		}
 	}
-	type[t] = ty; mism[t] = mm; row_len[t] = rl; flag_len[t] = fl; is_dp[t] = ty == FT_DP;
+	type[t] = ty; mism[t] = mm; row_len[t] = rl; flag_len[t] = fl; is_dp[t] = ty == FT_DP; dp_cls[t] = cls;
 }
 
 // rows of the non-DP fragment types + per-block sums (src/ProcessCandidateAlignment.cpp:303-331)
@@ -92,14 +85,14 @@ __global__ void k_frag_simple(gsa_frag *frag, int64_t nfr, const int32_t *fblk, 
 }
 
 __global__ void k_dp_problems(const int32_t *dp_idx, int64_t ndp, const gsa_frag *frag, const int64_t *row_off, const int64_t *flag_off,
-                              const unsigned char *seq, DpProblem *prob)
+                              const uint8_t *dp_cls, const unsigned char *seq, DpProblem *prob)
 {
 	int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= ndp) return;
 	int32_t t = dp_idx[k];
 	gsa_frag f = frag[t];
 	DpProblem p; p.ref_chars = nullptr; p.qry_chars = (const char *)seq + f.qPos; p.rpos = f.rPos; p.flag_off = flag_off[t]; p.out_off = row_off[t];
-	p.m = f.rLen; p.n = f.qLen; p.frag = t; p.pad = 0;
+	p.m = f.rLen; p.n = f.qLen; p.frag = t; p.cls = dp_cls[t];
 	prob[k] = p;
 }
 
@@ -207,13 +200,24 @@ static int launch_dp(gsa_ctx *ctx, const DpProblem *prob, int nprob, int dim_cap
 	return GSA_OK;
 }
 
-// problems are binned by max(m,n) so that small ones get small shared memory (many CTAs per SM)
+// Problems are sorted by (class, size).  ACGT-only pairs go to the packed-int16 wavefront kernel (dpx.cu), one launch per
+// size class; the rest take the scalar kernel, binned by max(m,n) so that small ones get small shared memory.
 static int run_dp_binned(gsa_ctx *ctx, std::vector<DpProblem> &hp, DpProblem *d_prob, uint8_t *flags, char *a1, char *a2, int32_t *out_len, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
-	std::stable_sort(hp.begin(), hp.end(), [](const DpProblem &a, const DpProblem &b) { return std::max(a.m, a.n) < std::max(b.m, b.n); });
+	std::stable_sort(hp.begin(), hp.end(), [](const DpProblem &a, const DpProblem &b) {
+		if (a.cls != b.cls) return a.cls < b.cls;
+		return std::max(a.m, a.n) < std::max(b.m, b.n);
+	});
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_prob, hp.data(), hp.size() * sizeof(DpProblem), cudaMemcpyHostToDevice, ctx->stream));
-	const int caps[] = {32, 128, 512, 2048, DP_MAX_DIM};
 	size_t beg = 0;
+	for (int cls = 0; cls < DPX_CLS_SCALAR; cls++) {
+		size_t end = beg;
+		int max_m = 1, max_n = 1;
+		for (; end < hp.size() && hp[end].cls == cls; end++) { max_m = std::max(max_m, hp[end].m); max_n = std::max(max_n, hp[end].n); }
+		GSA_TRY(gsa_dpx_launch(ctx, cls, max_m, max_n, d_prob + beg, (int)(end - beg), flags, a1, a2, out_len, frag, fblk, bsum));
+		beg = end;
+	}
+	const int caps[] = {32, 128, 512, 2048, DP_MAX_DIM};
 	for (int c = 0; c < 5; c++) {
 		size_t end = beg;
 		while (end < hp.size() && std::max(hp[end].m, hp[end].n) <= caps[c]) end++;
@@ -263,7 +267,7 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 	Ws3 ws(ctx);
 	gsa_frag *frag = (gsa_frag *)ctx->d_frag.p; const int32_t *fblk = (const int32_t *)ctx->d_fblk.p;
 	const unsigned char *seq = (const unsigned char *)ctx->d_seq.p;
-	uint8_t *type = ws.get<uint8_t>(nfr), *is_dp = ws.get<uint8_t>(nfr);
+	uint8_t *type = ws.get<uint8_t>(nfr), *is_dp = ws.get<uint8_t>(nfr), *dp_cls = ws.get<uint8_t>(nfr);
 	int32_t *mism = ws.get<int32_t>(nfr), *dp_idx = ws.get<int32_t>(nfr);
 	int64_t *row_len = ws.get<int64_t>(nfr + 1), *flag_len = ws.get<int64_t>(nfr + 1), *row_off = ws.get<int64_t>(nfr + 1), *flag_off = ws.get<int64_t>(nfr + 1);
 	if (ws.rc) return ws.rc;
@@ -271,7 +275,7 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 	unsigned int *bsum = (unsigned int *)ctx->d_bsum.p;
 	int32_t *d_ndp = (int32_t *)ctx->d_counter.p + 32;
 	CUDA_TRY(ctx, cudaMemsetAsync(bsum, 0, (size_t)nblk * 8, ctx->stream));
-	k_frag_classify<<<gsa_grid(nfr, 128), 128, 0, ctx->stream>>>(frag, nfr, seq, ctx->ix, type, mism, row_len, flag_len, is_dp);
+	k_frag_classify<<<gsa_grid(nfr, 128), 128, 0, ctx->stream>>>(frag, nfr, seq, (const uint32_t *)ctx->d_qinv.p, ctx->ix, type, mism, row_len, flag_len, is_dp, dp_cls);
 	KERNEL_CHECK(ctx);
 	CUDA_TRY(ctx, cudaMemsetAsync(row_len + nfr, 0, 8, ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(flag_len + nfr, 0, 8, ctx->stream));
@@ -299,14 +303,17 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 	ctx->tm.n_dp = ndp; ctx->tm.dp_cells = 0;
 	if (ndp > 0) {
 		DpProblem *d_prob = ws.get<DpProblem>(ndp);
-		uint8_t *flags = ws.get<uint8_t>(flag_bytes);
+		uint8_t *flags = ws.get<uint8_t>(flag_bytes + 256);
 		if (ws.rc) return ws.rc;
-		k_dp_problems<<<gsa_grid(ndp, 128), 128, 0, ctx->stream>>>(dp_idx, ndp, frag, row_off, flag_off, seq, d_prob);
+		k_dp_problems<<<gsa_grid(ndp, 128), 128, 0, ctx->stream>>>(dp_idx, ndp, frag, row_off, flag_off, dp_cls, seq, d_prob);
 		KERNEL_CHECK(ctx);
 		std::vector<DpProblem> hp((size_t)ndp);
 		CUDA_TRY(ctx, cudaMemcpyAsync(hp.data(), d_prob, (size_t)ndp * sizeof(DpProblem), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-		for (const DpProblem &p : hp) ctx->tm.dp_cells += (int64_t)p.m * p.n;
+		for (const DpProblem &p : hp) {
+			if (std::max(p.m, p.n) > DP_MAX_DIM) return gsa_fail(ctx, GSA_ERR_LIMIT, "DP fragment longer than %d", DP_MAX_DIM);
+			ctx->tm.dp_cells += (int64_t)p.m * p.n;
+		}
 		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
 		GSA_TRY(run_dp_binned(ctx, hp, d_prob, flags, a1, a2, nullptr, frag, fblk, bsum));
 		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
@@ -363,10 +370,14 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 		p.m = (int32_t)(ref_off[i + 1] - ref_off[i]); p.n = (int32_t)(qry_off[i + 1] - qry_off[i]);
 		if (p.m <= 0 || p.n <= 0) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dp_batch: empty fragment in pair %d", i);
 		p.ref_chars = d_ref + ref_off[i]; p.qry_chars = d_qry + qry_off[i]; p.rpos = 0; p.flag_off = fbytes; p.out_off = ref_off[i] + qry_off[i];
-		p.frag = i; p.pad = 0;
-		fbytes += (int64_t)(p.m + p.n - 1) * std::min(p.m, p.n);
+		if (std::max(p.m, p.n) > DP_MAX_DIM) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_dp_batch: fragment longer than %d in pair %d", DP_MAX_DIM, i);
+		bool other = false; // any letter outside ACGT/acgt sends the pair to the scalar kernel
+		for (int64_t k = ref_off[i]; k < ref_off[i + 1] && !other; k++) { char c = ref[k] & 0xDF; other = !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
+		for (int64_t k = qry_off[i]; k < qry_off[i + 1] && !other; k++) { char c = qry[k] & 0xDF; other = !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
+		p.frag = i; p.cls = dpx_class(p.m, p.n, other);
+		fbytes += dpx_flag_bytes(p.m, p.n, p.cls);
 	}
-	uint8_t *flags = ws.get<uint8_t>(fbytes);
+	uint8_t *flags = ws.get<uint8_t>(fbytes + 256);
 	if (ws.rc) return ws.rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_ref, ref, (size_t)rb, cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_qry, qry, (size_t)qb, cudaMemcpyHostToDevice, ctx->stream));

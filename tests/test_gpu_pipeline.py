@@ -156,3 +156,41 @@ def test_dp_batch_vs_oracle(oracle):
     for a, b, (x, y) in zip(refs, qrys, res):
         assert (x, y) == oracle.dp_align(a, b), (a, b)
     al.close()
+
+
+def _mutate(rng, a: bytes, p_sub: float, p_indel: float) -> bytes:
+    out = bytearray()
+    for ch in a:
+        u = rng.random()
+        if u < p_indel / 2:
+            continue
+        if u < p_indel:
+            out += bytes(rng.choice(list(b"ACGT")) for _ in range(rng.randint(1, 6)))
+        out.append(rng.choice(list(b"ACGT")) if rng.random() < p_sub else ch)
+    return bytes(out) or b"A"
+
+
+def test_dpx_classes_vs_oracle(oracle):
+    """every size class of the packed-int16 wavefront kernel (1-warp / 4-warp shared-memory flags, 8-warp pipelined strips
+    with flags in HBM) and the strip / group boundaries, ACGT only, vs the oracle's ksw2 restatement"""
+    import random
+    from gsalign_b200 import capi
+    rng = random.Random(11)
+    refs, qrys = [], []
+    dims = [(1, 1), (1, 70), (70, 1), (5, 64), (64, 5), (63, 63), (64, 64), (65, 65), (66, 127), (127, 66), (128, 128), (129, 130),
+            (200, 190), (257, 255), (300, 320), (500, 64), (64, 500), (3, 900), (900, 3), (640, 641), (1000, 1010), (1500, 1400),
+            (2100, 2000), (4000, 7), (7, 4000), (3100, 3000)]
+    for m, n in dims:
+        a = bytes(rng.choice(list(b"ACGT")) for _ in range(m))
+        refs.append(a); qrys.append(bytes(rng.choice(list(b"ACGT")) for _ in range(n)))          # unrelated
+        if min(m, n) > 8 and abs(m - n) < 0.2 * m:
+            refs.append(a); qrys.append(_mutate(rng, a, 0.05, 0.02))                                # related, indels
+            refs.append(a.lower()); qrys.append(_mutate(rng, a, 0.3, 0.05))                         # divergent, lower-case ref
+    for t in range(300):                                                                             # many small ones
+        m = rng.randint(1, 140); a = bytes(rng.choice(list(b"ACGT")) for _ in range(m))
+        refs.append(a); qrys.append(_mutate(rng, a, rng.choice([0.02, 0.1, 0.5]), rng.choice([0.0, 0.02, 0.1])))
+    al = capi.Aligner(0)
+    res, ms = al.dp_batch(refs, qrys)
+    for a, b, (x, y) in zip(refs, qrys, res):
+        assert (x, y) == oracle.dp_align(a, b), (len(a), len(b))
+    al.close()
