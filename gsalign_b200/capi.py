@@ -55,7 +55,7 @@ class Timing(C.Structure):
 
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
-           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump"]
+           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak"]
 
 
 def load_library() -> C.CDLL:
@@ -191,6 +191,23 @@ class Aligner:
         t = Timing()
         self._chk(self.lib.gsa_get_timing(self.ctx, C.byref(t)))
         return t
+
+    def dpx_peak(self, which: int = 0) -> float:
+        """issue rate of a packed-int16 DPX instruction, 1e9 thread-level instructions per second"""
+        v = C.c_double()
+        self._chk(self.lib.gsa_dpx_peak(self.ctx, C.c_int(which), C.byref(v)))
+        return v.value
+
+    def dp_batch_arrays(self, rb, ro, qb, qo):
+        """gsa_dp_batch on concatenated uint8 arrays + int64 offset arrays; returns (rows1, rows2, lens, kernel_ms)"""
+        n = ro.shape[0] - 1
+        tot = int(ro[-1] + qo[-1]) + 1
+        o1 = np.empty(tot, dtype=np.uint8); o2 = np.empty(tot, dtype=np.uint8); ol = np.zeros(max(n, 1), dtype=np.int32)
+        ms = C.c_float()
+        self._chk(self.lib.gsa_dp_batch(self.ctx, C.c_int32(n), rb.ctypes.data_as(C.c_char_p), _p(ro, C.c_int64),
+                                        qb.ctypes.data_as(C.c_char_p), _p(qo, C.c_int64), o1.ctypes.data_as(C.c_char_p),
+                                        o2.ctypes.data_as(C.c_char_p), _p(ol, C.c_int32), C.byref(ms)))
+        return o1, o2, ol, ms.value
 
     def dp_batch(self, refs, qrys):
         """refs/qrys: lists of bytes.  Returns (list of (row1,row2)), kernel_ms."""

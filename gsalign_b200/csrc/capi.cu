@@ -59,6 +59,8 @@ int gsa_create(int device, gsa_ctx **out)
 	memset(&ctx->ix, 0, sizeof(ctx->ix));
 	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
 	for (int i = 0; i < 12; i++) cudaEventCreate(&ctx->ev[i]);
+	if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
 	if (gsa_ensure_host(ctx, ctx->h_small, 1 << 20) != GSA_OK) { delete ctx; return GSA_ERR_NOMEM; }
 	*out = ctx;
 	return GSA_OK;
@@ -77,6 +79,9 @@ void gsa_destroy(gsa_ctx *ctx)
 	HostBuf *hb[] = {&ctx->h_small, &ctx->h_stage, &ctx->h_frag, &ctx->h_aln1, &ctx->h_aln2, &ctx->h_blocks};
 	for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
 	for (int i = 0; i < 12; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+	if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
 	if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }

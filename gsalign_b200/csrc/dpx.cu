@@ -21,6 +21,7 @@
 #include "fm.cuh"
 
 #define DPX_FULL 0xffffffffu
+#define DPX_TBW 16   // traceback window, in 8-step groups
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
@@ -35,7 +36,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 
 // max per half-word; ORs `bit` into f_lo / f_hi where b won strictly (a < b).  ptxas folds the max + setp pair into
 // one VIMNMX.S16x2 with two predicate outputs and predicates the two ORs on them.
-__device__ __forceinline__ uint32_t vmax_flag(uint32_t a, uint32_t b, uint32_t &f_lo, uint32_t &f_hi, uint32_t bit)
+template <uint32_t BIT>
+__device__ __forceinline__ uint32_t vmax_flag(uint32_t a, uint32_t b, uint32_t &f_lo, uint32_t &f_hi)
 {
 	uint32_t v;
 	asm("{.reg .pred pu, pv;\n\t"
@@ -47,7 +49,7 @@ __device__ __forceinline__ uint32_t vmax_flag(uint32_t a, uint32_t b, uint32_t &
 	    "setp.eq.s16 pu, rs1, rs3;\n\t"
 	    "@!pv or.b32 %1, %1, %5;\n\t"
 	    "@!pu or.b32 %2, %2, %5;}\n\t"
-	    : "=r"(v), "+r"(f_lo), "+r"(f_hi) : "r"(a), "r"(b), "r"(bit));
+	    : "=r"(v), "+r"(f_lo), "+r"(f_hi) : "r"(a), "r"(b), "n"(BIT));
 	return v;
 }
 
@@ -99,20 +101,22 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1
 			}
 			const int d0 = g << 3;
 			uint32_t f0 = 0, f1 = 0;
-#pragma unroll
-			for (int k = 0; k < 8; k++) {
-				const int d = d0 + k;
-				uint32_t rv = __shfl_up_sync(DPX_FULL, __byte_perm(Hl, El, 0x7632), 1);
-				if (lane == 0) rv = bhe[d];
-				uint32_t up = __byte_perm(rv, Hl, 0x5410), eu = __byte_perm(rv, El, 0x5432);
-				uint32_t s3 = prmt(TA, TB, qw ^ (uint32_t)ap[d]);
-				uint32_t E = vmax_flag(up, __vadd2(eu, M1), f0, f1, 4u << (4 * k));        // bit 2: E extended
-				uint32_t F = vmax_flag(Hl, __vadd2(Fl, M1), f0, f1, 8u << (4 * k));        // bit 3: F extended
-				uint32_t h = vmax_flag(__vadd2(Dg, s3), E, f0, f1, 1u << (4 * k));         // bit 0: E beats the diagonal
-				h = vmax_flag(h, F, f0, f1, 2u << (4 * k));                                // bit 1: F beats both
-				Dg = up; Hl = __vadd2(h, M3); El = E; Fl = F;
-				if (lane == 31) bhe[d - 63] = __byte_perm(Hl, El, 0x7632);
+#define DPX_STEP(k)                                                                                               \
+			{                                                                                                             \
+				const int d = d0 + (k);                                                                                   \
+				uint32_t rv = __shfl_up_sync(DPX_FULL, __byte_perm(Hl, El, 0x7632), 1);                                   \
+				if (lane == 0) rv = bhe[d];                                                                               \
+				uint32_t up = __byte_perm(rv, Hl, 0x5410), eu = __byte_perm(rv, El, 0x5432);                              \
+				uint32_t s3 = prmt(TA, TB, qw ^ (uint32_t)ap[d]);                                                         \
+				uint32_t E = vmax_flag<(4u << (4 * (k)))>(up, __vadd2(eu, M1), f0, f1);  /* bit 2: E extended */            \
+				uint32_t F = vmax_flag<(8u << (4 * (k)))>(Hl, __vadd2(Fl, M1), f0, f1);  /* bit 3: F extended */            \
+				uint32_t h = vmax_flag<(1u << (4 * (k)))>(__vadd2(Dg, s3), E, f0, f1);   /* bit 0: E beats the diagonal */  \
+				h = vmax_flag<(2u << (4 * (k)))>(h, F, f0, f1);                          /* bit 1: F beats both */          \
+				Dg = up; Hl = __vadd2(h, M3); El = E; Fl = F;                                                             \
+				if (lane == 31) bhe[d - 63] = __byte_perm(Hl, El, 0x7632);                                                \
 			}
+			DPX_STEP(0) DPX_STEP(1) DPX_STEP(2) DPX_STEP(3) DPX_STEP(4) DPX_STEP(5) DPX_STEP(6) DPX_STEP(7)
+#undef DPX_STEP
 			fs[(size_t)g * 32] = make_uint2(f0, f1);
 			if (W > 1 && lane == 31) { __threadfence_block(); prog[s] = g + 1; }
 		}
@@ -124,22 +128,58 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1
 	__shared__ int sL, sSame;
 	char *o1 = aln1 + P.out_off, *o2 = aln2 + P.out_off;
 	char *t1 = SMEMF ? (char *)dsm + L.off_st : o1, *t2 = SMEMF ? t1 + ((m + n + 3) & ~3) : o2;
-	if (tid == 0) {
+	if (SMEMF) {
+		if (tid == 0) {
+			int i = n - 1, j = m - 1, state = 0, cont = 0, len = 0;
+			while (i >= 0 && j >= 0) {
+				int ii = i & 63, d = j + ii;
+				uint32_t w = fl[(((size_t)(i >> 6) * G + (d >> 3)) * 32 + (ii >> 1)) * 2 + (ii & 1)];
+				int t = (w >> ((d & 7) << 2)) & 15;
+				if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
+				char c1, c2;
+				if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
+				else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
+				else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
+				t1[len] = c1; t2[len] = c2; len++;
+			}
+			for (; i >= 0; i--, len++) { t1[len] = '-'; t2[len] = (char)qch[i]; }
+			for (; j >= 0; j--, len++) { t1[len] = (char)rch[j]; t2[len] = '-'; }
+			sL = len; sSame = 0;
+		}
+	} else if (warp == 0) {
+		// flags live in HBM/L2: the warp stages a window of DPX_TBW step groups of the current strip (one coalesced
+		// 256-byte row per group) in shared memory, lane 0 walks while the path stays inside it (d = j + i%64 only
+		// ever decreases inside a strip)
+		__shared__ uint2 win[DPX_TBW * 32];
 		int i = n - 1, j = m - 1, state = 0, cont = 0, len = 0;
 		while (i >= 0 && j >= 0) {
-			int ii = i & 63, d = j + ii;
-			uint32_t w = fl[(((size_t)(i >> 6) * G + (d >> 3)) * 32 + (ii >> 1)) * 2 + (ii & 1)];
-			int t = (w >> ((d & 7) << 2)) & 15;
-			if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
-			char c1, c2;
-			if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
-			else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
-			else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
-			t1[len] = c1; t2[len] = c2; len++;
+			const int s = i >> 6, g_hi = (j + (i & 63)) >> 3, g_lo = max(0, g_hi - (DPX_TBW - 1));
+			const uint2 *src = (const uint2 *)fl + (size_t)s * G * 32 + lane;
+			for (int g = g_lo; g <= g_hi; g++) win[(g - g_lo) * 32 + lane] = src[(size_t)g * 32];
+			__syncwarp();
+			if (lane == 0) {
+				const uint32_t *w32 = (const uint32_t *)win;
+				while (i >= 0 && j >= 0 && (i >> 6) == s) {
+					int ii = i & 63, d = j + ii, g = d >> 3;
+					if (g < g_lo) break;
+					uint32_t w = w32[((g - g_lo) * 32 + (ii >> 1)) * 2 + (ii & 1)];
+					int t = (w >> ((d & 7) << 2)) & 15;
+					if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
+					char c1, c2;
+					if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
+					else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
+					else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
+					t1[len] = c1; t2[len] = c2; len++;
+				}
+			}
+			__syncwarp();
+			i = __shfl_sync(DPX_FULL, i, 0); j = __shfl_sync(DPX_FULL, j, 0);
 		}
-		for (; i >= 0; i--, len++) { t1[len] = '-'; t2[len] = (char)qch[i]; }
-		for (; j >= 0; j--, len++) { t1[len] = (char)rch[j]; t2[len] = '-'; }
-		sL = len; sSame = 0;
+		if (lane == 0) {
+			for (; i >= 0; i--, len++) { t1[len] = '-'; t2[len] = (char)qch[i]; }
+			for (; j >= 0; j--, len++) { t1[len] = (char)rch[j]; t2[len] = '-'; }
+			sL = len; sSame = 0;
+		}
 	}
 	if (W == 1) __syncwarp(); else __syncthreads();
 	const int len = sL;
@@ -175,24 +215,89 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1
 }
 
 template <int W, bool SMEMF>
-static int launch_dpx(gsa_ctx *ctx, size_t smem, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
+static int launch_dpx(gsa_ctx *ctx, cudaStream_t stream, size_t smem, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
                       gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
 	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<W, SMEMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_dpx<W, SMEMF><<<nprob, 32 * W, smem, ctx->stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, frag, fblk, bsum);
+	k_dpx<W, SMEMF><<<nprob, 32 * W, smem, stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, frag, fblk, bsum);
 	KERNEL_CHECK(ctx);
 	return GSA_OK;
 }
 
-int gsa_dpx_launch(gsa_ctx *ctx, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
+int gsa_dpx_launch(gsa_ctx *ctx, cudaStream_t stream, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
                    gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
 	if (nprob <= 0) return GSA_OK;
 	switch (cls) {
-	case DPX_CLS_S4: return launch_dpx<1, true>(ctx, DPX_SMEM_S4, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
-	case DPX_CLS_S12: return launch_dpx<1, true>(ctx, DPX_SMEM_S12, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
-	case DPX_CLS_S48: return launch_dpx<4, true>(ctx, DPX_SMEM_S48, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
-	case DPX_CLS_G: return launch_dpx<8, false>(ctx, dpx_layout(max_m, max_n, false).total, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_S4: return launch_dpx<1, true>(ctx, stream, DPX_SMEM_S4, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_S12: return launch_dpx<1, true>(ctx, stream, DPX_SMEM_S12, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_S48: return launch_dpx<4, true>(ctx, stream, DPX_SMEM_S48, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_G4: case DPX_CLS_G8: case DPX_CLS_G16: {
+		// warps per problem: one per strip (up to 16) gives the shortest critical path when problems are few; with many
+		// problems in flight fewer warps waste less on the 72-step stagger between consecutive strips
+		int W = cls == DPX_CLS_G4 ? 4 : cls == DPX_CLS_G8 ? 8 : 16;
+		while (W > 4 && (long long)nprob * W > 4096) W >>= 1;
+		size_t smem = dpx_layout(max_m, max_n, false).total;
+		if (W == 4) return launch_dpx<4, false>(ctx, stream, smem, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+		if (W == 8) return launch_dpx<8, false>(ctx, stream, smem, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+		return launch_dpx<16, false>(ctx, stream, smem, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	}
 	}
 	return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dpx_launch: bad class %d", cls);
+}
+
+// ---- on-box microbenchmark: issue rate of the packed-int16 DPX instructions (the roofline denominator of K3) ------------
+// which: 0 = VIADDMNMX.S16x2 (__viaddmax_s16x2), 1 = VIMNMX.S16x2 (__vmaxs2), 2 = VIADD.16x2 (__vadd2), 3 = VIMNMX3.S16x2
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_dpx_peak(uint32_t *out, int iters, uint32_t b, uint32_t c)
+{
+	uint32_t a[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++) a[k] = threadIdx.x * 0x00010001u + k;
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				if (WHICH == 0) a[k] = __viaddmax_s16x2(a[k], b, c);
+				else if (WHICH == 1) a[k] = __vmaxs2(a[k] ^ b, c);
+				else if (WHICH == 2) a[k] = __vadd2(a[k], b);
+				else a[k] = __vimax3_s16x2(a[k] ^ b, b, c);
+			}
+		}
+	}
+	uint32_t x = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) x ^= a[k];
+	if (x == 0x12345678u) out[0] = x; // keeps the chain alive
+}
+
+extern "C" int gsa_dpx_peak(gsa_ctx *ctx, int which, double *ginstr_per_s)
+{
+	if (!ctx || !ginstr_per_s || which < 0 || which > 3) return GSA_ERR_ARG;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	int sms = 0;
+	CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_counter, 1024));
+	const int iters = 4096, blocks = sms * 8, threads = 256;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; rep++) {
+		cudaEventRecord(e0, ctx->stream);
+		uint32_t *o = (uint32_t *)ctx->d_counter.p + 60;
+		if (which == 0) k_dpx_peak<0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0xFFFFFFFFu, 0x80018001u);
+		else if (which == 1) k_dpx_peak<1><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0x00010001u, 0x80018001u);
+		else if (which == 2) k_dpx_peak<2><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0x00030001u, 0);
+		else k_dpx_peak<3><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0x00010001u, 0x80018001u);
+		KERNEL_CHECK(ctx);
+		cudaEventRecord(e1, ctx->stream);
+		CUDA_TRY(ctx, cudaEventSynchronize(e1));
+		float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+		if (rep > 0 && ms < best) best = ms;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	double n = (double)blocks * threads * iters * 32.0; // DPX instructions (thread level); WHICH 1 and 3 also issue one LOP3 each
+	*ginstr_per_s = n / (best * 1e-3) / 1e9;
+	return GSA_OK;
 }

@@ -19,7 +19,7 @@ struct DpProblem {
 // Size classes.  A fragment pair made of ACGT only goes to the packed-int16 wavefront kernel k_dpx; the class picks the
 // number of warps per problem and where the direction flags live.  Pairs holding any other letter (score 0 against
 // everything, reference src/ksw2_alignment.cpp:258-262) take the scalar kernel k_dp.
-enum { DPX_CLS_S4 = 0, DPX_CLS_S12 = 1, DPX_CLS_S48 = 2, DPX_CLS_G = 3, DPX_CLS_SCALAR = 4, DPX_NCLS = 5 };
+enum { DPX_CLS_S4 = 0, DPX_CLS_S12 = 1, DPX_CLS_S48 = 2, DPX_CLS_G4 = 3, DPX_CLS_G8 = 4, DPX_CLS_G16 = 5, DPX_CLS_SCALAR = 6 };
 
 struct DpxLayout { // byte offsets into the dynamic shared memory of k_dpx
 	int G;          // 8-step groups per strip
@@ -50,7 +50,7 @@ __host__ __device__ inline DpxLayout dpx_layout(int m, int n, bool smem_flags)
 __host__ __device__ inline int64_t dpx_flag_bytes(int m, int n, int cls)
 {
 	if (cls == DPX_CLS_SCALAR) { int w = m < n ? m : n; return (((int64_t)(m + n - 1) * w) + 255) & ~255ll; }
-	if (cls != DPX_CLS_G) return 0;
+	if (cls < DPX_CLS_G4) return 0;
 	DpxLayout L = dpx_layout(m, n, false);
 	return 256ll * L.G * L.nstrips;
 }
@@ -66,9 +66,9 @@ __host__ __device__ inline int dpx_class(int m, int n, bool has_other)
 	if (t <= DPX_SMEM_S4) return DPX_CLS_S4;
 	if (t <= DPX_SMEM_S12) return DPX_CLS_S12;
 	if (t <= DPX_SMEM_S48) return DPX_CLS_S48;
-	return DPX_CLS_G;
+	return n <= 256 ? DPX_CLS_G4 : n <= 512 ? DPX_CLS_G8 : DPX_CLS_G16; // one warp per 64-row strip, up to 16
 }
 
 // launches k_dpx over problems [0, nprob) that all belong to class cls and are no larger than max_m x max_n (dpx.cu)
-int gsa_dpx_launch(gsa_ctx *ctx, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
+int gsa_dpx_launch(gsa_ctx *ctx, cudaStream_t stream, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
                    gsa_frag *frag, const int32_t *fblk, unsigned int *bsum);

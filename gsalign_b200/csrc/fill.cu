@@ -17,6 +17,7 @@
 // the final block order are O(#blocks) host logic (see gsa_impl_fill at the bottom).
 #include "dpx.cuh"
 #include "fm.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -200,39 +201,6 @@ static int launch_dp(gsa_ctx *ctx, const DpProblem *prob, int nprob, int dim_cap
 	return GSA_OK;
 }
 
-// Problems are sorted by (class, size).  ACGT-only pairs go to the packed-int16 wavefront kernel (dpx.cu), one launch per
-// size class; the rest take the scalar kernel, binned by max(m,n) so that small ones get small shared memory.
-static int run_dp_binned(gsa_ctx *ctx, std::vector<DpProblem> &hp, DpProblem *d_prob, uint8_t *flags, char *a1, char *a2, int32_t *out_len, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
-{
-	std::stable_sort(hp.begin(), hp.end(), [](const DpProblem &a, const DpProblem &b) {
-		if (a.cls != b.cls) return a.cls < b.cls;
-		return std::max(a.m, a.n) < std::max(b.m, b.n);
-	});
-	CUDA_TRY(ctx, cudaMemcpyAsync(d_prob, hp.data(), hp.size() * sizeof(DpProblem), cudaMemcpyHostToDevice, ctx->stream));
-	size_t beg = 0;
-	for (int cls = 0; cls < DPX_CLS_SCALAR; cls++) {
-		size_t end = beg;
-		int max_m = 1, max_n = 1;
-		for (; end < hp.size() && hp[end].cls == cls; end++) { max_m = std::max(max_m, hp[end].m); max_n = std::max(max_n, hp[end].n); }
-		GSA_TRY(gsa_dpx_launch(ctx, cls, max_m, max_n, d_prob + beg, (int)(end - beg), flags, a1, a2, out_len, frag, fblk, bsum));
-		beg = end;
-	}
-	const int caps[] = {32, 128, 512, 2048, DP_MAX_DIM};
-	for (int c = 0; c < 5; c++) {
-		size_t end = beg;
-		while (end < hp.size() && std::max(hp[end].m, hp[end].n) <= caps[c]) end++;
-		int cnt = (int)(end - beg);
-		if (cnt > 0) {
-			if (c == 0) GSA_TRY(launch_dp<32>(ctx, d_prob + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
-			else if (c == 1) GSA_TRY(launch_dp<64>(ctx, d_prob + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
-			else GSA_TRY(launch_dp<256>(ctx, d_prob + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
-		}
-		beg = end;
-	}
-	if (beg != hp.size()) return gsa_fail(ctx, GSA_ERR_LIMIT, "DP fragment longer than %d", DP_MAX_DIM);
-	return GSA_OK;
-}
-
 struct Ws3 {
 	gsa_ctx *ctx; int next = 0; int rc = GSA_OK;
 	explicit Ws3(gsa_ctx *c) : ctx(c) {}
@@ -245,6 +213,87 @@ struct Ws3 {
 		return (T *)b.p;
 	}
 };
+
+// ---- device-side binning ------------------------------------------------------------------------------------------------
+// Problems are ordered by (bin, size descending) with one radix sort; only the per-bin counts come back to the host.
+// Bins 0..5: ACGT-only pairs for the packed-int16 wavefront kernel (dpx.cu), one launch per size class; the next five:
+// pairs holding other letters for the scalar kernel, by max(m,n) so that small ones get small shared memory; last: too long.
+#define DP_BIN_SCALAR DPX_CLS_SCALAR
+#define DP_BIN_TOOLONG (DP_BIN_SCALAR + 5)
+#define DP_NBINS (DP_BIN_TOOLONG + 1)
+struct DpStats { unsigned int count[DP_NBINS]; int max_m[DPX_CLS_SCALAR], max_n[DPX_CLS_SCALAR]; unsigned long long cells; };
+
+__global__ void k_dp_keys(const DpProblem *prob, int n, uint32_t *key, uint32_t *idx, DpStats *st)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int m = prob[i].m, q = prob[i].n, cls = prob[i].cls, big = max(m, q), bin;
+	if (big > DP_MAX_DIM) bin = DP_BIN_TOOLONG;
+	else if (cls < DPX_CLS_SCALAR) { bin = cls; atomicMax(&st->max_m[cls], m); atomicMax(&st->max_n[cls], q); }
+	else bin = DP_BIN_SCALAR + (big <= 32 ? 0 : big <= 128 ? 1 : big <= 512 ? 2 : big <= 2048 ? 3 : 4);
+	atomicAdd(&st->count[bin], 1u);
+	atomicAdd(&st->cells, (unsigned long long)m * (unsigned long long)q);
+	key[i] = ((uint32_t)bin << 12) | (uint32_t)(4095 - min(4095, (m + q) >> 2));
+	idx[i] = (uint32_t)i;
+}
+
+__global__ void k_dp_permute(const DpProblem *in, const uint32_t *idx, DpProblem *out, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = in[idx[i]];
+}
+
+// d_prob: the problems in any order (device); d_sorted: scratch of the same size.  Records ctx->ev[10]/[11] around the DP
+// launches alone when timed.
+static int run_dp_binned(gsa_ctx *ctx, Ws3 &ws, const DpProblem *d_prob, DpProblem *d_sorted, int ndp, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
+                         gsa_frag *frag, const int32_t *fblk, unsigned int *bsum, cudaEvent_t e0, cudaEvent_t e1)
+{
+	uint32_t *key_in = ws.get<uint32_t>(ndp), *key_out = ws.get<uint32_t>(ndp), *idx_in = ws.get<uint32_t>(ndp), *idx_out = ws.get<uint32_t>(ndp);
+	if (ws.rc) return ws.rc;
+	GSA_TRY(gsa_ensure(ctx, ctx->d_counter, 1024));
+	DpStats *d_st = (DpStats *)((char *)ctx->d_counter.p + 512);
+	CUDA_TRY(ctx, cudaMemsetAsync(d_st, 0, sizeof(DpStats), ctx->stream));
+	k_dp_keys<<<gsa_grid(ndp, 256), 256, 0, ctx->stream>>>(d_prob, ndp, key_in, idx_in, d_st);
+	KERNEL_CHECK(ctx);
+	size_t bytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, idx_in, idx_out, ndp, 0, 16, ctx->stream);
+	GSA_TRY(gsa_ensure(ctx, ctx->d_cub, bytes));
+	CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, bytes, key_in, key_out, idx_in, idx_out, ndp, 0, 16, ctx->stream));
+	ctx->tm.launches += 3;
+	k_dp_permute<<<gsa_grid(ndp, 256), 256, 0, ctx->stream>>>(d_prob, idx_out, d_sorted, ndp);
+	KERNEL_CHECK(ctx);
+	DpStats *st = (DpStats *)((char *)ctx->h_small.p + 256);
+	CUDA_TRY(ctx, cudaMemcpyAsync(st, d_st, sizeof(DpStats), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->tm.dp_cells = (int64_t)st->cells;
+	if (st->count[DP_BIN_TOOLONG]) return gsa_fail(ctx, GSA_ERR_LIMIT, "DP fragment longer than %d", DP_MAX_DIM);
+	if (e0) CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+	// the big problems (classes G8 / G16, largest first) run on a side stream so that their long critical paths overlap
+	// the many small ones
+	size_t off[DP_NBINS + 1]; off[0] = 0;
+	for (int b = 0; b < DP_NBINS; b++) off[b + 1] = off[b] + st->count[b];
+	const bool side = (st->count[DPX_CLS_G8] + st->count[DPX_CLS_G16]) > 0;
+	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0)); }
+	const int order[DPX_CLS_SCALAR] = {DPX_CLS_G16, DPX_CLS_G8, DPX_CLS_S48, DPX_CLS_G4, DPX_CLS_S12, DPX_CLS_S4};
+	for (int cls : order) {
+		cudaStream_t st_cls = cls >= DPX_CLS_G8 ? ctx->stream2 : ctx->stream;
+		GSA_TRY(gsa_dpx_launch(ctx, st_cls, cls, std::max(1, st->max_m[cls]), std::max(1, st->max_n[cls]), d_sorted + off[cls], (int)st->count[cls], flags, a1, a2, out_len, frag, fblk, bsum));
+	}
+	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
+	size_t beg = off[DP_BIN_SCALAR];
+	const int caps[] = {32, 128, 512, 2048, DP_MAX_DIM};
+	for (int c = 0; c < 5; c++) {
+		int cnt = (int)st->count[DP_BIN_SCALAR + c];
+		if (cnt > 0) {
+			if (c == 0) GSA_TRY(launch_dp<32>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
+			else if (c == 1) GSA_TRY(launch_dp<64>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
+			else GSA_TRY(launch_dp<256>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
+		}
+		beg += cnt;
+	}
+	if (e1) CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+	return GSA_OK;
+}
 
 static int scan_ex64(gsa_ctx *ctx, const int64_t *in, int64_t *out, int64_t n)
 {
@@ -307,16 +356,9 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 		if (ws.rc) return ws.rc;
 		k_dp_problems<<<gsa_grid(ndp, 128), 128, 0, ctx->stream>>>(dp_idx, ndp, frag, row_off, flag_off, dp_cls, seq, d_prob);
 		KERNEL_CHECK(ctx);
-		std::vector<DpProblem> hp((size_t)ndp);
-		CUDA_TRY(ctx, cudaMemcpyAsync(hp.data(), d_prob, (size_t)ndp * sizeof(DpProblem), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-		for (const DpProblem &p : hp) {
-			if (std::max(p.m, p.n) > DP_MAX_DIM) return gsa_fail(ctx, GSA_ERR_LIMIT, "DP fragment longer than %d", DP_MAX_DIM);
-			ctx->tm.dp_cells += (int64_t)p.m * p.n;
-		}
-		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
-		GSA_TRY(run_dp_binned(ctx, hp, d_prob, flags, a1, a2, nullptr, frag, fblk, bsum));
-		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
+		DpProblem *d_sorted = ws.get<DpProblem>(ndp);
+		if (ws.rc) return ws.rc;
+		GSA_TRY(run_dp_binned(ctx, ws, d_prob, d_sorted, (int)ndp, flags, a1, a2, nullptr, frag, fblk, bsum, ctx->ev[10], ctx->ev[11]));
 		ctx->dp_timed = true;
 	}
 	// ---- results to pinned host memory ---------------------------------------------------------------------
@@ -361,7 +403,7 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 	int64_t rb = ref_off[n_pairs], qb = qry_off[n_pairs];
 	char *d_ref = ws.get<char>(rb + 1), *d_qry = ws.get<char>(qb + 1), *d_o1 = ws.get<char>(rb + qb + 1), *d_o2 = ws.get<char>(rb + qb + 1);
 	int32_t *d_len = ws.get<int32_t>(n_pairs);
-	DpProblem *d_prob = ws.get<DpProblem>(n_pairs);
+	DpProblem *d_prob = ws.get<DpProblem>(n_pairs), *d_sorted = ws.get<DpProblem>(n_pairs);
 	if (ws.rc) return ws.rc;
 	std::vector<DpProblem> hp((size_t)n_pairs);
 	int64_t fbytes = 0;
@@ -381,11 +423,10 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 	if (ws.rc) return ws.rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_ref, ref, (size_t)rb, cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_qry, qry, (size_t)qb, cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_prob, hp.data(), hp.size() * sizeof(DpProblem), cudaMemcpyHostToDevice, ctx->stream));
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
-	cudaEventRecord(e0, ctx->stream);
-	int rc = run_dp_binned(ctx, hp, d_prob, flags, d_o1, d_o2, d_len, nullptr, nullptr, nullptr);
-	cudaEventRecord(e1, ctx->stream);
+	int rc = run_dp_binned(ctx, ws, d_prob, d_sorted, n_pairs, flags, d_o1, d_o2, d_len, nullptr, nullptr, nullptr, e0, e1);
 	if (rc == GSA_OK) {
 		CUDA_TRY(ctx, cudaMemcpyAsync(out1, d_o1, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(out2, d_o2, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));

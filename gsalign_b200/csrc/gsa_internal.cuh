@@ -65,6 +65,8 @@ struct Piece {
 struct gsa_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t stream2 = nullptr; // side stream (forked from / joined to `stream` with ev_fork / ev_join)
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	cudaEvent_t ev[12] = {};        // 0/1 h2d, 2/3 seed, 4/5 cluster, 6/7 fill, 8/9 k_seed, 10/11 k_dp
 	bool own_stream = true; bool dp_timed = false;
 	std::string err;
@@ -87,6 +89,7 @@ struct gsa_ctx {
 
 	// K1 output / K2 working set
 	int64_t n_seeds = 0;
+	double seed_density = 0;       // highest seeds per query bp seen so far (sizes the raw seed buffer)
 	DevBuf d_counter;              // small block of device counters
 	DevBuf d_sq, d_sr, d_sl;       // seeds: qPos (i32), rPos (i64), len (i32), sorted by (PosDiff,qPos) after gsa_seed
 	DevBuf d_tmp[64];              // scratch arrays for K2/K3 (sized on demand)

@@ -17,6 +17,7 @@
 // One thread walks one chunk; all chunks of the contig are in flight together.
 #include "fm.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
 
 // ---- K0: 2-bit packing of the query + invalid-base bitmap -----------------------------------------
 // one thread per 32 bases: reads 32 chars (two 16-byte loads), writes two packed words + one bitmap word
@@ -233,10 +234,13 @@ int gsa_impl_seed(gsa_ctx *ctx)
 	int k = ctx->prm.min_seed_len < GSA_KTAB_MAX_K ? ctx->prm.min_seed_len : GSA_KTAB_MAX_K;
 	GSA_TRY(gsa_impl_build_ktab(ctx, k));
 	uint32_t nchunks = (ctx->qlen + GSA_SEED_CHUNK - 1) / GSA_SEED_CHUNK;
-	GSA_TRY(gsa_ensure(ctx, ctx->d_counter, 256));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_counter, 1024));
 	unsigned long long *d_count = (unsigned long long *)ctx->d_counter.p;
 	// raw (unsorted) seeds go to scratch 0..2, sorted seeds to d_sq/d_sr/d_sl
+	// capacity: 1 seed / 32 bp covers default mode on any divergence; a denser contig (sensitive mode, repeats) reruns
+	// once and the density is remembered so that later contigs of the same run do not
 	unsigned long long cap = (unsigned long long)ctx->qlen / 32 + (1u << 16);
+	cap = std::max(cap, (unsigned long long)(1.3 * ctx->seed_density * ctx->qlen) + (1u << 16));
 	unsigned long long produced = 0;
 	for (int attempt = 0; attempt < 2; attempt++) {
 		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[0], cap * 4));
@@ -262,6 +266,7 @@ int gsa_impl_seed(gsa_ctx *ctx)
 	if (produced > cap) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_seed: seed buffer overflow");
 	int64_t n = (int64_t)produced;
 	ctx->n_seeds = n;
+	if (ctx->qlen > 0) ctx->seed_density = std::max(ctx->seed_density, (double)produced / ctx->qlen);
 	GSA_TRY(gsa_ensure(ctx, ctx->d_sq, (size_t)(n + 1) * 4));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_sr, (size_t)(n + 1) * 8));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_sl, (size_t)(n + 1) * 4));
