@@ -55,7 +55,7 @@ class Timing(C.Structure):
 
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
-           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak"]
+           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared"]
 
 
 def load_library() -> C.CDLL:
@@ -82,12 +82,19 @@ def _as_array(ptr, n, dtype):
 class Aligner:
     """One context per GPU; mirrors the per-contig loop of GenomeComparison (reference src/GSAlign.cpp:473)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, owner: "Aligner | None" = None):
+        """owner: create a lane on the owner's GPU that shares its uploaded index (gsa_create_shared)"""
         self.lib = load_library()
         self.ctx = C.c_void_p()
-        rc = self.lib.gsa_create(C.c_int(device), C.byref(self.ctx))
-        if rc != 0:
-            raise GsaError(f"gsa_create(device={device}) failed with {rc}: no usable B200; there is no CPU fallback")
+        self._owner = owner
+        if owner is not None:
+            rc = self.lib.gsa_create_shared(owner.ctx, C.byref(self.ctx))
+            if rc != 0:
+                raise GsaError(f"gsa_create_shared failed with {rc}: {self.lib.gsa_last_error(owner.ctx).decode()}")
+        else:
+            rc = self.lib.gsa_create(C.c_int(device), C.byref(self.ctx))
+            if rc != 0:
+                raise GsaError(f"gsa_create(device={device}) failed with {rc}: no usable B200; there is no CPU fallback")
         self._keep = None
 
     def close(self):

@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" entry points of include/gsalign_b200.h.
 #include "gsa_internal.cuh"
+#include "dpx.cuh"
 #include <stdarg.h>
 #include <string.h>
 #include <chrono>
@@ -62,6 +63,34 @@ int gsa_create(int device, gsa_ctx **out)
 	if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
 	if (gsa_ensure_host(ctx, ctx->h_small, 1 << 20) != GSA_OK) { delete ctx; return GSA_ERR_NOMEM; }
+	if (gsa_dpx_init_device(ctx) != GSA_OK || gsa_dp_init_device(ctx) != GSA_OK) { fprintf(stderr, "gsalign_b200: %s\n", ctx->err.c_str()); delete ctx; return GSA_ERR_CUDA; }
+	*out = ctx;
+	return GSA_OK;
+}
+
+int gsa_create_shared(gsa_ctx *owner, gsa_ctx **out)
+{
+	if (!out) return GSA_ERR_ARG;
+	*out = nullptr;
+	if (!owner) return GSA_ERR_ARG;
+	if (!owner->have_index) return gsa_fail(owner, GSA_ERR_ARG, "gsa_create_shared: the owner has no index yet");
+	CUDA_TRY(owner, cudaSetDevice(owner->device));
+	// the k-mer prefix table of the owner's current parameters is shared too (a lane with another seed length builds its own)
+	int k = owner->prm.min_seed_len < GSA_KTAB_MAX_K ? owner->prm.min_seed_len : GSA_KTAB_MAX_K;
+	GSA_TRY(gsa_impl_build_ktab(owner, k));
+	CUDA_TRY(owner, cudaStreamSynchronize(owner->stream));
+	gsa_ctx *ctx = nullptr;
+	int rc = gsa_create(owner->device, &ctx);
+	if (rc != GSA_OK) return rc;
+	ctx->prm = owner->prm; ctx->ix = owner->ix; ctx->N = owner->N; ctx->cend = owner->cend;
+	ctx->contig_off = owner->contig_off; ctx->contig_len = owner->contig_len;
+	ctx->shares_index = true;
+	size_t cb = ctx->cend.size() * sizeof(ContigEnd);
+	if ((rc = gsa_ensure(ctx, ctx->d_cend, cb ? cb : 16)) != GSA_OK || cudaMemcpy(ctx->d_cend.p, ctx->cend.data(), cb, cudaMemcpyHostToDevice) != cudaSuccess) {
+		gsa_destroy(ctx);
+		return gsa_fail(owner, GSA_ERR_CUDA, "gsa_create_shared: cannot copy the contig table");
+	}
+	ctx->have_index = true;
 	*out = ctx;
 	return GSA_OK;
 }

@@ -1,27 +1,29 @@
-// dpx.cu -- K3's DP kernel: global affine-gap alignment as a register-resident anti-diagonal wavefront on packed
-// int16 pairs (DPX: VIADD.16x2, VIMNMX.S16x2 with predicate outputs).
+// dpx.cu -- K3's DP kernels: global affine-gap alignment as a register-resident anti-diagonal wavefront on packed
+// int16 pairs (DPX: VIADD.16x2, VIMNMX.S16x2 with predicate outputs), and its traceback.
 //
 // Same recurrence, tie rules and traceback as fill.cu's scalar kernel (ksw_extz2_sse / ksw_backtrack semantics,
 // reference src/ksw2_alignment.cpp:25-249; restated in SURVEY.md 8a A9), for fragment pairs made of ACGT only:
 //     E'(i,j) = max(H(i-1,j), E'(i-1,j) - 1)        E' = E + 3 (gap open 2 + extend 1 folded into H)
 //     F'(i,j) = max(H(i,j-1), F'(i,j-1) - 1)
 //     H(i,j)  = max(H(i-1,j-1) + s, E' - 3, F' - 3)  diag first, E only if strictly greater, F only if greater than both
-// Work split: the query rows are cut into strips of 64; a warp sweeps a strip along its anti-diagonals with lane p
-// holding rows 2p (low half-word) and 2p+1 (high half-word), so both halves of a register sit on the same
-// anti-diagonal.  Per step a lane needs H and E' of the row above (one packed __shfl_up; lane 0 reads the last row of the
-// strip above from shared memory, lane 31 writes its own there for the strip below) and one 16-bit shared-memory
-// load of the two reference bases.  Cells before column 0 are fixed points of the recurrence (sentinel base scores -1
-// against everything: H(i-1,-1) - 1 = H(i,-1)), cells past the last column are garbage nobody reads, so there is no
-// per-step bounds logic.  The match score comes out of one PRMT used as an 8-entry table on q XOR r.
-// Four decision bits per cell (E>diag, F>both, E extended, F extended) are the VIMNMX predicates, collected over 8 steps
-// into one word per row and written as 256-byte warp rows (shared memory for small problems, HBM otherwise).
-// Strips of one problem run on W warps as a pipeline: strip s+1 trails strip s by 72 steps, synchronised by a
-// per-strip progress counter in shared memory.
+// k_dpx: the query rows are cut into strips of 64; a warp sweeps a strip along its anti-diagonals with lane p holding
+// rows 2p (low half-word) and 2p+1 (high half-word), so both halves of a register sit on the same anti-diagonal.
+// Per step a lane needs H and E' of the row above (one packed __shfl_up; lane 0 reads the last row of the strip above
+// from shared memory, lane 31 writes its own there for the strip below) and one 16-bit shared-memory load of the two
+// reference bases.  Cells before column 0 are fixed points of the recurrence (sentinel base scores -1 against
+// everything: H(i-1,-1) - 1 = H(i,-1)), cells past the last column are garbage nobody reads, so there is no per-step
+// bounds logic.  The match score comes out of one PRMT used as an 8-entry table on q XOR r.  Four decision bits per
+// cell (E>diag, F>both, E extended, F extended) are the VIMNMX predicates, collected over 8 steps into one word per
+// row and written as coalesced 256-byte warp rows to the flag pool (HBM; L2-resident at these sizes).
+// Strips of one problem run one after the other on one warp (small problems, several problems per CTA) or on W warps as
+// a pipeline: strip s+1 trails strip s by 72 steps, synchronised by a per-strip progress counter in shared memory.
+// Traceback: warp 0 of the problem stages windows of the flag rows back in shared memory (coalesced) and lane 0 walks
+// them (ksw_backtrack), writing both rows right-aligned into the problem's slot of the row pools, so nothing has to be
+// reversed afterwards.
 #include "dpx.cuh"
 #include "fm.cuh"
 
 #define DPX_FULL 0xffffffffu
-#define DPX_TBW 16   // traceback window, in 8-step groups
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
@@ -34,8 +36,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 	return d;
 }
 
-// max per half-word; ORs `bit` into f_lo / f_hi where b won strictly (a < b).  ptxas folds the max + setp pair into
-// one VIMNMX.S16x2 with two predicate outputs and predicates the two ORs on them.
+// max per half-word; ORs BIT into f_lo / f_hi where b won strictly (a < b).  ptxas folds the max + setp.eq pair into
+// one VIMNMX.S16x2 with two predicate outputs (the pattern __vibmax_s16x2 uses) and predicates the two ORs on them.
 template <uint32_t BIT>
 __device__ __forceinline__ uint32_t vmax_flag(uint32_t a, uint32_t b, uint32_t &f_lo, uint32_t &f_hi)
 {
@@ -53,22 +55,27 @@ __device__ __forceinline__ uint32_t vmax_flag(uint32_t a, uint32_t b, uint32_t &
 	return v;
 }
 
-template <int W, bool SMEMF>
-__global__ void __launch_bounds__(32 * W)
-k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1, char *aln2, int32_t *out_len, gsa_frag *frag,
-      const int32_t *fblk, unsigned int *bsum)
+// W warps per problem and NP problems per CTA (NP > 1 only with W == 1); slot = shared-memory bytes per problem.
+// STAGE: rows are assembled in shared memory and copied out coalesced (small problems); otherwise lane 0 writes them
+// straight to the row pools.
+template <int W, int NP, bool STAGE>
+__global__ void __launch_bounds__(32 * W * NP)
+k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t slot, char *aln1, char *aln2, int32_t *out_len, int64_t *out_start,
+      gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
-	extern __shared__ uint32_t dsm[];
-	const int pi = blockIdx.x;
+	extern __shared__ uint32_t dsm_all[];
+	const int tid = threadIdx.x % (32 * W), lane = tid & 31, warp = tid >> 5, sub = threadIdx.x / (32 * W);
+	const int pi = blockIdx.x * NP + sub;
 	if (pi >= nprob) return;
+	uint32_t *dsm = dsm_all + (size_t)sub * (slot >> 2);
 	const DpProblem P = prob[pi];
-	const int m = P.m, n = P.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const DpxLayout L = dpx_layout(m, n, SMEMF);
+	const int m = P.m, n = P.n;
+	const DpxLayout L = dpx_layout(m, n, STAGE);
 	uint32_t *bhe = dsm + (L.off_bhe >> 2) + 64;                                   // bhe[j] = {H(i0-1,j), E'(i0-1,j)}
 	uint16_t *a16 = (uint16_t *)((char *)dsm + L.off_a16) + 64;                    // a16[k] = selector halves for columns k, k-1
 	volatile int *prog = (volatile int *)((char *)dsm + L.off_prog);
 	unsigned char *qch = (unsigned char *)dsm + L.off_qch, *rch = (unsigned char *)dsm + L.off_rch;
-	uint32_t *fl = SMEMF ? dsm + (L.off_flags >> 2) : (uint32_t *)(gflags + P.flag_off);
+	uint2 *fl = (uint2 *)(gflags + P.flag_off);
 	const int G = L.G, cols = 8 * G + 8;
 
 	// ---- stage both fragments, the reference selector array and the row above strip 0 --------------------------
@@ -80,7 +87,7 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1
 		a16[k] = (uint16_t)(c0 | 0x80 | (c1 << 8) | 0x8000);
 		bhe[k] = pack16(-(3 + k), DP_NEG);
 	}
-	for (int k = tid; k < L.nstrips; k += 32 * W) prog[k] = 0;
+	if (W > 1) for (int k = tid; k < L.nstrips; k += 32 * W) prog[k] = 0;
 	if (W == 1) __syncwarp(); else __syncthreads();
 
 	const uint32_t M1 = 0xFFFFFFFFu, M3 = 0xFFFDFFFDu, TA = 0x02020204u, TB = 0x02020202u;
@@ -92,7 +99,8 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1
 		uint32_t Dg = pack16(r0 == 0 ? 0 : -(2 + r0), -(2 + r1));   // H(i-1,-1)
 		const uint32_t qw = (uint32_t)(r0 < n ? gsa_nt4(qch[r0]) : 0) | ((uint32_t)(r1 < n ? gsa_nt4(qch[r1]) : 0) << 8);
 		const uint16_t *ap = a16 - 2 * lane;
-		uint2 *fs = (uint2 *)fl + (size_t)s * G * 32 + lane;
+		uint2 *fs = fl + (size_t)s * G * 32 + lane;
+		if (W == 1 && s > 0) __syncwarp(); // lane 31's boundary row of the previous strip is complete
 		for (int g = 0; g < Gs; g++) {
 			if (W > 1 && s > 0) {
 				if (lane == 0) { int need = min(g + 9, G); while (prog[s - 1] < need) { } }
@@ -123,124 +131,109 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, char *aln1
 		if (W > 1 && lane == 31) { __threadfence_block(); prog[s] = G; } // a short last strip still releases its (absent) follower
 	}
 	if (W == 1) __syncwarp(); else __syncthreads();
+	if (warp != 0) return;
 
-	// ---- traceback (ksw_backtrack, src/ksw2_alignment.cpp:25-68); rows are produced back to front ------------------
-	__shared__ int sL, sSame;
+	// ---- traceback (ksw_backtrack, reference src/ksw2_alignment.cpp:25-68) by warp 0 ------------------------------
+	// The flags were written to the pool (HBM / L2): the warp stages a window of up to DPX_TBW step groups of the current
+	// strip (one coalesced 256-byte row per group) in shared memory and lane 0 walks while the path stays inside it
+	// (d = j + i%64 only ever decreases inside a strip).  Rows come out back to front, so they are written from the end of
+	// the problem's slot downwards: nothing is reversed afterwards.
+	uint2 *win = (uint2 *)((char *)dsm + L.off_win);
 	char *o1 = aln1 + P.out_off, *o2 = aln2 + P.out_off;
-	char *t1 = SMEMF ? (char *)dsm + L.off_st : o1, *t2 = SMEMF ? t1 + ((m + n + 3) & ~3) : o2;
-	if (SMEMF) {
-		if (tid == 0) {
-			int i = n - 1, j = m - 1, state = 0, cont = 0, len = 0;
-			while (i >= 0 && j >= 0) {
-				int ii = i & 63, d = j + ii;
-				uint32_t w = fl[(((size_t)(i >> 6) * G + (d >> 3)) * 32 + (ii >> 1)) * 2 + (ii & 1)];
+	char *t1 = STAGE ? (char *)dsm + L.off_st : o1, *t2 = STAGE ? t1 + ((m + n + 3) & ~3) : o2;
+	const int wgroups = min(G, DPX_TBW);
+	int i = n - 1, j = m - 1, state = 0, cont = 0, pos = m + n, same = 0;
+	__threadfence_block();
+	while (i >= 0 && j >= 0) {
+		const int s = i >> 6, g_hi = (j + (i & 63)) >> 3, g_lo = max(0, g_hi - (wgroups - 1));
+		const uint2 *src = fl + (size_t)s * G * 32 + lane;
+		for (int g = g_lo; g <= g_hi; g++) win[(g - g_lo) * 32 + lane] = __ldcg(src + (size_t)g * 32);
+		__syncwarp();
+		if (lane == 0) {
+			const uint32_t *w32 = (const uint32_t *)win;
+			while (i >= 0 && j >= 0 && (i >> 6) == s) {
+				int ii = i & 63, d = j + ii, g = d >> 3;
+				if (g < g_lo) break;
+				uint32_t w = w32[((g - g_lo) * 32 + (ii >> 1)) * 2 + (ii & 1)];
 				int t = (w >> ((d & 7) << 2)) & 15;
 				if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
 				char c1, c2;
-				if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
-				else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
+				if (state == 0) {
+					c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--;
+					if (!STAGE) same += gsa_nt4((unsigned char)c1) == gsa_nt4((unsigned char)c2);
+				} else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
 				else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
-				t1[len] = c1; t2[len] = c2; len++;
+				pos--; t1[pos] = c1; t2[pos] = c2;
 			}
-			for (; i >= 0; i--, len++) { t1[len] = '-'; t2[len] = (char)qch[i]; }
-			for (; j >= 0; j--, len++) { t1[len] = (char)rch[j]; t2[len] = '-'; }
-			sL = len; sSame = 0;
 		}
-	} else if (warp == 0) {
-		// flags live in HBM/L2: the warp stages a window of DPX_TBW step groups of the current strip (one coalesced
-		// 256-byte row per group) in shared memory, lane 0 walks while the path stays inside it (d = j + i%64 only
-		// ever decreases inside a strip)
-		__shared__ uint2 win[DPX_TBW * 32];
-		int i = n - 1, j = m - 1, state = 0, cont = 0, len = 0;
-		while (i >= 0 && j >= 0) {
-			const int s = i >> 6, g_hi = (j + (i & 63)) >> 3, g_lo = max(0, g_hi - (DPX_TBW - 1));
-			const uint2 *src = (const uint2 *)fl + (size_t)s * G * 32 + lane;
-			for (int g = g_lo; g <= g_hi; g++) win[(g - g_lo) * 32 + lane] = src[(size_t)g * 32];
-			__syncwarp();
-			if (lane == 0) {
-				const uint32_t *w32 = (const uint32_t *)win;
-				while (i >= 0 && j >= 0 && (i >> 6) == s) {
-					int ii = i & 63, d = j + ii, g = d >> 3;
-					if (g < g_lo) break;
-					uint32_t w = w32[((g - g_lo) * 32 + (ii >> 1)) * 2 + (ii & 1)];
-					int t = (w >> ((d & 7) << 2)) & 15;
-					if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
-					char c1, c2;
-					if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
-					else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
-					else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
-					t1[len] = c1; t2[len] = c2; len++;
-				}
-			}
-			__syncwarp();
-			i = __shfl_sync(DPX_FULL, i, 0); j = __shfl_sync(DPX_FULL, j, 0);
-		}
-		if (lane == 0) {
-			for (; i >= 0; i--, len++) { t1[len] = '-'; t2[len] = (char)qch[i]; }
-			for (; j >= 0; j--, len++) { t1[len] = (char)rch[j]; t2[len] = '-'; }
-			sL = len; sSame = 0;
-		}
+		__syncwarp();
+		i = __shfl_sync(DPX_FULL, i, 0); j = __shfl_sync(DPX_FULL, j, 0);
 	}
-	if (W == 1) __syncwarp(); else __syncthreads();
-	const int len = sL;
-	int same = 0;
-	if (SMEMF) {
-		for (int k = tid; k < len; k += 32 * W) {
-			char a = t1[len - 1 - k], b = t2[len - 1 - k];
+	if (lane == 0) {
+		for (; i >= 0; i--) { pos--; t1[pos] = '-'; t2[pos] = (char)qch[i]; }
+		for (; j >= 0; j--) { pos--; t1[pos] = (char)rch[j]; t2[pos] = '-'; }
+	}
+	pos = __shfl_sync(DPX_FULL, pos, 0);
+	const int len = m + n - pos;
+	if (STAGE) { // coalesced copy-out + CountIdenticalPairs (src/ProcessCandidateAlignment.cpp:38-47; '-' is class 4, never equal to ACGT)
+		__syncwarp();
+		for (int k = pos + lane; k < m + n; k += 32) {
+			char a = t1[k], b = t2[k];
 			o1[k] = a; o2[k] = b;
-			same += gsa_nt4((unsigned char)a) == gsa_nt4((unsigned char)b); // CountIdenticalPairs: '-' is class 4, never equal to ACGT
+			same += gsa_nt4((unsigned char)a) == gsa_nt4((unsigned char)b);
 		}
-	} else {
-		for (int k = tid; k < len / 2; k += 32 * W) {
-			char a = o1[k], b = o1[len - 1 - k]; o1[k] = b; o1[len - 1 - k] = a;
-			a = o2[k]; b = o2[len - 1 - k]; o2[k] = b; o2[len - 1 - k] = a;
-		}
-		__syncthreads();
-		for (int k = tid; k < len; k += 32 * W) same += gsa_nt4((unsigned char)o1[k]) == gsa_nt4((unsigned char)o2[k]);
+		for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(DPX_FULL, same, o);
 	}
-	for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(DPX_FULL, same, o);
-	if (W > 1) {
-		if (lane == 0 && same) atomicAdd(&sSame, same);
-		__syncthreads();
-		same = sSame;
-	}
-	if (tid == 0) {
-		if (out_len) out_len[P.frag] = len;
+	if (lane == 0) {
+		if (out_len) { out_len[P.frag] = len; out_start[P.frag] = P.out_off + pos; }
 		if (frag) {
-			frag[P.frag].aln_off = P.out_off; frag[P.frag].aln_len = len;
+			frag[P.frag].aln_off = P.out_off + pos; frag[P.frag].aln_len = len;
 			int b = fblk[P.frag];
 			atomicAdd(bsum + 2 * b, (unsigned)len); atomicAdd(bsum + 2 * b + 1, (unsigned)same);
 		}
 	}
 }
 
-template <int W, bool SMEMF>
-static int launch_dpx(gsa_ctx *ctx, cudaStream_t stream, size_t smem, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
-                      gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+template <int W, int NP, bool STAGE>
+static int launch_dpx(gsa_ctx *ctx, cudaStream_t stream, uint32_t slot, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
+                      int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<W, SMEMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_dpx<W, SMEMF><<<nprob, 32 * W, smem, stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, frag, fblk, bsum);
+	size_t smem = (size_t)slot * NP;
+	k_dpx<W, NP, STAGE><<<(nprob + NP - 1) / NP, 32 * W * NP, smem, stream>>>(prob, nprob, ctx->ix, flags, slot, a1, a2, out_len, out_start, frag, fblk, bsum);
 	KERNEL_CHECK(ctx);
 	return GSA_OK;
 }
 
-int gsa_dpx_launch(gsa_ctx *ctx, cudaStream_t stream, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
-                   gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+// The dynamic shared-memory ceiling is a per-function, per-device attribute: it is raised once per device to the largest
+// slot any launch can ask for, never per launch (lanes launch concurrently from several host threads).
+int gsa_dpx_init_device(gsa_ctx *ctx)
+{
+	const int big = (int)dpx_layout(DP_MAX_DIM, DP_MAX_DIM, false).total;
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	return GSA_OK; // the S classes stay below the 48 KB default (m <= 1000, n <= 256)
+}
+
+int gsa_dpx_launch(gsa_ctx *ctx, cudaStream_t stream, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
+                   int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
 	if (nprob <= 0) return GSA_OK;
 	switch (cls) {
-	case DPX_CLS_S4: return launch_dpx<1, true>(ctx, stream, DPX_SMEM_S4, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
-	case DPX_CLS_S12: return launch_dpx<1, true>(ctx, stream, DPX_SMEM_S12, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
-	case DPX_CLS_S48: return launch_dpx<4, true>(ctx, stream, DPX_SMEM_S48, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+	case DPX_CLS_S1: case DPX_CLS_S2: {
+		const uint32_t slot = dpx_layout(max_m, max_n, true).total;
+		if (slot <= 3584) return launch_dpx<1, 2, true>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+		return launch_dpx<1, 1, true>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+	}
 	case DPX_CLS_G4: case DPX_CLS_G8: case DPX_CLS_G16: {
 		// warps per problem: one per strip (up to 16) gives the shortest critical path when problems are few; with many
 		// problems in flight fewer warps waste less on the 72-step stagger between consecutive strips
+		const uint32_t slot = dpx_layout(max_m, max_n, false).total;
 		int W = cls == DPX_CLS_G4 ? 4 : cls == DPX_CLS_G8 ? 8 : 16;
 		while (W > 4 && (long long)nprob * W > 4096) W >>= 1;
-		size_t smem = dpx_layout(max_m, max_n, false).total;
-		if (W == 4) return launch_dpx<4, false>(ctx, stream, smem, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
-		if (W == 8) return launch_dpx<8, false>(ctx, stream, smem, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
-		return launch_dpx<16, false>(ctx, stream, smem, prob, nprob, flags, a1, a2, out_len, frag, fblk, bsum);
+		if (W == 4) return launch_dpx<4, 1, false>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+		if (W == 8) return launch_dpx<8, 1, false>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+		return launch_dpx<16, 1, false>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
 	}
 	}
 	return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dpx_launch: bad class %d", cls);

@@ -102,7 +102,7 @@ __global__ void k_dp_problems(const int32_t *dp_idx, int64_t ndp, const gsa_frag
 // H on diagonals d-1 and d-2 and the one being written, E and F on d-1 and the one being written.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_dp(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *flags, char *aln1, char *aln2, int32_t *out_len, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum, int rows_cap)
+k_dp(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *flags, char *aln1, char *aln2, int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum, int rows_cap)
 {
 	extern __shared__ int16_t smem[];
 	int pi = blockIdx.x;
@@ -177,7 +177,7 @@ k_dp(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *flags, char *aln1, 
 	if (same) atomicAdd(&sSame, same);
 	__syncthreads();
 	if (tid == 0) {
-		if (out_len) out_len[P.frag] = L;
+		if (out_len) { out_len[P.frag] = L; out_start[P.frag] = P.out_off; }
 		if (frag) {
 			frag[P.frag].aln_off = P.out_off; frag[P.frag].aln_len = L;
 			int b = fblk[P.frag];
@@ -190,13 +190,12 @@ static size_t dp_smem_bytes(int rows_cap) { return (size_t)rows_cap * (7 * sizeo
 
 // launches the DP over problems [0,nprob) whose max(m,n) <= dim_cap
 template <int THREADS>
-static int launch_dp(gsa_ctx *ctx, const DpProblem *prob, int nprob, int dim_cap, uint8_t *flags, char *a1, char *a2, int32_t *out_len, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+static int launch_dp(gsa_ctx *ctx, const DpProblem *prob, int nprob, int dim_cap, uint8_t *flags, char *a1, char *a2, int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
 	if (nprob <= 0) return GSA_OK;
 	int rows_cap = (dim_cap + 15) & ~15;
 	size_t smem = dp_smem_bytes(rows_cap);
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_dp<THREADS><<<nprob, THREADS, smem, ctx->stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, frag, fblk, bsum, rows_cap);
+	k_dp<THREADS><<<nprob, THREADS, smem, ctx->stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, out_start, frag, fblk, bsum, rows_cap);
 	KERNEL_CHECK(ctx);
 	return GSA_OK;
 }
@@ -213,6 +212,15 @@ struct Ws3 {
 		return (T *)b.p;
 	}
 };
+
+int gsa_dp_init_device(gsa_ctx *ctx)
+{ // see gsa_dpx_init_device: set once, to the largest request
+	const int big = (int)dp_smem_bytes((DP_MAX_DIM + 15) & ~15);
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	return GSA_OK;
+}
 
 // ---- device-side binning ------------------------------------------------------------------------------------------------
 // Problems are ordered by (bin, size descending) with one radix sort; only the per-bin counts come back to the host.
@@ -246,7 +254,7 @@ __global__ void k_dp_permute(const DpProblem *in, const uint32_t *idx, DpProblem
 // d_prob: the problems in any order (device); d_sorted: scratch of the same size.  Records ctx->ev[10]/[11] around the DP
 // launches alone when timed.
 static int run_dp_binned(gsa_ctx *ctx, Ws3 &ws, const DpProblem *d_prob, DpProblem *d_sorted, int ndp, uint8_t *flags, char *a1, char *a2, int32_t *out_len,
-                         gsa_frag *frag, const int32_t *fblk, unsigned int *bsum, cudaEvent_t e0, cudaEvent_t e1)
+                         int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum, cudaEvent_t e0, cudaEvent_t e1)
 {
 	uint32_t *key_in = ws.get<uint32_t>(ndp), *key_out = ws.get<uint32_t>(ndp), *idx_in = ws.get<uint32_t>(ndp), *idx_out = ws.get<uint32_t>(ndp);
 	if (ws.rc) return ws.rc;
@@ -274,10 +282,10 @@ static int run_dp_binned(gsa_ctx *ctx, Ws3 &ws, const DpProblem *d_prob, DpProbl
 	for (int b = 0; b < DP_NBINS; b++) off[b + 1] = off[b] + st->count[b];
 	const bool side = (st->count[DPX_CLS_G8] + st->count[DPX_CLS_G16]) > 0;
 	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0)); }
-	const int order[DPX_CLS_SCALAR] = {DPX_CLS_G16, DPX_CLS_G8, DPX_CLS_S48, DPX_CLS_G4, DPX_CLS_S12, DPX_CLS_S4};
+	const int order[DPX_CLS_SCALAR] = {DPX_CLS_G16, DPX_CLS_G8, DPX_CLS_G4, DPX_CLS_S2, DPX_CLS_S1};
 	for (int cls : order) {
 		cudaStream_t st_cls = cls >= DPX_CLS_G8 ? ctx->stream2 : ctx->stream;
-		GSA_TRY(gsa_dpx_launch(ctx, st_cls, cls, std::max(1, st->max_m[cls]), std::max(1, st->max_n[cls]), d_sorted + off[cls], (int)st->count[cls], flags, a1, a2, out_len, frag, fblk, bsum));
+		GSA_TRY(gsa_dpx_launch(ctx, st_cls, cls, std::max(1, st->max_m[cls]), std::max(1, st->max_n[cls]), d_sorted + off[cls], (int)st->count[cls], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
 	}
 	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
 	size_t beg = off[DP_BIN_SCALAR];
@@ -285,9 +293,9 @@ static int run_dp_binned(gsa_ctx *ctx, Ws3 &ws, const DpProblem *d_prob, DpProbl
 	for (int c = 0; c < 5; c++) {
 		int cnt = (int)st->count[DP_BIN_SCALAR + c];
 		if (cnt > 0) {
-			if (c == 0) GSA_TRY(launch_dp<32>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
-			else if (c == 1) GSA_TRY(launch_dp<64>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
-			else GSA_TRY(launch_dp<256>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, frag, fblk, bsum));
+			if (c == 0) GSA_TRY(launch_dp<32>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
+			else if (c == 1) GSA_TRY(launch_dp<64>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
+			else GSA_TRY(launch_dp<256>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
 		}
 		beg += cnt;
 	}
@@ -358,7 +366,7 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 		KERNEL_CHECK(ctx);
 		DpProblem *d_sorted = ws.get<DpProblem>(ndp);
 		if (ws.rc) return ws.rc;
-		GSA_TRY(run_dp_binned(ctx, ws, d_prob, d_sorted, (int)ndp, flags, a1, a2, nullptr, frag, fblk, bsum, ctx->ev[10], ctx->ev[11]));
+		GSA_TRY(run_dp_binned(ctx, ws, d_prob, d_sorted, (int)ndp, flags, a1, a2, nullptr, nullptr, frag, fblk, bsum, ctx->ev[10], ctx->ev[11]));
 		ctx->dp_timed = true;
 	}
 	// ---- results to pinned host memory ---------------------------------------------------------------------
@@ -392,6 +400,15 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 	return GSA_OK;
 }
 
+// batch mode: rows sit wherever the kernels left them inside each pair's slot; move them to the start of the slot
+__global__ void k_batch_left_align(const DpProblem *prob, int n, const int32_t *len, const int64_t *start, const char *t1, const char *t2, char *o1, char *o2)
+{
+	int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if (pi >= n) return;
+	int64_t dst = prob[pi].out_off, src = start[pi];
+	for (int k = lane; k < len[pi]; k += 32) { o1[dst + k] = t1[src + k]; o2[dst + k] = t2[src + k]; }
+}
+
 // ---- stand-alone DP batch (dump hook / DP stress bench) -----------------------------------------------------
 int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
                       const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms)
@@ -402,7 +419,9 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 	Ws3 ws(ctx);
 	int64_t rb = ref_off[n_pairs], qb = qry_off[n_pairs];
 	char *d_ref = ws.get<char>(rb + 1), *d_qry = ws.get<char>(qb + 1), *d_o1 = ws.get<char>(rb + qb + 1), *d_o2 = ws.get<char>(rb + qb + 1);
+	char *d_t1 = ws.get<char>(rb + qb + 1), *d_t2 = ws.get<char>(rb + qb + 1);
 	int32_t *d_len = ws.get<int32_t>(n_pairs);
+	int64_t *d_start = ws.get<int64_t>(n_pairs);
 	DpProblem *d_prob = ws.get<DpProblem>(n_pairs), *d_sorted = ws.get<DpProblem>(n_pairs);
 	if (ws.rc) return ws.rc;
 	std::vector<DpProblem> hp((size_t)n_pairs);
@@ -426,8 +445,10 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_prob, hp.data(), hp.size() * sizeof(DpProblem), cudaMemcpyHostToDevice, ctx->stream));
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
-	int rc = run_dp_binned(ctx, ws, d_prob, d_sorted, n_pairs, flags, d_o1, d_o2, d_len, nullptr, nullptr, nullptr, e0, e1);
+	int rc = run_dp_binned(ctx, ws, d_prob, d_sorted, n_pairs, flags, d_t1, d_t2, d_len, d_start, nullptr, nullptr, nullptr, e0, e1);
 	if (rc == GSA_OK) {
+		k_batch_left_align<<<gsa_grid(n_pairs, 8), 256, 0, ctx->stream>>>(d_prob, n_pairs, d_len, d_start, d_t1, d_t2, d_o1, d_o2);
+		KERNEL_CHECK(ctx);
 		CUDA_TRY(ctx, cudaMemcpyAsync(out1, d_o1, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(out2, d_o2, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(out_len, d_len, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -75,6 +75,7 @@ struct gsa_ctx {
 
 	// index
 	bool have_index = false;
+	bool shares_index = false;     // lane created by gsa_create_shared: occ/txt/sa (and possibly ktab) belong to the owner
 	DevIndex ix;
 	int64_t N = 0;                 // GenomeSize
 	DevBuf d_occ, d_txt, d_sa, d_ktab, d_cend;

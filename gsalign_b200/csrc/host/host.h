@@ -48,7 +48,7 @@ Coordinate gen_coordinate(const HostIndex &ix, int64_t rPos);              // Ge
 struct Variant { int pos, chr_idx, query_idx; std::string ref_frag, alt_frag; int type; }; // Variant_t
 
 struct Options {                   // the globals of src/main.cpp:10-12,203-215
-	int threads = 8, out_format = 1, n_gpus = 1;
+	int threads = 8, out_format = 1, n_gpus = 1, lanes = 4;
 	bool sensitive = false, show_plot = false, debug = false, vcf = true, allow_dup = true, one_on_one = false;
 	int min_seed_len = 15, min_block_score = 200, min_aln_len = 200, min_idy = 70, max_indel = 25;
 	const char *ref_fa = nullptr, *index_prefix = nullptr, *query = nullptr, *out_prefix = nullptr, *gnuplot = nullptr;

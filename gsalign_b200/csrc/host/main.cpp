@@ -33,6 +33,7 @@ static void usage(const char *prog, const Options &o)
 	fprintf(stderr, "         -one           set one on one aligment mode[false]\n");
 	fprintf(stderr, "         -gp    STR     Specify the path of gnuplot\n");
 	fprintf(stderr, "         -gpus  INT     number of B200s to spread the query contigs over [1]\n");
+	fprintf(stderr, "         -lanes INT     query contigs in flight per GPU [%d]\n", o.lanes);
 	fprintf(stderr, "\n");
 }
 
@@ -93,6 +94,7 @@ int main(int argc, char *argv[])
 		else if (p == "-d" || p == "-debug") o.debug = true;
 		else if (p == "-obr") ++i;
 		else if (p == "-gpus" && i + 1 < argc) o.n_gpus = std::max(1, atoi(argv[++i]));
+		else if (p == "-lanes" && i + 1 < argc) o.lanes = std::max(1, atoi(argv[++i]));
 		else fprintf(stderr, "Warning! Unknow parameter: %s\n", argv[i]);
 	}
 	if ((!o.index_prefix && !o.ref_fa) || !o.query) { usage(argv[0], o); return 0; }
@@ -122,55 +124,57 @@ int main(int argc, char *argv[])
 	if (o.out_format == 2) o.aln = op + ".aln";
 	o.vcf_name = op + ".vcf";
 
-	// ---- one context per GPU, index replicated in each GPU's HBM ------------------------------------------------
+	// ---- one index replica per GPU; on every GPU `lanes` contexts share it (gsa_create_shared), one host thread each ---------
 	gsa_params prm; gsa_default_params(&prm);
 	prm.min_seed_len = o.min_seed_len; prm.sensitive = o.sensitive; prm.max_indel = o.max_indel; prm.min_block_score = o.min_block_score;
 	prm.min_aln_len = o.min_aln_len; prm.min_idy = o.min_idy; prm.one_on_one = o.one_on_one;
 	gsa_index_view view; ix.view(&view);
-	int ngpu = std::min<int>(o.n_gpus, (int)query.size());
-	std::vector<gsa_ctx *> ctx((size_t)ngpu, nullptr);
-	for (int g = 0; g < ngpu; g++) {
-		if (gsa_create(g, &ctx[g]) != 0) { fprintf(stderr, "FatalError: cannot open CUDA device %d (this build has no CPU path)\n", g); return 0; }
-		if (gsa_set_params(ctx[g], &prm) != 0 || gsa_index_upload(ctx[g], &view) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g])); return 0; }
-	}
-
-	// ---- GenomeComparison ------------------------------------------------------------------------------------------------
-	fprintf(stderr, "Step2. Sequence analysis for all query chromosomes\n");
 	int nq = (int)query.size();
-	std::vector<ContigResult> results((size_t)nq);
-	std::vector<int> done((size_t)nq, 0);
-	std::mutex mu; std::condition_variable cv;
+	int ngpu = std::min<int>(o.n_gpus, nq);
 	// longest-processing-time dealing of contigs to GPUs
 	std::vector<int> order((size_t)nq); for (int i = 0; i < nq; i++) order[i] = i;
 	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return query[a].seq.size() > query[b].seq.size(); });
 	std::vector<std::vector<int> > work((size_t)ngpu); std::vector<size_t> load((size_t)ngpu, 0);
 	for (int qi : order) { int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); work[g].push_back(qi); load[g] += query[qi].seq.size(); }
 	for (auto &w : work) std::sort(w.begin(), w.end()); // each GPU walks its share in contig order so that the emitter is never starved
+	std::vector<std::vector<gsa_ctx *> > ctx((size_t)ngpu);
+	for (int g = 0; g < ngpu; g++) {
+		int nl = std::max(1, std::min<int>(o.lanes, (int)work[g].size()));
+		ctx[g].assign((size_t)nl, nullptr);
+		if (gsa_create(g, &ctx[g][0]) != 0) { fprintf(stderr, "FatalError: cannot open CUDA device %d (this build has no CPU path)\n", g); return 0; }
+		if (gsa_set_params(ctx[g][0], &prm) != 0 || gsa_index_upload(ctx[g][0], &view) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g][0])); return 0; }
+		for (int l = 1; l < nl; l++)
+			if (gsa_create_shared(ctx[g][0], &ctx[g][l]) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g][0])); return 0; }
+	}
+
+	// ---- GenomeComparison ------------------------------------------------------------------------------------------------
+	fprintf(stderr, "Step2. Sequence analysis for all query chromosomes\n");
+	std::vector<ContigResult> results((size_t)nq);
+	std::vector<int> done((size_t)nq, 0);
+	std::mutex mu; std::condition_variable cv;
+	std::vector<size_t> cursor((size_t)ngpu, 0);
 	bool failed = false;
-	auto run_gpu = [&](int g) {
-		for (int qi : work[g]) {
+	auto run_lane = [&](int g, gsa_ctx *c) { // a lane takes the next contig of its GPU's share until none is left
+		for (;;) {
+			int qi;
+			{ std::unique_lock<std::mutex> lk(mu); if (cursor[g] >= work[g].size()) return; qi = work[g][cursor[g]++]; }
 			gsa_alignment al;
-			int rc = gsa_align_contig(ctx[g], query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al);
+			int rc = gsa_align_contig(c, query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al);
 			std::unique_lock<std::mutex> lk(mu);
-			if (rc != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g])); failed = true; }
+			if (rc != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(c)); failed = true; }
 			else results[qi].assign(al);
 			done[qi] = 1;
 			cv.notify_all();
 		}
 	};
 	std::vector<std::thread> threads;
-	if (ngpu > 1) for (int g = 0; g < ngpu; g++) threads.emplace_back(run_gpu, g);
+	for (int g = 0; g < ngpu; g++) for (gsa_ctx *c : ctx[g]) threads.emplace_back(run_lane, g, c);
 
 	EmitState st;
 	for (int qi = 0; qi < nq; qi++) {
 		fprintf(stderr, "\tProcess query chromsomoe: %s...\n", query[qi].name.c_str());
 		ContigResult &r = results[(size_t)qi];
-		if (ngpu > 1) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[qi] != 0; }); }
-		else {
-			gsa_alignment al;
-			if (gsa_align_contig(ctx[0], query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[0])); failed = true; break; }
-			r.assign(al);
-		}
+		{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[qi] != 0; }); }
 		if (failed) break;
 		int n = 0; int64_t aln_score = 0, aln_len = 0;
 		for (const gsa_block &b : r.blocks) { // src/GSAlign.cpp:529-539 (the identity filter itself ran inside gsa_fill)
@@ -195,6 +199,6 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "\nGSAlign identifies %d SNVs, %d insertions, and %d deletions [%s].\n\n", st.iSNV, st.iInsertion, st.iDeletion, o.vcf_name.c_str());
 		output_variants(o, ix, st);
 	}
-	for (gsa_ctx *c : ctx) gsa_destroy(c);
+	for (auto &v : ctx) for (size_t l = v.size(); l-- > 0;) gsa_destroy(v[l]); // lanes first, the index owner last
 	return 0;
 }

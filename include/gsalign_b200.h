@@ -105,6 +105,11 @@ typedef struct {
 
 /* --- lifecycle ------------------------------------------------------------------------------- */
 int gsa_create(int device, gsa_ctx **out);
+/* A second lane on the owner's GPU: own stream, own scratch and result buffers, but the owner's uploaded index (read
+ * only).  Query contigs are independent, so several lanes driven by one host thread each keep the GPU
+ * busy across the host-side steps of a contig.  The owner must have its index uploaded and parameters set, and must
+ * outlive every lane created from it. */
+int gsa_create_shared(gsa_ctx *owner, gsa_ctx **out);
 void gsa_destroy(gsa_ctx *ctx);
 const char *gsa_last_error(const gsa_ctx *ctx);
 

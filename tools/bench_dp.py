@@ -39,6 +39,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--cells", type=float, default=4e9, help="target cells per batch")
+    ap.add_argument("--sizes", default="16,32,64,128,256,512,1024,2048")
+    ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     al = capi.Aligner(0)
     peaks = {n: al.dpx_peak(i) for i, n in enumerate(["VIADDMNMX.S16x2", "VIMNMX.S16x2(+LOP3)", "VIADD.16x2", "VIMNMX3.S16x2(+LOP3)"])}
@@ -47,13 +49,13 @@ def main():
     O = orc.Oracle()
     rng = np.random.default_rng(5)
     rows = []
-    for L in (16, 32, 64, 128, 256, 512, 1024, 2048):
+    for L in [int(x) for x in args.sizes.split(",")]:
         n_pairs = int(max(64, min(2_000_000, args.cells / (L * L))))
         rb, ro, qb, qo = make_batch(rng, n_pairs, L)
         cells = int(np.sum((ro[1:] - ro[:-1]) * (qo[1:] - qo[:-1])))
         al.dp_batch_arrays(rb, ro, qb, qo)  # warm-up (allocations)
         best = 1e30
-        for _ in range(3):
+        for _ in range(args.reps):
             o1, o2, ol, ms = al.dp_batch_arrays(rb, ro, qb, qo)
             best = min(best, ms)
         for i in list(range(0, n_pairs, max(1, n_pairs // 8)))[:8]:  # parity sample
