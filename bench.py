@@ -15,7 +15,8 @@ A "step" is one pass of the hot path over every contig of the synthetic query ge
             CUDA-event duration / the measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline  the unmodified reference binary (oracle/_ref/GSAlign -t nproc) on a bounded sample
 N > 1: weak scaling -- every rank aligns its own copy of the workload against an index replicated in its
-HBM; no data-path collective (query contigs are independent).
+HBM (query contigs are independent); once per step the finished alignment records of all ranks
+are gathered to rank 0 over NCCL (gsalign_b200/gather.py), the only collective of the path.
 """
 from __future__ import annotations
 
@@ -248,11 +249,49 @@ def main():
             f.result()
         return out
 
+    # N > 1: the one collective of the path -- every rank packs its finished records (device memory) into an outbox and
+    # rank 0 gathers them over NCCL once per step (gsalign_b200/gather.py); inside the timed region of `value`
+    from gsalign_b200 import gather
+    outbox = {"box": None, "lock": threading.Lock(), "bytes": 0}
+
+    class _DevView:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def _dev_u8(ptr, nbytes):
+        return torch.as_tensor(_DevView(ptr, nbytes), device=f"cuda:{local}") if nbytes else torch.empty(0, dtype=torch.uint8, device=f"cuda:{local}")
+
     def contig_device(ln, i):
         t = dev[i]
         ln.contig_begin_device(t.data_ptr(), t.shape[0]); ln.seed(); ln.cluster()
         ln._chk(ln.lib.gsa_fill(ln.ctx, ctypes.byref(capi.Alignment())))
+        if world > 1:
+            r = ln.result_device()
+            nb = gather.record_bytes(r.n_blocks, r.n_frags, r.aln_bytes)
+            with outbox["lock"]:
+                outbox["bytes"] += nb
+                off = outbox["box"].reserve(nb) if outbox["box"] is not None else None
+            if off is not None:
+                nbb = r.n_blocks * gather.BLOCK_BYTES
+                blocks = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(r.blocks, ctypes.POINTER(ctypes.c_uint8)), shape=(nbb,)).copy()) if nbb else torch.empty(0, dtype=torch.uint8)
+                with torch.cuda.stream(streams[lanes.index(ln)]):
+                    outbox["box"].put(off, i, blocks, _dev_u8(r.frags, r.n_frags * gather.FRAG_BYTES), _dev_u8(r.aln1, r.aln_bytes), _dev_u8(r.aln2, r.aln_bytes))
         return ln.timing()
+
+    def gather_step():
+        """after every lane finished its contigs: one NCCL gather of this step's records to rank 0"""
+        if world == 1:
+            return 0
+        for st in streams:
+            ev = torch.cuda.Event(); ev.record(st); master.wait_event(ev)
+        with torch.cuda.stream(master):
+            inbox = gather.gather_to_root(outbox["box"].buf, outbox["box"].used)
+        got = sum(int(b.numel()) for b in inbox) if inbox is not None else 0
+        ev = torch.cuda.Event(); ev.record(master)
+        for st in streams:
+            st.wait_event(ev)                      # the outbox is reused by the next step
+        outbox["box"].reset()
+        return got
 
     def contig_host(ln, i):
         r = ln.align_contig_raw(pinned_np[i])
@@ -265,14 +304,19 @@ def main():
             torch.cuda.synchronize()
 
     # ---- value: device-resident inputs; CUDA events: every lane's stream starts after e0 and e1 follows all of them ---
+    master = torch.cuda.Stream()
+    run_lanes(contig_device)                       # sizes the outbox (N > 1) and warms the allocators
+    if world > 1:
+        outbox["box"] = gather.Outbox(int(outbox["bytes"] * 1.1) + (1 << 20), torch.device("cuda", local))
     for _ in range(args.warmup):
         run_lanes(contig_device)
+        gather_step()
     sampler = ClockSampler(local)
     sampler.start()
     sync_all()
-    master = torch.cuda.Stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_seed_ms, k_dp_ms, launches, seed_ms, cluster_ms, fill_ms, dp_cells, n_seeds = [], [], 0, 0.0, 0.0, 0.0, 0, 0
+    gathered = 0
     e0.record(master)
     for st in streams:
         st.wait_event(e0)
@@ -280,6 +324,7 @@ def main():
         for t in run_lanes(contig_device):
             k_seed_ms.append(t.k_seed_ms); k_dp_ms.append(t.k_dp_ms); launches += t.launches
             seed_ms += t.seed_ms; cluster_ms += t.cluster_ms; fill_ms += t.fill_ms; dp_cells += t.dp_cells; n_seeds += t.n_seeds
+        gathered = gather_step()
     for st in streams:
         ev = torch.cuda.Event()
         ev.record(st)
@@ -356,7 +401,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['n'] // 1_000_000} Mbp ref x {total_bp} bp query in {len(contigs)} contigs, SNV {w['snv']}, indel {w['indel']}, "
                                    f"params {w['prm'] or 'reference defaults'}",
-                       "parallelism": f"{world} x (full index replica + own query copy), {n_lanes} contigs in flight per GPU, no collective on the data path",
+                       "parallelism": f"{world} x (full index replica + own query copy), {n_lanes} contigs in flight per GPU; "
+                                      + ("no collective (1 GPU)" if world == 1 else f"one NCCL record gather to rank 0 per step ({gathered} bytes) inside the timed region of value"),
                        "l2": "inputs larger than L2 (index " + f"{(bi.seq_len * 4 + bi.seq_len // 2 + bi.seq_len // 4) / 1e6:.0f} MB resident, query {total_bp / 1e6:.0f} MB); no flush needed"},
             "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": int(total_bp), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / args.steps * 1e3},

@@ -149,7 +149,7 @@ static int contig_reset(gsa_ctx *ctx, uint32_t len)
 	if (len >= 0x7FFFFF00u) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_contig_begin: contig longer than 2^31 (positions are int in the reference)");
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	ctx->qlen = len; ctx->have_contig = false; ctx->have_seeds = false; ctx->have_cluster = false;
-	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->dp_timed = false;
+	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->aln_bytes = 0; ctx->dp_timed = false;
 	memset(&ctx->tm, 0, sizeof(ctx->tm));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_seq, (size_t)len + 64));
 	return GSA_OK;
@@ -236,6 +236,18 @@ int gsa_fill(gsa_ctx *ctx, gsa_alignment *out)
 	cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[7]);
 	if (ctx->qlen > 0) cudaEventElapsedTime(&ctx->tm.k_seed_ms, ctx->ev[8], ctx->ev[9]);
 	if (ctx->dp_timed) cudaEventElapsedTime(&ctx->tm.k_dp_ms, ctx->ev[10], ctx->ev[11]);
+	return GSA_OK;
+}
+
+int gsa_result_device(gsa_ctx *ctx, gsa_alignment *out)
+{
+	if (!ctx || !out) return GSA_ERR_ARG;
+	if (!ctx->have_cluster) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_result_device: call gsa_fill first");
+	memset(out, 0, sizeof(*out));
+	out->n_blocks = (int32_t)ctx->out_blocks.size(); out->blocks = ctx->out_blocks.data();
+	if (out->n_blocks == 0) return GSA_OK;
+	out->n_frags = ctx->n_frags; out->frags = (const gsa_frag *)ctx->d_frag.p;
+	out->aln_bytes = ctx->aln_bytes; out->aln1 = (const char *)ctx->d_aln1.p; out->aln2 = (const char *)ctx->d_aln2.p;
 	return GSA_OK;
 }
 

@@ -352,6 +352,7 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 	CUDA_TRY(ctx, cudaMemcpyAsync(hs + 2, d_ndp, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	int64_t row_bytes = hs[0], flag_bytes = hs[1], ndp = *(int32_t *)(hs + 2);
+	ctx->aln_bytes = row_bytes;
 	GSA_TRY(gsa_ensure(ctx, ctx->d_aln1, (size_t)row_bytes + 16));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_aln2, (size_t)row_bytes + 16));
 	char *a1 = (char *)ctx->d_aln1.p, *a2 = (char *)ctx->d_aln2.p;

@@ -109,6 +109,7 @@ struct gsa_ctx {
 
 	// fragments (after FillAlnBlockGaps) and K3 output
 	int64_t n_frags = 0;
+	int64_t aln_bytes = 0;         // bytes used in each row pool
 	DevBuf d_frag;                 // gsa_frag[n_frags]
 	DevBuf d_fblk;                 // block index per fragment
 	DevBuf d_aln1, d_aln2;         // row pools

@@ -141,6 +141,11 @@ int gsa_cluster(gsa_ctx *ctx, int32_t *n_blocks);
  * pinned host memory and fills *out. */
 int gsa_fill(gsa_ctx *ctx, gsa_alignment *out);
 
+/* The result of the last gsa_fill() where it was produced: same struct, but frags / aln1 / aln2 are DEVICE pointers
+ * (blocks stays a host pointer, O(#blocks)).  Valid until the next gsa_contig_begin*() on this context.  This is what a
+ * multi-GPU host packs into its outbox for the single record gather over NVLink. */
+int gsa_result_device(gsa_ctx *ctx, gsa_alignment *out);
+
 /* The three phases back to back on a host buffer: the call GenomeComparison() would make per contig. */
 int gsa_align_contig(gsa_ctx *ctx, const char *seq, uint32_t len, gsa_alignment *out);
 

@@ -125,3 +125,49 @@ def test_two_rank_gloo_sharding_and_reduction():
     assert all(r[1] == res[0][1] and r[2] == 6 for r in res)
     assert sorted(res[0][3][0] + res[0][3][1]) == list(range(6))
     assert res[0][1] == 400.0
+
+
+def _gather_worker(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsalign_b200 import gather
+    from gsalign_b200.shard import lpt_assign
+    lens = [300, 200, 120, 90, 80, 10]
+    mine = lpt_assign(lens, world)[rank]
+    rng = np.random.default_rng(100 + rank)
+    box = gather.Outbox(1 << 20, "cpu")
+    sent = []
+    for c in mine:   # one fake record per contig this rank owns; contig 5 has no alignment at all
+        nb, nf, ab = (0, 0, 0) if c == 5 else (1 + c, 3 * c + 2, 17 * c + 5)
+        parts = [torch.from_numpy(rng.integers(0, 256, size=k, dtype=np.uint8)) for k in (nb * gather.BLOCK_BYTES, nf * gather.FRAG_BYTES, ab, ab)]
+        off = box.reserve(gather.record_bytes(nb, nf, ab))
+        box.put(off, c, *parts)
+        sent.append((c, [p.numpy().tobytes() for p in parts]))
+    inbox = gather.gather_to_root(box.buf, box.used)
+    got = None
+    if rank == 0:
+        got = [[(c, [x.tobytes() for x in rest]) for c, *rest in gather.unpack(b)] for b in inbox]
+    q.put((rank, sent, got))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_record_gather():
+    """the N > 1 record gather (gsalign_b200/gather.py): what every rank packed arrives on rank 0, byte for byte"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in ps), key=lambda r: r[0])
+    for p in ps:
+        p.join(timeout=60)
+    got = res[0][2]
+    assert got is not None and len(got) == 2
+    for r in range(2):
+        assert got[r] == res[r][1]
+    assert sorted(c for r in range(2) for c, _ in got[r]) == list(range(6))
