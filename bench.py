@@ -45,6 +45,9 @@ WORKLOADS = {
     "C2": dict(n=100_000_000, k=4, snv=0.01, indel=0.0, seed=2, prm={}, flags=[]),
     "C2s": dict(n=20_000_000, k=4, snv=0.01, indel=0.0, seed=2, prm={}, flags=[]),       # dev-size C2
     "C3s": dict(n=20_000_000, k=4, snv=0.02, indel=0.002, seed=3, prm={}, flags=[]),     # dev-size C3
+    "C3": dict(n=1_000_000_000, k=8, snv=0.02, indel=0.002, seed=3, prm={}, flags=[]),
+    "C5": dict(n=500_000_000, k=4, snv=0.10, indel=0.0, seed=5, prm=dict(min_seed_len=10, sensitive=1, min_block_score=50, min_idy=70),
+               flags=["-sen", "-slen", "10", "-idy", "70"]),
     "C5s": dict(n=10_000_000, k=4, snv=0.10, indel=0.0, seed=5, prm=dict(min_seed_len=10, sensitive=1, min_block_score=50, min_idy=70),
                 flags=["-sen", "-slen", "10", "-idy", "70"]),
 }
@@ -278,6 +281,12 @@ def main():
                     outbox["box"].put(off, i, blocks, _dev_u8(r.frags, r.n_frags * gather.FRAG_BYTES), _dev_u8(r.aln1, r.aln_bytes), _dev_u8(r.aln2, r.aln_bytes))
         return ln.timing()
 
+    def contig_device_plain(ln, i):
+        t = dev[i]
+        ln.contig_begin_device(t.data_ptr(), t.shape[0]); ln.seed(); ln.cluster()
+        ln._chk(ln.lib.gsa_fill(ln.ctx, ctypes.byref(capi.Alignment())))
+        return ln.timing()
+
     def gather_step():
         """after every lane finished its contigs: one NCCL gather of this step's records to rank 0"""
         if world == 1:
@@ -303,7 +312,10 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- value: device-resident inputs; CUDA events: every lane's stream starts after e0 and e1 follows all of them ---
+    # ---- value: device-resident inputs and results (block headers come to the host; fragments and rows stay in HBM, where
+    # the record gather of N > 1 reads them); CUDA events: every lane's stream starts after e0 and e1 follows all of them ---
+    for ln in lanes:
+        ln.set_host_results(False)
     master = torch.cuda.Stream()
     run_lanes(contig_device)                       # sizes the outbox (N > 1) and warms the allocators
     if world > 1:
@@ -332,6 +344,14 @@ def main():
     e1.record(master)
     sync_all()
     dev_ms = e0.elapsed_time(e1)
+
+    # ---- roofline pass: the dominant kernel timed alone (one lane, nothing else on the GPU), CUDA events on its stream ------
+    k_seed_alone = []
+    for _ in range(max(1, min(args.steps, 3))):
+        for i in order:
+            k_seed_alone.append((contig_device_plain(lanes[0], i).k_seed_ms, contigs[i][1].shape[0]))
+    for ln in lanes:
+        ln.set_host_results(True)
 
     # ---- e2e: host buffers through gsa_align_contig, wall clock between synchronisations -------------------------
     for _ in range(args.warmup):
@@ -377,14 +397,36 @@ def main():
     prm = orc.params(**{k: v for k, v in w["prm"].items() if k in ("min_seed_len", "sensitive")})
     sq, _, _ = O.seed_contig(oix, prm, samp, ctr)
     bseed_per_bp = ctr.algorithmic_bytes(len(samp), len(sq)) / len(samp)
-    mean_k_seed_ms = float(np.mean(k_seed_ms))
-    bp_per_launch = total_bp / len(contigs)
+    mean_k_seed_ms = float(np.mean([t for t, _ in k_seed_alone]))
+    bp_per_launch = float(np.mean([b for _, b in k_seed_alone]))
     achieved = bseed_per_bp * bp_per_launch / (mean_k_seed_ms * 1e-3) / 1e9
+    traffic = None   # dram__bytes_read+write per k_seed launch from the committed ncu --set full capture of this workload
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("k_seed_dram_bytes_per_launch")
     roofline = {"kernel": "k_seed (K1 fm_seed)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "note": f"achieved = B_seed of the reference's algorithm ({bseed_per_bp:.1f} B/query bp, oracle counters on the first {len(samp)} bp) "
-                        f"x {bp_per_launch:.0f} bp per launch / {mean_k_seed_ms:.3f} ms mean launch; an EFFECTIVE fraction: this kernel replaces "
+                        f"x {bp_per_launch:.0f} bp per launch / {mean_k_seed_ms:.3f} ms mean launch (timed alone on its stream after the timed region; "
+                        f"inside it, with {n_lanes} contigs in flight, launches overlap and average {float(np.mean(k_seed_ms)):.3f} ms); an EFFECTIVE fraction: this kernel replaces "
                         "per-base rank walks by a prefix table + full SA + text compare, actual DRAM bytes are in profiles/"}
+
+    # ---- K3 roofline: DP-only stress batch against the packed-int16 DPX issue rate measured on this box -----
+    roofline_k3 = None
+    try:
+        dpx_peak = al.dpx_peak(0)
+        rb, ro, qb, qo = synth.make_dp_batch(np.random.default_rng(5), 1024, 1024)
+        cells = int(np.sum((ro[1:] - ro[:-1]) * (qo[1:] - qo[:-1])))
+        al.dp_batch_arrays(rb, ro, qb, qo)
+        dp_ms = min(al.dp_batch_arrays(rb, ro, qb, qo)[3] for _ in range(3))
+        gcups = cells / (dp_ms * 1e-3) / 1e9
+        roofline_k3 = {"kernel": "k_dpx (K3 gapped fill)", "bound": "dpx", "achieved": 1.5 * gcups, "peak": dpx_peak, "unit": "G s16x2-instr/s",
+                       "frac": 1.5 * gcups / dpx_peak, "gcups": gcups, "executed_frac": 4.0 * gcups / dpx_peak,
+                       "note": f"stress batch of 1024 pairs ~1024x1024 at 10 % divergence ({cells} cells, {dp_ms:.3f} ms, gsa_dp_batch kernel span); "
+                               "achieved = 1.5 packed add-max per cell (SURVEY 8d) x GCUPS; peak = VIADDMNMX.S16x2 issue rate measured by "
+                               "gsa_dpx_peak() on this GPU; executed_frac counts the 8 VIMNMX/VIADD.16x2 the kernel issues per 2 cells"}
+    except Exception as e:  # noqa: BLE001
+        log("K3 stress batch failed:", e)
 
     # ---- CPU baseline: the unmodified reference on a bounded sample ---------------------------------------------------
     cpu = None
@@ -411,7 +453,7 @@ def main():
             "phases_ms_per_step": {"seed": seed_ms / args.steps, "cluster": cluster_ms / args.steps, "fill": fill_ms / args.steps,
                                    "k_seed": float(np.sum(k_seed_ms)) / args.steps, "k_dp": float(np.sum(k_dp_ms)) / args.steps},
             "counts_per_step": {"seeds": n_seeds // args.steps, "dp_cells": dp_cells // args.steps},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}
+            "roofline": roofline, "roofline_k3": roofline_k3, "cpu_baseline": cpu, "clocks": sampler.summary()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

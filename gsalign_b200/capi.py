@@ -55,7 +55,7 @@ class Timing(C.Structure):
 
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
-           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device"]
+           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device", "gsa_set_host_results"]
 
 
 def load_library() -> C.CDLL:
@@ -193,6 +193,9 @@ class Aligner:
         al = Alignment()
         self._chk(self.lib.gsa_align_contig(self.ctx, a.ctypes.data_as(C.c_char_p), C.c_uint32(a.shape[0]), C.byref(al)))
         return al
+
+    def set_host_results(self, enable: bool):
+        self._chk(self.lib.gsa_set_host_results(self.ctx, C.c_int(1 if enable else 0)))
 
     def result_device(self) -> Alignment:
         """the last gsa_fill() result with DEVICE pointers for frags / aln1 / aln2 (blocks: host)"""

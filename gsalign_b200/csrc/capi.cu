@@ -239,6 +239,13 @@ int gsa_fill(gsa_ctx *ctx, gsa_alignment *out)
 	return GSA_OK;
 }
 
+int gsa_set_host_results(gsa_ctx *ctx, int enable)
+{
+	if (!ctx) return GSA_ERR_ARG;
+	ctx->host_results = enable != 0;
+	return GSA_OK;
+}
+
 int gsa_result_device(gsa_ctx *ctx, gsa_alignment *out)
 {
 	if (!ctx || !out) return GSA_ERR_ARG;

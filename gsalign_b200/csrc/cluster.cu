@@ -242,17 +242,26 @@ __device__ __forceinline__ uint32_t hash64(uint64_t k)
 __global__ void k_hist_insert(GroupView v, const int32_t *uq, const int32_t *wid1, unsigned long long *keys, int32_t *cnt, int32_t *slot_of, uint32_t hmask)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= v.n || !uq[i]) return;
-	int32_t bin = (int32_t)(pd_of(v, i) >> 4);
-	unsigned long long key = ((unsigned long long)(uint32_t)(wid1[i] - 1) << 32) | (uint32_t)bin;
-	uint32_t s = hash64(key) & hmask;
-	for (;;) {
-		unsigned long long old = atomicCAS(keys + s, HASH_EMPTY, key);
-		if (old == HASH_EMPTY || old == key) break;
-		s = (s + 1) & hmask;
+	const bool act = i < v.n && uq[i];
+	// inactive lanes get distinct keys no (window,bin) can take (window ids are < 2^31)
+	unsigned long long key = 0xFFFFFFFF00000000ull | (threadIdx.x & 31);
+	if (act) key = ((unsigned long long)(uint32_t)(wid1[i] - 1) << 32) | (uint32_t)(int32_t)(pd_of(v, i) >> 4);
+	// neighbouring seeds mostly share the bin: one probe + one add per distinct key of the warp
+	unsigned peers = __match_any_sync(0xffffffffu, key);
+	bool leader;
+	int total = gsa_peer_sum(peers, 1, leader);
+	uint32_t s = 0;
+	if (leader && act) {
+		s = hash64(key) & hmask;
+		for (;;) {
+			unsigned long long old = atomicCAS(keys + s, HASH_EMPTY, key);
+			if (old == HASH_EMPTY || old == key) break;
+			s = (s + 1) & hmask;
+		}
+		atomicAdd(cnt + s, total);
 	}
-	atomicAdd(cnt + s, 1);
-	slot_of[i] = (int32_t)s;
+	s = __shfl_sync(0xffffffffu, s, __ffs(peers) - 1);
+	if (act) slot_of[i] = (int32_t)s;
 }
 
 // mode per window = the smallest bin with the maximal count (RefinePDFmap, src/GSAlign.cpp:250-251)
@@ -273,13 +282,21 @@ __device__ __forceinline__ int32_t mode_of(unsigned long long packed) { return (
 __global__ void k_win_sum(GroupView v, const int32_t *uq, const int32_t *wid1, const unsigned long long *best, unsigned long long *sum, int32_t *cntk)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= v.n || !uq[i]) return;
-	int w = wid1[i] - 1;
-	int64_t pd = pd_of(v, i);
-	int32_t bin = (int32_t)(pd >> 4), mode = mode_of(best[w]);
-	long long d = (long long)bin - mode;
-	if (d < 0) d = -d;
-	if (d < 3) { atomicAdd(sum + w, (unsigned long long)pd); atomicAdd(cntk + w, 1); }
+	int w = -1 - (int)(threadIdx.x & 31);
+	int64_t pd = 0;
+	if (i < v.n && uq[i]) {
+		int wi = wid1[i] - 1;
+		pd = pd_of(v, i);
+		int32_t bin = (int32_t)(pd >> 4), mode = mode_of(best[wi]);
+		long long d = (long long)bin - mode;
+		if (d < 0) d = -d;
+		if (d < 3) w = wi;
+	}
+	unsigned peers = __match_any_sync(0xffffffffu, w);
+	bool leader;
+	unsigned long long tot = gsa_peer_sum(peers, (unsigned long long)(w >= 0 ? pd : 0), leader);
+	int c = gsa_peer_sum(peers, w >= 0 ? 1 : 0, leader);
+	if (leader && w >= 0) { atomicAdd(sum + w, tot); atomicAdd(cntk + w, c); }
 }
 
 __global__ void k_outlier_kill(GroupView v, const int32_t *uq, const int32_t *wid1, const unsigned long long *best, const unsigned long long *sum,
@@ -427,7 +444,7 @@ __global__ void k_overlap_pass(const int32_t *q, const int64_t *r, int32_t *l, c
 		}
 	}
 	alive[i] = a;
-	if (!a) atomicAdd(kills, 1);
+	if (!a) atomicAdd(kills, 1); // rare
 }
 
 __device__ __forceinline__ int64_t contig_end_of(const ContigEnd *ce, int nce, int64_t rpos)

@@ -66,23 +66,30 @@ __global__ void k_frag_simple(gsa_frag *frag, int64_t nfr, const int32_t *fblk, 
                               const unsigned char *seq, DevIndex ix, char *aln1, char *aln2, unsigned int *bsum)
 {
 	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= nfr) return;
-	gsa_frag f = frag[t];
-	int ty = type[t], b = fblk[t];
-	int64_t o = row_off[t];
 	unsigned int alen = 0, sc = 0;
-	if (ty == FT_SEED) { alen = (unsigned)f.qLen; sc = (unsigned)f.qLen; }
-	else if (ty == FT_DEL) {
-		for (int k = 0; k < f.rLen; k++) { aln1[o + k] = gsa_text_char(ix, f.rPos + k); aln2[o + k] = '-'; }
-		alen = (unsigned)f.rLen; frag[t].aln_off = o; frag[t].aln_len = f.rLen;
-	} else if (ty == FT_INS) {
-		for (int k = 0; k < f.qLen; k++) { aln1[o + k] = '-'; aln2[o + k] = (char)seq[f.qPos + k]; }
-		alen = (unsigned)f.qLen; frag[t].aln_off = o; frag[t].aln_len = f.qLen;
-	} else if (ty == FT_COPY) {
-		for (int k = 0; k < f.qLen; k++) { aln1[o + k] = gsa_text_char(ix, f.rPos + k); aln2[o + k] = (char)seq[f.qPos + k]; }
-		alen = (unsigned)f.qLen; sc = (unsigned)(f.qLen - mism[t]); frag[t].aln_off = o; frag[t].aln_len = f.qLen;
-	} else return; // DP fragments are accounted by the DP kernel
-	atomicAdd(bsum + 2 * b, alen); atomicAdd(bsum + 2 * b + 1, sc);
+	int b = -1 - (int)(threadIdx.x & 31); // lanes with nothing to add form singleton groups
+	if (t < nfr) {
+		gsa_frag f = frag[t];
+		int ty = type[t];
+		int64_t o = row_off[t];
+		if (ty != FT_DP) b = fblk[t];     // DP fragments are accounted by the DP kernels
+		if (ty == FT_SEED) { alen = (unsigned)f.qLen; sc = (unsigned)f.qLen; }
+		else if (ty == FT_DEL) {
+			for (int k = 0; k < f.rLen; k++) { aln1[o + k] = gsa_text_char(ix, f.rPos + k); aln2[o + k] = '-'; }
+			alen = (unsigned)f.rLen; frag[t].aln_off = o; frag[t].aln_len = f.rLen;
+		} else if (ty == FT_INS) {
+			for (int k = 0; k < f.qLen; k++) { aln1[o + k] = '-'; aln2[o + k] = (char)seq[f.qPos + k]; }
+			alen = (unsigned)f.qLen; frag[t].aln_off = o; frag[t].aln_len = f.qLen;
+		} else if (ty == FT_COPY) {
+			for (int k = 0; k < f.qLen; k++) { aln1[o + k] = gsa_text_char(ix, f.rPos + k); aln2[o + k] = (char)seq[f.qPos + k]; }
+			alen = (unsigned)f.qLen; sc = (unsigned)(f.qLen - mism[t]); frag[t].aln_off = o; frag[t].aln_len = f.qLen;
+		}
+	}
+	// per-block sums: fragments are in block order, so a warp usually feeds one block -> one atomic pair per warp
+	unsigned peers = __match_any_sync(0xffffffffu, b);
+	bool leader;
+	unsigned long long both = gsa_peer_sum(peers, ((unsigned long long)alen << 32) | sc, leader); // a warp adds < 2^32 to either half
+	if (leader && b >= 0) { atomicAdd(bsum + 2 * b, (unsigned)(both >> 32)); atomicAdd(bsum + 2 * b + 1, (unsigned)both); }
 }
 
 __global__ void k_dp_problems(const int32_t *dp_idx, int64_t ndp, const gsa_frag *frag, const int64_t *row_off, const int64_t *flag_off,
@@ -370,15 +377,17 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 		GSA_TRY(run_dp_binned(ctx, ws, d_prob, d_sorted, (int)ndp, flags, a1, a2, nullptr, nullptr, frag, fblk, bsum, ctx->ev[10], ctx->ev[11]));
 		ctx->dp_timed = true;
 	}
-	// ---- results to pinned host memory ---------------------------------------------------------------------
-	GSA_TRY(gsa_ensure_host(ctx, ctx->h_frag, (size_t)nfr * sizeof(gsa_frag)));
-	GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln1, (size_t)row_bytes + 16));
-	GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln2, (size_t)row_bytes + 16));
+	// ---- results to pinned host memory (skipped when the consumer reads them on the device, gsa_set_host_results) ---------
 	GSA_TRY(gsa_ensure_host(ctx, ctx->h_blocks, (size_t)nblk * 8));
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_frag.p, frag, (size_t)nfr * sizeof(gsa_frag), cudaMemcpyDeviceToHost, ctx->stream));
-	if (row_bytes) {
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln1.p, a1, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln2.p, a2, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->host_results) {
+		GSA_TRY(gsa_ensure_host(ctx, ctx->h_frag, (size_t)nfr * sizeof(gsa_frag)));
+		GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln1, (size_t)row_bytes + 16));
+		GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln2, (size_t)row_bytes + 16));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_frag.p, frag, (size_t)nfr * sizeof(gsa_frag), cudaMemcpyDeviceToHost, ctx->stream));
+		if (row_bytes) {
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln1.p, a1, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln2.p, a2, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		}
 	}
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_blocks.p, bsum, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -396,8 +405,8 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 		b.score = vec[k].score; b.aln_len = vec[k].aln_len; b.bDup = vec[k].bDup; b.n_frags = vec[k].n_frags; b.frag_beg = vec[k].frag_beg;
 	}
 	out->n_blocks = (int32_t)ctx->out_blocks.size(); out->blocks = ctx->out_blocks.data();
-	out->n_frags = nfr; out->frags = (const gsa_frag *)ctx->h_frag.p;
-	out->aln_bytes = row_bytes; out->aln1 = (const char *)ctx->h_aln1.p; out->aln2 = (const char *)ctx->h_aln2.p;
+	out->n_frags = nfr; out->aln_bytes = row_bytes;
+	if (ctx->host_results) { out->frags = (const gsa_frag *)ctx->h_frag.p; out->aln1 = (const char *)ctx->h_aln1.p; out->aln2 = (const char *)ctx->h_aln2.p; }
 	return GSA_OK;
 }
 

@@ -77,3 +77,23 @@ __device__ __forceinline__ char gsa_text_char(const DevIndex &ix, int64_t pos)
 {
 	return "ACGT"[gsa_pk_base(ix.txt, (uint32_t)pos)];
 }
+
+// ---- warp-aggregated atomics -----------------------------------------------------------------------------------
+// Seeds and fragments arrive sorted, so the lanes of a warp mostly update the same counter (one giant block, one
+// outlier window, one histogram bin); same-address atomics serialise, so peers are summed in registers first.
+// peers = __match_any_sync(FULL, key) of the calling lane; ALL 32 lanes must call.  Returns the group total in the group's
+// lowest lane (leader == true there); other lanes get a partial sum.
+template <typename T>
+__device__ __forceinline__ T gsa_peer_sum(unsigned peers, T v, bool &leader)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned rank = __popc(peers & ((1u << lane) - 1));
+	leader = rank == 0;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		unsigned src = __fns(peers, lane, d + 1);                // the d-th peer above this lane, or 0xffffffff
+		T t = __shfl_sync(0xffffffffu, v, src == 0xffffffffu ? lane : (int)src);
+		if (src != 0xffffffffu && (rank & (2 * d - 1)) == 0) v += t;
+	}
+	return v;
+}

@@ -105,6 +105,7 @@ struct gsa_ctx {
 	DevBuf d_s0q, d_s0r, d_s0l;    // stage-0 seed arrays (pre-overlap), kept only when dumps are enabled
 	int64_t n_s0 = 0;
 	bool keep_dumps = false;
+	bool host_results = true;      // gsa_fill copies fragments and rows to pinned host memory
 	std::vector<BlockHdr> final_blocks;   // after dedup, reference order
 
 	// fragments (after FillAlnBlockGaps) and K3 output

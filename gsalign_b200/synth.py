@@ -107,3 +107,25 @@ def read_fasta(path: str):
     if name is not None:
         out.append((name, np.frombuffer(b"".join(parts), dtype=np.uint8)))
     return out
+
+
+def make_dp_batch(rng, n_pairs, L, div=0.10, jitter=0.1):
+    """DP-only stress batch: n_pairs fragment pairs, query = ref with `div` substitutions, lengths
+    L*(1 +- jitter); returns (ref bytes, ref offsets, query bytes, query offsets) for gsa_dp_batch"""
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lens_r = np.maximum(1, (L * (1 + jitter * (rng.random(n_pairs) * 2 - 1))).astype(np.int64))
+    lens_q = np.maximum(1, lens_r + rng.integers(-min(3, L // 4), min(3, L // 4) + 1, size=n_pairs))
+    ro = np.zeros(n_pairs + 1, dtype=np.int64); ro[1:] = np.cumsum(lens_r)
+    qo = np.zeros(n_pairs + 1, dtype=np.int64); qo[1:] = np.cumsum(lens_q)
+    rb = acgt[rng.integers(0, 4, size=int(ro[-1]) + 1, dtype=np.uint8)]
+    qb = acgt[rng.integers(0, 4, size=int(qo[-1]) + 1, dtype=np.uint8)]
+    # copy the common prefix of every pair from the reference, then substitute
+    for i in range(n_pairs) if n_pairs <= 4096 else []:
+        k = int(min(lens_r[i], lens_q[i])); qb[qo[i]:qo[i] + k] = rb[ro[i]:ro[i] + k]
+    if n_pairs > 4096:  # vectorised: position-wise copy where both exist
+        idx_pair = np.repeat(np.arange(n_pairs), np.minimum(lens_r, lens_q))
+        within = np.arange(idx_pair.shape[0]) - np.repeat(np.concatenate([[0], np.cumsum(np.minimum(lens_r, lens_q))[:-1]]), np.minimum(lens_r, lens_q))
+        qb[qo[idx_pair] + within] = rb[ro[idx_pair] + within]
+    sub = rng.random(qb.shape[0]) < div
+    qb[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()), dtype=np.uint8)]
+    return rb, ro, qb, qo

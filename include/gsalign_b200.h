@@ -141,6 +141,11 @@ int gsa_cluster(gsa_ctx *ctx, int32_t *n_blocks);
  * pinned host memory and fills *out. */
 int gsa_fill(gsa_ctx *ctx, gsa_alignment *out);
 
+/* enable = 0: gsa_fill() leaves fragments and rows in device memory (frags / aln1 / aln2 of its output stay NULL; the block
+ * headers still come to the host) for consumers that read them there with gsa_result_device(), e.g. the record gather
+ * of a multi-GPU job.  Default 1. */
+int gsa_set_host_results(gsa_ctx *ctx, int enable);
+
 /* The result of the last gsa_fill() where it was produced: same struct, but frags / aln1 / aln2 are DEVICE pointers
  * (blocks stays a host pointer, O(#blocks)).  Valid until the next gsa_contig_begin*() on this context.  This is what a
  * multi-GPU host packs into its outbox for the single record gather over NVLink. */

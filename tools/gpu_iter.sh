@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-python bench.py --workload C2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_C2.json 2> gpurun_out/bench_C2.err; tail -2 gpurun_out/bench_C2.err | cut -c1-300; cut -c1-600 gpurun_out/bench_C2.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload C2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_C2_n2.json 2> gpurun_out/bench_C2_n2.err; tail -3 gpurun_out/bench_C2_n2.err | cut -c1-300; cut -c1-900 gpurun_out/bench_C2_n2.json
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+for w in C2 C3s C3; do python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; grep -v Warn gpurun_out/bench_$w.err | tail -2 | cut -c1-300; cat gpurun_out/bench_$w.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['phases_ms_per_step'], d['roofline']['frac'], d['roofline_k3'] and d['roofline_k3']['gcups'])"; done

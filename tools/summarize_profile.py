@@ -12,6 +12,8 @@ for path in sorted(glob.glob("gpurun_out/launches_*.csv")):
         v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]
         v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v * 1e6 if u == "s" else v
         name = re.sub(r"\(.*", "", re.sub(r"<.*", "", row["Kernel Name"]))[:50]
+        if re.match(r"k_ib_|k_fill_sa|k_build_|k_dpx_peak", name):   # index construction / upload / microbenchmark: setup, not the path
+            continue
         agg[name][0] += 1; agg[name][1] += v; tot += v
     out.append(f"\n## launch list {os.path.basename(path)} (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare SHARES)\n")
     out.append("| kernel | launches | total us | share |\n|---|---|---|---|")
