@@ -78,6 +78,7 @@ int gsa_create_shared(gsa_ctx *owner, gsa_ctx **out)
 	// the k-mer prefix table of the owner's current parameters is shared too (a lane with another seed length builds its own)
 	int k = owner->prm.min_seed_len < GSA_KTAB_MAX_K ? owner->prm.min_seed_len : GSA_KTAB_MAX_K;
 	GSA_TRY(gsa_impl_build_ktab(owner, k));
+	GSA_TRY(gsa_impl_build_kbits(owner, owner->prm.min_seed_len));
 	CUDA_TRY(owner, cudaStreamSynchronize(owner->stream));
 	gsa_ctx *ctx = nullptr;
 	int rc = gsa_create(owner->device, &ctx);
@@ -100,7 +101,7 @@ void gsa_destroy(gsa_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	DevBuf *bufs[] = {&ctx->d_occ, &ctx->d_txt, &ctx->d_sa, &ctx->d_ktab, &ctx->d_cend, &ctx->d_seq, &ctx->d_qpk, &ctx->d_qinv,
+	DevBuf *bufs[] = {&ctx->d_occ, &ctx->d_txt, &ctx->d_sa, &ctx->d_ktab, &ctx->d_kbits, &ctx->d_cend, &ctx->d_seq, &ctx->d_qpk, &ctx->d_qinv,
 	                  &ctx->d_counter, &ctx->d_sq, &ctx->d_sr, &ctx->d_sl, &ctx->d_cub, &ctx->d_cq, &ctx->d_cr, &ctx->d_cl, &ctx->d_cb,
 	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);

@@ -10,7 +10,8 @@
 #define GSA_SEED_CHUNK 10000   // SeedExplorationChunk, reference src/GSAlign.cpp:5 (observable: MEMs are cut at chunk ends)
 #define GSA_MAX_SEED_FREQ 100  // MaxSeedFreq, reference src/bwt_search.cpp:3
 #define GSA_MAX_SEED_GAP 5000  // MaxSeedGap, reference src/structure.h:23
-#define GSA_KTAB_MAX_K 12      // k-mer prefix table depth (never above MinSeedLength, see seed.cu)
+#define GSA_KTAB_MAX_K 12
+#define GSA_KBITS_MAX_K 16     // presence bitmap depth: 4^16 bits = 512 MB      // k-mer prefix table depth (never above MinSeedLength, see seed.cu)
 
 // ----------------------------------------------------------------------------------------------
 // Device index.  rows 0..n of the sorted suffix matrix of T$ (T = F . revcomp(F), |T| = n = 2N).
@@ -20,6 +21,8 @@
 //         rows [0, 64b) INCLUDING that placeholder.  One rank query = one 32-byte sector.
 //   txt   T itself, 2 bit per base, MSB first in u32 words (16 bases per word), padded with 2 words.
 //   sa    the FULL suffix array, u32 per row (n < 2^32 in this build): sa[row] = start of the suffix.
+//   kbits one bit per k-mer, k = min(MinSeedLength, 16): set iff the k-mer occurs in T (T is its own reverse complement).
+//         A search whose first k bases do not occur cannot yield a seed: zero index accesses for it.
 //   ktab  for every k-mer w (k = ktab_k, code = bases big-endian): the row interval {lo, size} of
 //         revcomp(w); size 0 = w does not occur in T.
 // ----------------------------------------------------------------------------------------------
@@ -28,10 +31,12 @@ struct DevIndex {
 	const uint32_t *txt;
 	const uint32_t *sa;
 	const uint2 *ktab;
+	const uint32_t *kbits; // presence bitmap of the kbits_k-mers of T (bit `code`): a clear bit = the search cannot reach kbits_k bases
 	uint32_t L2[5];
 	uint32_t primary;
 	uint32_t n;        // 2N
 	int ktab_k;
+	int kbits_k;
 };
 
 struct DevBuf {
@@ -78,7 +83,7 @@ struct gsa_ctx {
 	bool shares_index = false;     // lane created by gsa_create_shared: occ/txt/sa (and possibly ktab) belong to the owner
 	DevIndex ix;
 	int64_t N = 0;                 // GenomeSize
-	DevBuf d_occ, d_txt, d_sa, d_ktab, d_cend;
+	DevBuf d_occ, d_txt, d_sa, d_ktab, d_kbits, d_cend;
 	std::vector<ContigEnd> cend;   // sorted by end (forward and reverse ends of every contig)
 	std::vector<int64_t> contig_off; std::vector<int32_t> contig_len;
 
@@ -143,6 +148,7 @@ static inline unsigned gsa_grid(int64_t n, int block) { return (unsigned)((n + b
 // phase entry points implemented per translation unit
 int gsa_impl_index_upload(gsa_ctx *ctx, const gsa_index_view *v);
 int gsa_impl_build_ktab(gsa_ctx *ctx, int k);
+int gsa_impl_build_kbits(gsa_ctx *ctx, int k);
 int gsa_impl_pack_query(gsa_ctx *ctx);
 int gsa_impl_seed(gsa_ctx *ctx);
 int gsa_impl_cluster(gsa_ctx *ctx);

@@ -118,6 +118,35 @@ int gsa_impl_build_ktab(gsa_ctx *ctx, int k)
 	return GSA_OK;
 }
 
+// one thread per text position: marks the k-mer starting there (every window of T counts, junction-spanning ones included:
+// BWT_Search does not filter them either, SURVEY.md hazard H12)
+__global__ void k_build_kbits(DevIndex ix, int k, uint32_t *bits)
+{
+	uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p + (uint64_t)k > ix.n) return;
+	uint32_t code = gsa_pk_window(ix.txt, (uint32_t)p) >> (32 - 2 * k);
+	uint32_t bit = 1u << (code & 31);
+	uint32_t *w = bits + (code >> 5);
+	if (!(*w & bit)) atomicOr(w, bit); // most k-mers are already marked after the first pass over a repeat-free genome's 2 strands
+}
+
+int gsa_impl_build_kbits(gsa_ctx *ctx, int k)
+{
+	if (k > GSA_KBITS_MAX_K) k = GSA_KBITS_MAX_K;
+	if (k < 1) k = 1;
+	// worth its accesses only while most k-mers are absent from T: with |T| >= 4^k / 2 nearly every k-mer occurs
+	if ((double)ctx->ix.n >= 0.5 * (double)(1ull << (2 * k))) { ctx->ix.kbits = nullptr; ctx->ix.kbits_k = k; return GSA_OK; }
+	if (ctx->ix.kbits_k == k && ctx->ix.kbits) return GSA_OK;
+	size_t words = k >= 3 ? ((size_t)1 << (2 * k - 5)) : 1;
+	GSA_TRY(gsa_ensure(ctx, ctx->d_kbits, words * 4));
+	ctx->ix.kbits = nullptr; ctx->ix.kbits_k = 0;
+	CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_kbits.p, 0, words * 4, ctx->stream));
+	k_build_kbits<<<gsa_grid((int64_t)ctx->ix.n, 256), 256, 0, ctx->stream>>>(ctx->ix, k, (uint32_t *)ctx->d_kbits.p);
+	KERNEL_CHECK(ctx);
+	ctx->ix.kbits = (const uint32_t *)ctx->d_kbits.p; ctx->ix.kbits_k = k;
+	return GSA_OK;
+}
+
 int gsa_impl_index_upload(gsa_ctx *ctx, const gsa_index_view *v)
 {
 	if (!v || !v->bwt || !v->sa || !v->pac || v->n_contigs <= 0) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_index_upload: incomplete view");
@@ -129,7 +158,7 @@ int gsa_impl_index_upload(gsa_ctx *ctx, const gsa_index_view *v)
 	ctx->N = v->l_pac;
 	ctx->ix.n = (uint32_t)n; ctx->ix.primary = (uint32_t)v->primary;
 	for (int i = 0; i < 5; i++) ctx->ix.L2[i] = (uint32_t)v->L2[i];
-	ctx->ix.ktab = nullptr; ctx->ix.ktab_k = 0;
+	ctx->ix.ktab = nullptr; ctx->ix.ktab_k = 0; ctx->ix.kbits = nullptr; ctx->ix.kbits_k = 0;
 
 	uint64_t nblocks = (n >> 6) + 2, nwords = (n >> 4) + 3;
 	GSA_TRY(gsa_ensure(ctx, ctx->d_occ, nblocks * 32));

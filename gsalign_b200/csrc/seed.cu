@@ -68,8 +68,11 @@ struct SeedOut {
 struct SeedArgs {
 	const uint32_t *qpk, *qinv;
 	uint32_t qlen, nchunks;
+	uint32_t qpk_words, qinv_words; // allocated words of qpk / qinv
 	int min_seed_len, sensitive;
 };
+
+#define SEED_SPEC 0x40000000   // flag in the raw seed's len: found by a speculative walk, valid only from the lane's merge point on
 
 __device__ __forceinline__ void emit_seed(const SeedOut &o, unsigned long long slot, int32_t q, int64_t r, int32_t len)
 {
@@ -129,18 +132,18 @@ __device__ __forceinline__ void vis_mark(uint32_t *vis, uint32_t a, uint32_t b)
 }
 
 // Walks the chunk's search chain from `start` until it leaves [.., limit); returns the first chain start >= limit.
-//   MODE 0: speculative pass -- records every visited start of [base, limit) in vis
-//   MODE 1: repair pass      -- stops as soon as it lands on a start the speculative pass visited (returns UINT_MAX then)
-//   MODE 2: emitting pass    -- writes the seeds
+//   MODE 1: repair walk -- the true chain from the true entry of a sub-chunk: emits its seeds and stops as soon as it lands
+//           on a start the speculative walk visited (returns UINT_MAX then, the start in `merge`)
+//   (MODE 0 / 2, the straight-line speculative and emitting walks, are what seed_walk_pipe replaces)
 // Misses advance by one position, so a run of guaranteed misses (k-mer cut by a non-ACGT base or by the chunk end)
 // is a run of consecutive visited starts.
 template <int MODE>
 __device__ __forceinline__ uint32_t seed_walk(const DevIndex &ix, const SeedArgs &A, uint32_t start, uint32_t base, uint32_t limit, uint32_t stop,
-                                              uint32_t *vis, const SeedOut &out)
+                                              uint32_t *vis, const SeedOut &out, uint32_t &merge)
 {
 	const int K = ix.ktab_k;
 	while (start < limit) {
-		if (MODE == 1 && ((vis[(start - base) >> 5] >> ((start - base) & 31)) & 1)) return 0xFFFFFFFFu;
+		if (MODE == 1 && ((vis[(start - base) >> 5] >> ((start - base) & 31)) & 1)) { merge = start; return 0xFFFFFFFFu; }
 		if (start + K > stop) { // fewer than K (<= MinSeedLength) bases left in the chunk: misses all the way
 			if (MODE == 0) vis_mark(vis, start - base, limit - base);
 			return limit;
@@ -150,7 +153,7 @@ __device__ __forceinline__ uint32_t seed_walk(const DevIndex &ix, const SeedArgs
 			uint32_t ns = min(start + bad + 1, limit);
 			if (MODE == 0) vis_mark(vis, start - base, ns - base);
 			if (MODE == 1) { // any visited start inside the run merges the chains
-				for (uint32_t s2 = start + 1; s2 < ns; s2++) if ((vis[(s2 - base) >> 5] >> ((s2 - base) & 31)) & 1) return 0xFFFFFFFFu;
+				for (uint32_t s2 = start + 1; s2 < ns; s2++) if ((vis[(s2 - base) >> 5] >> ((s2 - base) & 31)) & 1) { merge = s2; return 0xFFFFFFFFu; }
 			}
 			start = ns;
 			continue;
@@ -159,7 +162,7 @@ __device__ __forceinline__ uint32_t seed_walk(const DevIndex &ix, const SeedArgs
 		uint32_t lo, size, rpos = 0;
 		int len = seed_search(ix, A.qpk, A.qinv, start, stop, K, lo, size, rpos);
 		if (len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ) {
-			if (MODE == 2) {
+			if (MODE >= 1) {
 				unsigned long long slot = atomicAdd(out.count, (unsigned long long)size);
 				if (size == 1) emit_seed(out, slot, (int32_t)start, (int64_t)rpos, len);
 				else
@@ -172,52 +175,274 @@ __device__ __forceinline__ uint32_t seed_walk(const DevIndex &ix, const SeedArgs
 	return start;
 }
 
+#ifdef SEED_PROFILE
+__device__ unsigned long long g_seed_prof[16]; // trips A, trips B, active lanes A, active lanes B, cycles A, resolve, B, repairs, searches A/B, fails
+#endif
+// ---- the pipelined walk ---------------------------------------------------------------------------------------------
+// The lanes of a warp walk different sub-chunks, so a straight-line search (table -> rank steps -> locate -> compare)
+// leaves them in different loops and the warp executes one lane's dependent DRAM access at a time.  Here every lane is a
+// small state machine instead: one trip of the warp-wide loop lets each lane consume the load it issued in the previous
+// trip and issue the next one, so the random 32-byte accesses of all 32 lanes are in flight together and the warp pays
+// one memory latency per trip, not one per lane.  The search semantics are those of seed_search / seed_walk above.
+enum { ST_DONE = 0, ST_NEXT, ST_PRES, ST_KTAB, ST_BWD, ST_SA, ST_CMP, ST_BWD_ISSUE, ST_AFTER_BWD, ST_CMP_ISSUE };
+#define SEED_LOOK 8   // starts whose presence bits are fetched together
+
+// the 16 bases at offset off (0..31) of the 48 held by three consecutive packed words
+__device__ __forceinline__ uint32_t win48(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t off)
+{
+	return off < 16 ? __funnelshift_l(w1, w0, off << 1) : __funnelshift_l(w2, w1, (off - 16) << 1);
+}
+
+// The chunk's slice of the packed query and of the invalid-base bitmap, staged in shared memory by its warp: the walk
+// reads them at every step, and in L1 they would compete with the random index sectors.
+#define SEED_QWORDS 632   // (10000 + 112) / 16 packed words
+#define SEED_IWORDS 320   // (16 + 10000 + 112) / 32 bitmap words, rounded up
+struct ChunkQuery {
+	const uint32_t *sq, *si;
+	uint32_t qb, ib;        // first base held by sq / si (qb = chunk start, a multiple of 16; ib = chunk start rounded down to 32)
+	__device__ __forceinline__ const uint32_t *words(uint32_t p) const { return sq + ((p - qb) >> 4); }
+	__device__ __forceinline__ uint32_t window(uint32_t p) const { const uint32_t *w = words(p); return __funnelshift_l(w[1], w[0], (p & 15) << 1); }
+	__device__ __forceinline__ int base(uint32_t p) const { return (int)(sq[(p - qb) >> 4] >> ((~p & 15) << 1)) & 3; }
+	__device__ __forceinline__ uint32_t inv_window(uint32_t p) const { const uint32_t *w = si + ((p - ib) >> 5); return __funnelshift_l(w[1], w[0], p & 31); }
+	__device__ __forceinline__ bool invalid(uint32_t p) const { return (si[(p - ib) >> 5] >> (~p & 31)) & 1; }
+};
+
+// Records every visited start of [base, limit) in vis and emits every seed it finds flagged SEED_SPEC.
+__device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const SeedArgs &A, const ChunkQuery &Q, uint32_t start, uint32_t base, uint32_t limit, uint32_t stop,
+                                                   uint32_t *vis, const SeedOut &out, bool active)
+{
+	const int K = ix.ktab_k, KB = ix.kbits_k, KMIN = A.min_seed_len, lane = threadIdx.x & 31;
+	const uint32_t *occw = (const uint32_t *)ix.occ;
+	uint32_t look = 0; // candidates of the presence lookahead in flight
+	bool retry = false; // the previous search of this lane failed: misses come in runs (two differences closer than MinSeedLength)
+	int st = (active && start < limit) ? ST_NEXT : ST_DONE;
+	uint32_t lo = 0, size = 0, pos = 0, tpos = 0, rpos = 0, r1 = 0, r2 = 0;
+	int c = 0;
+	// pending loads: one register set per kind of access.  Lanes in different states issue their loads from different
+	// branches of the same trip; if two branches loaded into the same register the second would have to wait for the first
+	// (write-after-write on the warp's scoreboard) and the branches' DRAM latencies would add up again.
+	uint4 bw_s1 = make_uint4(0, 0, 0, 0), bw_s2 = bw_s1; uint32_t bw_c1 = 0, bw_c2 = 0; // rank step: symbols + count of both blocks
+	uint32_t kt_lo = 0, kt_size = 0, sa_v = 0, tx0 = 0, tx1 = 0, tx2 = 0;                  // prefix table entry, SA entry, text words
+	uint32_t pr[SEED_LOOK] = {0, 0, 0, 0, 0, 0, 0, 0};                                      // presence words
+	while (__any_sync(0xffffffffu, st != ST_DONE)) {
+		bool fin = false;
+#ifdef SEED_PROFILE
+		if (lane == 0) { atomicAdd(&g_seed_prof[0], 1ull); atomicAdd(&g_seed_prof[2], (unsigned long long)__popc(__ballot_sync(0xffffffffu, st != ST_DONE))); }
+		else __ballot_sync(0xffffffffu, st != ST_DONE);
+#endif
+		// ---- consume the load issued in the previous trip ------------------------------------------------------------
+		if (st == ST_PRES) { // presence bits of the KB-mers at start .. start+look-1: the first present one is searched, the rest miss
+			const uint32_t *qw = Q.words(start);
+			const uint32_t w0 = qw[0], w1 = qw[1], w2 = qw[2], o = start & 15;
+			uint32_t f = look;
+#pragma unroll
+			for (int i = SEED_LOOK - 1; i >= 0; i--)
+				if ((uint32_t)i < look && ((pr[i] >> ((win48(w0, w1, w2, o + i) >> (32 - 2 * KB)) & 31)) & 1)) f = i;
+			vis_mark(vis, start - base, start - base + min(f + 1, look));
+			start += f;
+			if (f < look) {
+				uint2 iv = __ldg(ix.ktab + (win48(w0, w1, w2, o + f) >> (32 - 2 * K)));
+				kt_lo = iv.x; kt_size = iv.y;
+				st = ST_KTAB;
+			} else st = ST_NEXT;
+		} else if (st == ST_KTAB) {
+			lo = kt_lo; size = kt_size;
+			if (size == 0) { pos = start; fin = true; }
+			else { pos = start + K; st = ST_BWD_ISSUE; }
+		} else if (st == ST_BWD) {
+			uint32_t o1 = bw_c1 + gsa_block_count(bw_s1, c, (int)(r1 & 63) + 1) - (uint32_t)(c == 0 && r1 >= ix.primary);
+			uint32_t o2 = bw_c2 + gsa_block_count(bw_s2, c, (int)(r2 & 63) + 1) - (uint32_t)(c == 0 && r2 >= ix.primary);
+			if (o2 == o1) st = ST_AFTER_BWD;
+			else { lo = ix.L2[c] + o1 + 1; size = o2 - o1; pos++; st = ST_BWD_ISSUE; }
+		} else if (st == ST_SA) {
+			uint32_t m = pos - start;
+			rpos = ix.n - sa_v - m; tpos = rpos + m;
+			st = ST_CMP_ISSUE;
+		} else if (st == ST_CMP) { // 32 bases per trip: the text words were loaded last trip, the query sits in L1
+			uint32_t sh = (tpos & 15) << 1;
+			uint32_t t0 = __funnelshift_l(tx1, tx0, sh), t1 = __funnelshift_l(tx2, tx1, sh);
+			uint32_t x0 = Q.window(pos) ^ t0, x1 = Q.window(pos + 16) ^ t1;
+			uint32_t ext = x0 ? (uint32_t)(__clz(x0) >> 1) : 16u + (uint32_t)(__clz(x1) >> 1);
+			ext = min(ext, (uint32_t)__clz(Q.inv_window(pos)));         // first non-ACGT base
+			uint32_t lim = min(stop - pos, ix.n - tpos);
+			if (ext >= lim) { pos += lim; fin = true; }
+			else { pos += ext; tpos += ext; if (ext < 32) fin = true; else st = ST_CMP_ISSUE; }
+		}
+		// ---- decide the next access of a running search and issue it ------------------------------------------------------
+		if (st == ST_BWD_ISSUE) {
+			if (size > 1 && pos < stop && !Q.invalid(pos)) {
+				c = 3 - Q.base(pos);
+				r1 = lo - 1; r2 = lo + size - 1;
+				const size_t b1 = (size_t)(r1 >> 6), b2 = (size_t)(r2 >> 6);
+				bw_c1 = __ldg(occw + b1 * 8 + c); bw_s1 = __ldg(ix.occ + b1 * 2 + 1);
+				bw_c2 = __ldg(occw + b2 * 8 + c); bw_s2 = __ldg(ix.occ + b2 * 2 + 1);
+				st = ST_BWD;
+			} else st = ST_AFTER_BWD;
+		}
+		if (st == ST_AFTER_BWD) {
+			if (size == 1) { sa_v = __ldg(ix.sa + lo); st = ST_SA; }
+			else fin = true;
+		}
+		if (st == ST_CMP_ISSUE) {
+			if (pos < stop && tpos < ix.n) {
+				const uint32_t *tw = ix.txt + (tpos >> 4);
+				tx0 = __ldg(tw); tx1 = __ldg(tw + 1); tx2 = __ldg(tw + 2);
+				st = ST_CMP;
+			} else fin = true;
+		}
+		// ---- a search ended: seeds (emitting pass), next start ------------------------------------------------------------
+		uint32_t n_emit = 0; int len = 0;
+		if (fin) {
+#ifdef SEED_PROFILE
+			atomicAdd(&g_seed_prof[9], 1ull);
+#endif
+			len = (int)(pos - start);
+			if (len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ) n_emit = size;
+		}
+		if (__any_sync(0xffffffffu, n_emit != 0)) { // one counter update per warp: exclusive scan of the lanes' seed counts
+			uint32_t incl = n_emit;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+			unsigned long long wbase = 0;
+			if (lane == 31) wbase = atomicAdd(out.count, (unsigned long long)incl);
+			wbase = __shfl_sync(0xffffffffu, wbase, 31);
+			if (n_emit) {
+				unsigned long long slot = wbase + incl - n_emit;
+				if (size == 1) emit_seed(out, slot, (int32_t)start, (int64_t)rpos, len | SEED_SPEC);
+				else
+					for (uint32_t i = 0; i < size; i++)
+						emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - __ldg(ix.sa + lo + i) - (uint32_t)len), len | SEED_SPEC);
+			}
+		}
+		if (fin) {
+			start += n_emit ? (A.sensitive ? 5u : (uint32_t)len + 1u) : 1u;
+			retry = n_emit == 0;
+			st = ST_NEXT;
+		}
+		// ---- find the next search of this lane: guaranteed misses are skipped without touching the index -----------------
+		// (a search yields a seed only if it reaches MinSeedLength bases: impossible when the chunk ends or a non-ACGT base
+		// comes before that, or when the KB-mer (KB <= MinSeedLength) at the start does not occur in T at all)
+		if (st == ST_NEXT) {
+			st = ST_DONE;
+			while (start < limit) {
+				if (start + KMIN > stop) { // fewer than MinSeedLength bases left in the chunk: misses all the way
+					vis_mark(vis, start - base, limit - base);
+					start = limit;
+					break;
+				}
+				int bad = __clz(Q.inv_window(start)); // offset of the first non-ACGT base at or after start
+				if (bad < KMIN) { // every search starting in [start, start+bad] misses
+					uint32_t ns = min(start + bad + 1, limit);
+					vis_mark(vis, start - base, ns - base);
+					start = ns;
+					continue;
+				}
+				if (!retry || !ix.kbits) { // straight to the prefix table
+					vis[(start - base) >> 5] |= 1u << ((start - base) & 31);
+					uint2 iv = __ldg(ix.ktab + (Q.window(start) >> (32 - 2 * K)));
+					kt_lo = iv.x; kt_size = iv.y;
+					st = ST_KTAB;
+					break;
+				}
+				// starts start .. start+look-1 have MinSeedLength clean bases inside the chunk: fetch their presence bits together
+				look = min(min((uint32_t)SEED_LOOK, limit - start), min(stop - KMIN - start + 1, (uint32_t)(bad - KMIN + 1)));
+				const uint32_t *qw = Q.words(start);
+				const uint32_t w0 = qw[0], w1 = qw[1], w2 = qw[2], o = start & 15;
+#pragma unroll
+				for (int i = 0; i < SEED_LOOK; i++) if ((uint32_t)i < look) pr[i] = __ldg(ix.kbits + (win48(w0, w1, w2, o + i) >> (32 - 2 * KB + 5)));
+				st = ST_PRES;
+				break;
+			}
+		}
+	}
+	return start;
+}
+
 // One warp per 10 kb chunk, one lane per 313-bp sub-chunk.  The chain of search starts inside a chunk is serial
 // (reference src/GSAlign.cpp:70-93), but chains started anywhere re-synchronise at the next mismatch, so:
-//   pass A  every lane walks its sub-chunk speculatively from the sub-chunk's first base and records the visited starts;
+//   walk    every lane walks its sub-chunk speculatively from the sub-chunk's first base, records the visited starts and
+//           emits the seeds it finds, flagged speculative;
 //   resolve lane by lane, the true entry point of sub-chunk j (= exit of the true chain from sub-chunk j-1) is looked
-//           up in lane j's visited set; if it is not there the lane repairs by walking from the true entry until it
-//           merges with its speculative chain (rare: needs a spurious seed spanning the entry);
-//   pass B  every lane re-walks from its true entry and emits.  Results are exactly the serial chain's.
+//           up in lane j's visited set; if it is not there the lane walks the true chain from the true entry (emitting
+//           its seeds unflagged) until it merges with the speculative chain (rare: needs a spurious seed spanning the
+//           entry).  From the merge point on the speculative chain IS the true chain, so the lane's speculative seeds
+//           are valid from there on and void before: the merge point goes to merge_from[] and k_seed_keys drops the rest.
+// Results are exactly the serial chain's; every search of the true chain is done once.
 __global__ void __launch_bounds__(32 * SEED_WARPS)
-k_seed(DevIndex ix, SeedArgs A, SeedOut out)
+k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 {
 	__shared__ uint32_t s_vis[SEED_WARPS][32][SEED_VIS_WORDS];
+	__shared__ uint32_t s_q[SEED_WARPS][SEED_QWORDS], s_i[SEED_WARPS][SEED_IWORDS];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	uint32_t chunk = blockIdx.x * SEED_WARPS + wib;
 	if (chunk >= A.nchunks) return;
 	uint32_t cs = chunk * GSA_SEED_CHUNK, stop = min(cs + GSA_SEED_CHUNK, A.qlen);
+	ChunkQuery Q; Q.sq = s_q[wib]; Q.si = s_i[wib]; Q.qb = cs; Q.ib = cs & ~31u;
+	for (uint32_t w = lane; w < SEED_QWORDS; w += 32) { uint32_t g = (cs >> 4) + w; s_q[wib][w] = g < A.qpk_words ? __ldg(A.qpk + g) : 0u; }
+	for (uint32_t w = lane; w < SEED_IWORDS; w += 32) { uint32_t g = (cs >> 5) + w; s_i[wib][w] = g < A.qinv_words ? __ldg(A.qinv + g) : 0xFFFFFFFFu; }
+	__syncwarp();
 	uint32_t base = min(cs + lane * SEED_SUB, stop), limit = min(base + SEED_SUB, stop);
 	uint32_t *vis = s_vis[wib][lane];
 #pragma unroll
 	for (int w = 0; w < SEED_VIS_WORDS; w++) vis[w] = 0;
-	uint32_t spec_exit = seed_walk<0>(ix, A, base, base, limit, stop, vis, out);
+#ifdef SEED_PROFILE
+	long long t0 = clock64();
+#endif
+	uint32_t spec_exit = seed_walk_pipe(ix, A, Q, base, base, limit, stop, vis, out, true);
 	__syncwarp();
+#ifdef SEED_PROFILE
+	long long t1 = clock64();
+#endif
 	// resolve the true entry of every sub-chunk
-	uint32_t entry = cs, my_entry = cs;
+	uint32_t entry = cs, merge = 0xFFFFFFFFu;
 	for (int j = 0; j < 32; j++) {
 		uint32_t ex = entry;
-		if (lane == j) {
-			my_entry = entry;
-			if (entry < limit) {
-				if ((vis[(entry - base) >> 5] >> ((entry - base) & 31)) & 1) ex = spec_exit;
-				else { ex = seed_walk<1>(ix, A, entry, base, limit, stop, vis, out); if (ex == 0xFFFFFFFFu) ex = spec_exit; }
+		if (lane == j && entry < limit) {
+			if ((vis[(entry - base) >> 5] >> ((entry - base) & 31)) & 1) { merge = entry; ex = spec_exit; }
+			else {
+#ifdef SEED_PROFILE
+				atomicAdd(&g_seed_prof[7], 1ull);
+#endif
+				ex = seed_walk<1>(ix, A, entry, base, limit, stop, vis, out, merge);
+				if (ex == 0xFFFFFFFFu) ex = spec_exit;
 			}
 		}
 		entry = __shfl_sync(0xffffffffu, ex, j);
 	}
-	if (my_entry < limit) seed_walk<2>(ix, A, my_entry, base, limit, stop, vis, out);
+	merge_from[chunk * 32 + lane] = merge;
+#ifdef SEED_PROFILE
+	if (lane == 0) { long long t2 = clock64(); atomicAdd(&g_seed_prof[4], (unsigned long long)(t1 - t0)); atomicAdd(&g_seed_prof[5], (unsigned long long)(t2 - t1)); atomicAdd(&g_seed_prof[8], 1ull); }
+#endif
 }
+
+#ifdef SEED_PROFILE
+extern "C" int gsa_seed_profile(unsigned long long *out16, int reset)
+{
+	cudaDeviceSynchronize();
+	if (cudaMemcpyFromSymbol(out16, g_seed_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+	if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_seed_prof, z, sizeof(z)); }
+	return 0;
+}
+#endif
 
 // sort key: ((PosDiff + 2^31) << 31) | qPos -- a strict total order on seeds, identical to CompByPosDiff
 // (reference src/ProcessCandidateAlignment.cpp:3-7).  PosDiff + 2^31 < 2^33 because |T| < 2^32 here.
-__global__ void k_seed_keys(const int32_t *q, const int64_t *r, uint64_t *key, uint32_t *val, int64_t n)
+// Raw seeds flagged SEED_SPEC count only from their sub-chunk's merge point on (see k_seed); the others get the largest
+// key, sort to the end and are dropped.  *n_valid receives the number of real seeds.
+__global__ void k_seed_keys(const int32_t *q, const int64_t *r, const int32_t *len, const uint32_t *merge_from, uint64_t *key, uint32_t *val, int64_t n,
+                            unsigned long long *n_valid)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint64_t pd = (uint64_t)(r[i] - q[i] + (1ll << 31));
-	key[i] = (pd << 31) | (uint64_t)(uint32_t)q[i];
-	val[i] = (uint32_t)i;
+	bool ok = false;
+	if (i < n) {
+		uint32_t qi = (uint32_t)q[i], chunk = qi / GSA_SEED_CHUNK, sub = (qi - chunk * GSA_SEED_CHUNK) / SEED_SUB;
+		ok = !(len[i] & SEED_SPEC) || qi >= merge_from[chunk * 32 + sub];
+		uint64_t pd = (uint64_t)(r[i] - q[i] + (1ll << 31));
+		key[i] = ok ? (pd << 31) | (uint64_t)qi : ~0ull;
+		val[i] = (uint32_t)i;
+	}
+	unsigned m = __ballot_sync(0xffffffffu, ok);
+	if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
 }
 
 __global__ void k_seed_gather(const uint32_t *perm, const int32_t *q, const int64_t *r, const int32_t *l,
@@ -226,13 +451,14 @@ __global__ void k_seed_gather(const uint32_t *perm, const int32_t *q, const int6
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t s = perm[i];
-	oq[i] = q[s]; orr[i] = r[s]; ol[i] = l[s];
+	oq[i] = q[s]; orr[i] = r[s]; ol[i] = l[s] & ~SEED_SPEC;
 }
 
 int gsa_impl_seed(gsa_ctx *ctx)
 {
 	int k = ctx->prm.min_seed_len < GSA_KTAB_MAX_K ? ctx->prm.min_seed_len : GSA_KTAB_MAX_K;
 	GSA_TRY(gsa_impl_build_ktab(ctx, k));
+	GSA_TRY(gsa_impl_build_kbits(ctx, ctx->prm.min_seed_len));
 	uint32_t nchunks = (ctx->qlen + GSA_SEED_CHUNK - 1) / GSA_SEED_CHUNK;
 	GSA_TRY(gsa_ensure(ctx, ctx->d_counter, 1024));
 	unsigned long long *d_count = (unsigned long long *)ctx->d_counter.p;
@@ -246,14 +472,16 @@ int gsa_impl_seed(gsa_ctx *ctx)
 		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[0], cap * 4));
 		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[1], cap * 8));
 		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[2], cap * 4));
-		CUDA_TRY(ctx, cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[7], (size_t)(nchunks + 1) * 32 * 4)); // merge point per sub-chunk
+		CUDA_TRY(ctx, cudaMemsetAsync(d_count, 0, 16, ctx->stream));
 		SeedOut so; so.q = (int32_t *)ctx->d_tmp[0].p; so.r = (int64_t *)ctx->d_tmp[1].p; so.len = (int32_t *)ctx->d_tmp[2].p;
 		so.count = d_count; so.capacity = cap;
 		if (nchunks > 0) {
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
 			SeedArgs sa; sa.qpk = (const uint32_t *)ctx->d_qpk.p; sa.qinv = (const uint32_t *)ctx->d_qinv.p; sa.qlen = ctx->qlen; sa.nchunks = nchunks;
+			sa.qpk_words = 2 * ((ctx->qlen >> 5) + 2); sa.qinv_words = (ctx->qlen >> 5) + 2;
 			sa.min_seed_len = ctx->prm.min_seed_len; sa.sensitive = ctx->prm.sensitive;
-			k_seed<<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so);
+			k_seed<<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so, (uint32_t *)ctx->d_tmp[7].p);
 			KERNEL_CHECK(ctx);
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
 		}
@@ -264,24 +492,31 @@ int gsa_impl_seed(gsa_ctx *ctx)
 		cap = produced + 1024; // the kernel kept counting: rerun once with room for everything
 	}
 	if (produced > cap) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_seed: seed buffer overflow");
-	int64_t n = (int64_t)produced;
-	ctx->n_seeds = n;
+	// raw seeds (speculative ones included) -> keys -> sort; the void ones sort to the end and only the real ones are gathered
+	int64_t nraw = (int64_t)produced, n = 0;
 	if (ctx->qlen > 0) ctx->seed_density = std::max(ctx->seed_density, (double)produced / ctx->qlen);
+	if (nraw > 0) {
+		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[3], (size_t)nraw * 8)); // keys in
+		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[4], (size_t)nraw * 8)); // keys out
+		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[5], (size_t)nraw * 4)); // vals in
+		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[6], (size_t)nraw * 4)); // vals out
+		k_seed_keys<<<gsa_grid(nraw, 256), 256, 0, ctx->stream>>>((int32_t *)ctx->d_tmp[0].p, (int64_t *)ctx->d_tmp[1].p, (int32_t *)ctx->d_tmp[2].p, (const uint32_t *)ctx->d_tmp[7].p,
+		                                                         (uint64_t *)ctx->d_tmp[3].p, (uint32_t *)ctx->d_tmp[5].p, nraw, d_count + 1);
+		KERNEL_CHECK(ctx);
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small.p, d_count + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		size_t tmp_bytes = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint64_t *)ctx->d_tmp[3].p, (uint64_t *)ctx->d_tmp[4].p, (uint32_t *)ctx->d_tmp[5].p, (uint32_t *)ctx->d_tmp[6].p, nraw, 0, 64, ctx->stream);
+		GSA_TRY(gsa_ensure(ctx, ctx->d_cub, tmp_bytes));
+		CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, tmp_bytes, (uint64_t *)ctx->d_tmp[3].p, (uint64_t *)ctx->d_tmp[4].p, (uint32_t *)ctx->d_tmp[5].p, (uint32_t *)ctx->d_tmp[6].p, nraw, 0, 64, ctx->stream));
+		ctx->tm.launches += 4; // cub radix sort passes (upsweep/scan/downsweep family)
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		n = (int64_t)*(unsigned long long *)ctx->h_small.p;
+	}
+	ctx->n_seeds = n;
 	GSA_TRY(gsa_ensure(ctx, ctx->d_sq, (size_t)(n + 1) * 4));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_sr, (size_t)(n + 1) * 8));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_sl, (size_t)(n + 1) * 4));
 	if (n > 0) {
-		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[3], (size_t)n * 8)); // keys in
-		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[4], (size_t)n * 8)); // keys out
-		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[5], (size_t)n * 4)); // vals in
-		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[6], (size_t)n * 4)); // vals out
-		k_seed_keys<<<gsa_grid(n, 256), 256, 0, ctx->stream>>>((int32_t *)ctx->d_tmp[0].p, (int64_t *)ctx->d_tmp[1].p, (uint64_t *)ctx->d_tmp[3].p, (uint32_t *)ctx->d_tmp[5].p, n);
-		KERNEL_CHECK(ctx);
-		size_t tmp_bytes = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint64_t *)ctx->d_tmp[3].p, (uint64_t *)ctx->d_tmp[4].p, (uint32_t *)ctx->d_tmp[5].p, (uint32_t *)ctx->d_tmp[6].p, n, 0, 64, ctx->stream);
-		GSA_TRY(gsa_ensure(ctx, ctx->d_cub, tmp_bytes));
-		CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, tmp_bytes, (uint64_t *)ctx->d_tmp[3].p, (uint64_t *)ctx->d_tmp[4].p, (uint32_t *)ctx->d_tmp[5].p, (uint32_t *)ctx->d_tmp[6].p, n, 0, 64, ctx->stream));
-		ctx->tm.launches += 4; // cub radix sort passes (upsweep/scan/downsweep family)
 		k_seed_gather<<<gsa_grid(n, 256), 256, 0, ctx->stream>>>((uint32_t *)ctx->d_tmp[6].p, (int32_t *)ctx->d_tmp[0].p, (int64_t *)ctx->d_tmp[1].p, (int32_t *)ctx->d_tmp[2].p,
 		                                                        (int32_t *)ctx->d_sq.p, (int64_t *)ctx->d_sr.p, (int32_t *)ctx->d_sl.p, n);
 		KERNEL_CHECK(ctx);
