@@ -10,7 +10,7 @@
 #define GSA_SEED_CHUNK 10000   // SeedExplorationChunk, reference src/GSAlign.cpp:5 (observable: MEMs are cut at chunk ends)
 #define GSA_MAX_SEED_FREQ 100  // MaxSeedFreq, reference src/bwt_search.cpp:3
 #define GSA_MAX_SEED_GAP 5000  // MaxSeedGap, reference src/structure.h:23
-#define GSA_KTAB_MAX_K 12
+#define GSA_KTAB_MAX_K 14
 #define GSA_KBITS_MAX_K 16     // presence bitmap depth: 4^16 bits = 512 MB      // k-mer prefix table depth (never above MinSeedLength, see seed.cu)
 
 // ----------------------------------------------------------------------------------------------

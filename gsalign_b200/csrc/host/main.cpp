@@ -4,6 +4,7 @@
 // then the emitters on the host.  Query contigs are independent, so with -gpus N they are dealt to N
 // GPUs (longest first); records are emitted in contig order whatever GPU produced them.
 #include <ctype.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 #include <algorithm>
@@ -57,6 +58,18 @@ static bool index_files_present(const std::string &prefix)
 	return true;
 }
 
+// GSA_TIMING=1: wall-clock of the host-side stages on stderr (development aid, silent otherwise)
+#include <chrono>
+static void tick(const char *what)
+{
+	static const bool on = getenv("GSA_TIMING") != nullptr;
+	static auto t0 = std::chrono::steady_clock::now(), last = t0;
+	if (!on) return;
+	auto now = std::chrono::steady_clock::now();
+	fprintf(stderr, "[timing] %-28s +%.3f s (total %.3f s)\n", what, std::chrono::duration<double>(now - last).count(), std::chrono::duration<double>(now - t0).count());
+	last = now;
+}
+
 struct Worker {
 	gsa_ctx *ctx = nullptr;
 	std::thread th;
@@ -102,10 +115,12 @@ int main(int argc, char *argv[])
 	else if (!check_output_prefix(o.out_prefix)) return 0;
 
 	time_t t_start = time(NULL);
+	tick("start");
 	fprintf(stderr, "Step1. Load the two genome sequences...\n");
 	std::vector<QueryChr> query;
 	if (!check_input_file(o.query) || !load_query_file(o.query, query)) { fprintf(stderr, "Please check the query file: %s\n", o.query); return 0; }
 
+	tick("query loaded");
 	HostIndex ix;
 	std::string err, prefix;
 	if (o.index_prefix && index_files_present(o.index_prefix)) prefix = o.index_prefix;
@@ -116,6 +131,7 @@ int main(int argc, char *argv[])
 		if (gsa_build_index_files(o.ref_fa, prefix.c_str(), 0) != 0) { fprintf(stderr, "\n\nError! Please check your input!\n"); return 0; }
 	} else { fprintf(stderr, "Please specify a valid reference genome\n"); return 0; }
 	if (!ix.load(prefix, err)) { fprintf(stderr, "\n\nError! Please check your input! (%s)\n", err.c_str()); return 0; }
+	tick("index files loaded");
 	fprintf(stderr, "\tLoad the reference sequences (%d %s)\n", (int)ix.names.size(), ix.names.size() > 1 ? "chromosomes" : "chromosome");
 	if (o.sensitive) o.min_seed_len = 10; // src/main.cpp:323
 	if (o.show_plot) fprintf(stderr, "Warning! dot-plots need gnuplot and are not produced by this build\n");
@@ -147,6 +163,7 @@ int main(int argc, char *argv[])
 			if (gsa_create_shared(ctx[g][0], &ctx[g][l]) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g][0])); return 0; }
 	}
 
+	tick("contexts + index upload");
 	// ---- GenomeComparison ------------------------------------------------------------------------------------------------
 	fprintf(stderr, "Step2. Sequence analysis for all query chromosomes\n");
 	std::vector<ContigResult> results((size_t)nq);
@@ -191,6 +208,7 @@ int main(int argc, char *argv[])
 		r = ContigResult();
 	}
 	for (auto &t : threads) t.join();
+	tick("align + emit");
 	if (st.local_aln_num > 0)
 		fprintf(stderr, "\tAlignment#=%d (total alignment length=%lld) ANI=%.2f%%, unique alignment#=%d\n", (int)st.local_aln_num, (long long)st.total_aln_len,
 		        100 * (1.0 * st.total_matches / st.total_aln_len), (int)(st.local_aln_num - st.dup_num));
@@ -199,6 +217,8 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "\nGSAlign identifies %d SNVs, %d insertions, and %d deletions [%s].\n\n", st.iSNV, st.iInsertion, st.iDeletion, o.vcf_name.c_str());
 		output_variants(o, ix, st);
 	}
+	tick("variants written");
 	for (auto &v : ctx) for (size_t l = v.size(); l-- > 0;) gsa_destroy(v[l]); // lanes first, the index owner last
+	tick("contexts destroyed");
 	return 0;
 }

@@ -186,6 +186,8 @@ __device__ unsigned long long g_seed_prof[16]; // trips A, trips B, active lanes
 // one memory latency per trip, not one per lane.  The search semantics are those of seed_search / seed_walk above.
 enum { ST_DONE = 0, ST_NEXT, ST_PRES, ST_KTAB, ST_BWD, ST_SA, ST_CMP, ST_BWD_ISSUE, ST_AFTER_BWD, ST_CMP_ISSUE };
 #define SEED_LOOK 8   // starts whose presence bits are fetched together
+#define SEED_PREROLL 24      // bases a speculative walk starts before its sub-chunk (default mode: chains merge at the next difference)
+#define SEED_PREROLL_SEN 64  // sensitive mode steps by 5 after a hit, so chains take longer to fall in step
 
 // the 16 bases at offset off (0..31) of the 48 held by three consecutive packed words
 __device__ __forceinline__ uint32_t win48(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t off)
@@ -213,6 +215,8 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 {
 	const int K = ix.ktab_k, KB = ix.kbits_k, KMIN = A.min_seed_len, lane = threadIdx.x & 31;
 	const uint32_t *occw = (const uint32_t *)ix.occ;
+	// the walk may start a little before `base` (pre-roll, see k_seed): starts below base are neither recorded nor emitted
+	auto mark = [&](uint32_t a, uint32_t b) { a = max(a, base); if (a < b) vis_mark(vis, a - base, b - base); };
 	uint32_t look = 0; // candidates of the presence lookahead in flight
 	bool retry = false; // the previous search of this lane failed: misses come in runs (two differences closer than MinSeedLength)
 	int st = (active && start < limit) ? ST_NEXT : ST_DONE;
@@ -238,7 +242,7 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 #pragma unroll
 			for (int i = SEED_LOOK - 1; i >= 0; i--)
 				if ((uint32_t)i < look && ((pr[i] >> ((win48(w0, w1, w2, o + i) >> (32 - 2 * KB)) & 31)) & 1)) f = i;
-			vis_mark(vis, start - base, start - base + min(f + 1, look));
+			mark(start, start + min(f + 1, look));
 			start += f;
 			if (f < look) {
 				uint2 iv = __ldg(ix.ktab + (win48(w0, w1, w2, o + f) >> (32 - 2 * K)));
@@ -291,13 +295,14 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 			} else fin = true;
 		}
 		// ---- a search ended: seeds (emitting pass), next start ------------------------------------------------------------
-		uint32_t n_emit = 0; int len = 0;
+		uint32_t n_emit = 0; int len = 0; bool hit = false;
 		if (fin) {
 #ifdef SEED_PROFILE
 			atomicAdd(&g_seed_prof[9], 1ull);
 #endif
 			len = (int)(pos - start);
-			if (len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ) n_emit = size;
+			hit = len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ;
+			if (hit && start >= base) n_emit = size;
 		}
 		if (__any_sync(0xffffffffu, n_emit != 0)) { // one counter update per warp: exclusive scan of the lanes' seed counts
 			uint32_t incl = n_emit;
@@ -315,8 +320,8 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 			}
 		}
 		if (fin) {
-			start += n_emit ? (A.sensitive ? 5u : (uint32_t)len + 1u) : 1u;
-			retry = n_emit == 0;
+			start += hit ? (A.sensitive ? 5u : (uint32_t)len + 1u) : 1u;
+			retry = !hit;
 			st = ST_NEXT;
 		}
 		// ---- find the next search of this lane: guaranteed misses are skipped without touching the index -----------------
@@ -326,19 +331,19 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 			st = ST_DONE;
 			while (start < limit) {
 				if (start + KMIN > stop) { // fewer than MinSeedLength bases left in the chunk: misses all the way
-					vis_mark(vis, start - base, limit - base);
+					mark(start, limit);
 					start = limit;
 					break;
 				}
 				int bad = __clz(Q.inv_window(start)); // offset of the first non-ACGT base at or after start
 				if (bad < KMIN) { // every search starting in [start, start+bad] misses
 					uint32_t ns = min(start + bad + 1, limit);
-					vis_mark(vis, start - base, ns - base);
+					mark(start, ns);
 					start = ns;
 					continue;
 				}
 				if (!retry || !ix.kbits) { // straight to the prefix table
-					vis[(start - base) >> 5] |= 1u << ((start - base) & 31);
+					mark(start, start + 1);
 					uint2 iv = __ldg(ix.ktab + (Q.window(start) >> (32 - 2 * K)));
 					kt_lo = iv.x; kt_size = iv.y;
 					st = ST_KTAB;
@@ -388,7 +393,10 @@ k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 #ifdef SEED_PROFILE
 	long long t0 = clock64();
 #endif
-	uint32_t spec_exit = seed_walk_pipe(ix, A, Q, base, base, limit, stop, vis, out, true);
+	// pre-roll: start a little before the sub-chunk so that the walk has usually fallen in step with the true chain by
+	// the time it reaches `base` (chains merge at the first start they share); saves most of the serial repair walks
+	const uint32_t pre = min((uint32_t)(A.sensitive ? SEED_PREROLL_SEN : SEED_PREROLL), base - cs);
+	uint32_t spec_exit = seed_walk_pipe(ix, A, Q, base - pre, base, limit, stop, vis, out, base < limit);
 	__syncwarp();
 #ifdef SEED_PROFILE
 	long long t1 = clock64();
