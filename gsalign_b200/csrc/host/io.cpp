@@ -1,4 +1,7 @@
 // io.cpp -- BWA-format index reader and query FASTA reader of bin/GSAlign.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <string.h>
 #include <algorithm>
 #include <fstream>
@@ -113,28 +116,42 @@ bool check_input_file(const char *path)
 }
 
 bool load_query_file(const char *path, std::vector<QueryChr> &out)
-{
-	std::ifstream f(path);
-	if (!f.is_open()) return false;
-	std::string s;
+{ // LoadQueryFile, src/main.cpp:82-114: one bulk read, then line by line with memchr (same acceptance rules)
+	FILE *fp = fopen(path, "rb");
+	if (!fp) return false;
+	std::string buf;
+	{
+		fseek(fp, 0, SEEK_END);
+		long sz = ftell(fp);
+		fseek(fp, 0, SEEK_SET);
+		if (sz > 0) { buf.resize((size_t)sz); if (fread(&buf[0], 1, (size_t)sz, fp) != (size_t)sz) { fclose(fp); return false; } }
+		fclose(fp);
+	}
 	int idx = -1;
-	while (!f.eof()) {
-		std::getline(f, s);
-		if (s.empty()) continue;
-		if (s[0] == '>') {
-			out.push_back(QueryChr()); idx++;
-			out[idx].name = trim_chromosome_name(s.substr(1));
-		} else {
-			if (s[s.size() - 1] == '\r') s.resize(s.size() - 1);   // CheckQuerySeq, src/main.cpp:66-80
-			for (size_t i = 0; i < s.size(); i++)
-				if (!isalpha((unsigned char)s[i])) {
-					printf("%s\n", s.c_str());
-					fprintf(stderr, "The query sequence contains non-alphabet characters!\n");
-					return false;
-				}
-			if (idx < 0) return false;
-			out[idx].seq.append(s);
+	const char *p = buf.data(), *end = p + buf.size();
+	while (p < end) {
+		const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+		const char *le = nl ? nl : end;
+		size_t len = (size_t)(le - p);
+		if (len > 0) {
+			if (p[0] == '>') {
+				out.push_back(QueryChr()); idx++;
+				out[idx].name = trim_chromosome_name(std::string(p + 1, len - 1));
+				const char *nx = (const char *)memmem(le, (size_t)(end - le), "\n>", 2); // this record ends at the next header
+				out[idx].seq.reserve((size_t)((nx ? nx : end) - le));
+			} else {
+				if (p[len - 1] == '\r') len--;   // CheckQuerySeq, src/main.cpp:66-80
+				for (size_t i = 0; i < len; i++)
+					if (!isalpha((unsigned char)p[i])) {
+						printf("%.*s\n", (int)len, p);
+						fprintf(stderr, "The query sequence contains non-alphabet characters!\n");
+						return false;
+					}
+				if (idx < 0) return false;
+				out[idx].seq.append(p, len);
+			}
 		}
+		p = nl ? nl + 1 : end;
 	}
 	fprintf(stderr, "\tLoad the query sequences (%d %s)\n", (int)out.size(), out.size() > 1 ? "chromosomes" : "chromosome");
 	return !out.empty();

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
@@ -117,23 +118,42 @@ int main(int argc, char *argv[])
 	time_t t_start = time(NULL);
 	tick("start");
 	fprintf(stderr, "Step1. Load the two genome sequences...\n");
-	std::vector<QueryChr> query;
-	if (!check_input_file(o.query) || !load_query_file(o.query, query)) { fprintf(stderr, "Please check the query file: %s\n", o.query); return 0; }
-
-	tick("query loaded");
-	HostIndex ix;
-	std::string err, prefix;
-	if (o.index_prefix && index_files_present(o.index_prefix)) prefix = o.index_prefix;
-	else if (o.ref_fa && check_input_file(o.ref_fa)) {
-		prefix = o.ref_fa;
-		size_t p = prefix.find_last_of('.');
-		if (p != std::string::npos && p > 0) prefix.resize(p);
-		if (gsa_build_index_files(o.ref_fa, prefix.c_str(), 0) != 0) { fprintf(stderr, "\n\nError! Please check your input!\n"); return 0; }
-	} else { fprintf(stderr, "Please specify a valid reference genome\n"); return 0; }
-	if (!ix.load(prefix, err)) { fprintf(stderr, "\n\nError! Please check your input! (%s)\n", err.c_str()); return 0; }
-	tick("index files loaded");
-	fprintf(stderr, "\tLoad the reference sequences (%d %s)\n", (int)ix.names.size(), ix.names.size() > 1 ? "chromosomes" : "chromosome");
 	if (o.sensitive) o.min_seed_len = 10; // src/main.cpp:323
+	gsa_params prm; gsa_default_params(&prm);
+	prm.min_seed_len = o.min_seed_len; prm.sensitive = o.sensitive; prm.max_indel = o.max_indel; prm.min_block_score = o.min_block_score;
+	prm.min_aln_len = o.min_aln_len; prm.min_idy = o.min_idy; prm.one_on_one = o.one_on_one;
+
+	// The reference side (index files -> host -> every GPU's HBM) is prepared by a helper thread while this thread
+	// parses the query FASTA; the messages keep the reference's order.
+	HostIndex ix;
+	std::string idx_err;   // empty = ok; otherwise the message to print
+	int n_dev = std::max(1, o.n_gpus);
+	std::vector<gsa_ctx *> owners((size_t)n_dev, nullptr);
+	std::thread idx_thread([&] {
+		std::string err, prefix;
+		if (o.index_prefix && index_files_present(o.index_prefix)) prefix = o.index_prefix;
+		else if (o.ref_fa && check_input_file(o.ref_fa)) {
+			prefix = o.ref_fa;
+			size_t p = prefix.find_last_of('.');
+			if (p != std::string::npos && p > 0) prefix.resize(p);
+			if (gsa_build_index_files(o.ref_fa, prefix.c_str(), 0) != 0) { idx_err = "\n\nError! Please check your input!\n"; return; }
+		} else { idx_err = "Please specify a valid reference genome\n"; return; }
+		if (!ix.load(prefix, err)) { idx_err = "\n\nError! Please check your input! (" + err + ")\n"; return; }
+		tick("index files loaded");
+		gsa_index_view view; ix.view(&view);
+		for (int g = 0; g < n_dev; g++) {
+			if (gsa_create(g, &owners[g]) != 0) { idx_err = "FatalError: cannot open CUDA device " + std::to_string(g) + " (this build has no CPU path)\n"; return; }
+			if (gsa_set_params(owners[g], &prm) != 0 || gsa_index_upload(owners[g], &view) != 0) { idx_err = std::string("FatalError: ") + gsa_last_error(owners[g]) + "\n"; return; }
+		}
+		tick("index uploaded");
+	});
+	std::vector<QueryChr> query;
+	bool query_ok = check_input_file(o.query) && load_query_file(o.query, query);
+	tick("query loaded");
+	idx_thread.join();
+	if (!query_ok) { fprintf(stderr, "Please check the query file: %s\n", o.query); return 0; }
+	if (!idx_err.empty()) { fprintf(stderr, "%s", idx_err.c_str()); return 0; }
+	fprintf(stderr, "\tLoad the reference sequences (%d %s)\n", (int)ix.names.size(), ix.names.size() > 1 ? "chromosomes" : "chromosome");
 	if (o.show_plot) fprintf(stderr, "Warning! dot-plots need gnuplot and are not produced by this build\n");
 	std::string op = o.out_prefix;
 	if (o.out_format == 1) o.maf = op + ".maf";
@@ -141,12 +161,8 @@ int main(int argc, char *argv[])
 	o.vcf_name = op + ".vcf";
 
 	// ---- one index replica per GPU; on every GPU `lanes` contexts share it (gsa_create_shared), one host thread each ---------
-	gsa_params prm; gsa_default_params(&prm);
-	prm.min_seed_len = o.min_seed_len; prm.sensitive = o.sensitive; prm.max_indel = o.max_indel; prm.min_block_score = o.min_block_score;
-	prm.min_aln_len = o.min_aln_len; prm.min_idy = o.min_idy; prm.one_on_one = o.one_on_one;
-	gsa_index_view view; ix.view(&view);
 	int nq = (int)query.size();
-	int ngpu = std::min<int>(o.n_gpus, nq);
+	int ngpu = std::min<int>(n_dev, nq);
 	// longest-processing-time dealing of contigs to GPUs
 	std::vector<int> order((size_t)nq); for (int i = 0; i < nq; i++) order[i] = i;
 	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return query[a].seq.size() > query[b].seq.size(); });
@@ -157,13 +173,12 @@ int main(int argc, char *argv[])
 	for (int g = 0; g < ngpu; g++) {
 		int nl = std::max(1, std::min<int>(o.lanes, (int)work[g].size()));
 		ctx[g].assign((size_t)nl, nullptr);
-		if (gsa_create(g, &ctx[g][0]) != 0) { fprintf(stderr, "FatalError: cannot open CUDA device %d (this build has no CPU path)\n", g); return 0; }
-		if (gsa_set_params(ctx[g][0], &prm) != 0 || gsa_index_upload(ctx[g][0], &view) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g][0])); return 0; }
+		ctx[g][0] = owners[g];
 		for (int l = 1; l < nl; l++)
 			if (gsa_create_shared(ctx[g][0], &ctx[g][l]) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g][0])); return 0; }
 	}
+	tick("lanes ready");
 
-	tick("contexts + index upload");
 	// ---- GenomeComparison ------------------------------------------------------------------------------------------------
 	fprintf(stderr, "Step2. Sequence analysis for all query chromosomes\n");
 	std::vector<ContigResult> results((size_t)nq);
@@ -218,7 +233,9 @@ int main(int argc, char *argv[])
 		output_variants(o, ix, st);
 	}
 	tick("variants written");
-	for (auto &v : ctx) for (size_t l = v.size(); l-- > 0;) gsa_destroy(v[l]); // lanes first, the index owner last
-	tick("contexts destroyed");
-	return 0;
+	// the process ends here: files are closed, device and pinned memory go back with the process (tearing contexts down one
+	// buffer at a time costs more than the whole alignment of a small genome)
+	fflush(NULL);
+	tick("done");
+	_exit(0);
 }
