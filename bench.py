@@ -187,7 +187,8 @@ def main():
     ap.add_argument("--cpu-sample-bp", type=int, default=50_000_000)
     ap.add_argument("--oracle-sample-bp", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=4, help="contigs in flight per GPU (contexts sharing one index, one host thread each)")
+    ap.add_argument("--lanes", type=int, default=0, help="contigs in flight per GPU (contexts sharing one index, one host thread each); "
+                                                         "0 = min(4, host cores / ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -220,7 +221,8 @@ def main():
     al.upload_index(bi)
     # lanes: contexts on this GPU sharing the uploaded index, one host thread and one stream each; query contigs are
     # independent, so the lanes keep the GPU busy across each other's host-side steps
-    n_lanes = max(1, min(args.lanes, len(contigs)))
+    want_lanes = args.lanes if args.lanes > 0 else max(1, min(4, (os.cpu_count() or 4) // max(1, world)))
+    n_lanes = max(1, min(want_lanes, len(contigs)))
     lanes = [al] + [capi.Aligner(local, owner=al) for _ in range(n_lanes - 1)]
     streams = [torch.cuda.Stream() for _ in lanes]
     for ln, st in zip(lanes, streams):

@@ -12,7 +12,7 @@ for path in sorted(glob.glob("gpurun_out/launches_*.csv")):
         v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]
         v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v * 1e6 if u == "s" else v
         name = re.sub(r"\(.*", "", re.sub(r"<.*", "", row["Kernel Name"]))[:50]
-        if re.match(r"k_ib_|k_fill_sa|k_build_|k_dpx_peak", name):   # index construction / upload / microbenchmark: setup, not the path
+        if re.search(r"k_ib_|k_fill_sa|k_build_|k_dpx_peak", name):   # index construction / upload / microbenchmark: setup, not the path
             continue
         agg[name][0] += 1; agg[name][1] += v; tot += v
     out.append(f"\n## launch list {os.path.basename(path)} (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare SHARES)\n")
@@ -20,6 +20,9 @@ for path in sorted(glob.glob("gpurun_out/launches_*.csv")):
     for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:22]:
         out.append(f"| {k} | {c} | {t:.1f} | {100 * t / tot:.1f}% |")
     out.append(f"| **all** | {sum(c for c, _ in agg.values())} | {tot:.1f} | 100% |")
+def _num(x):
+    return float(x.replace(",", ""))
+
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
@@ -39,6 +42,26 @@ for path in sorted(glob.glob("gpurun_out/prof_*.ncu-rep")):
         if w in hdr:
             i = hdr.index(w)
             out.append(f"| {w} | {rows[1][i]} | " + " | ".join(row[i] for row in rows[2:]) + " |")
+# dram bytes per k_seed launch of the C2 capture -> profiles/traffic.json (bench.py reports it as roofline.traffic)
+kp = "gpurun_out/prof_kseed.ncu-rep"
+if os.path.exists(kp):
+    r = subprocess.run(["ncu", "-i", kp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(r.splitlines()))
+    if len(rows) >= 3:
+        hdr, units = rows[0], rows[1]
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = []
+        for row in rows[2:]:
+            b = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(m); b += _num(row[i]) * mult[units[i]]
+            tot.append(b)
+        tj = {"C2": {"k_seed_dram_bytes_per_launch": sum(tot) / len(tot), "launches": len(tot),
+                     "source": f"profiles/{tag}_summary.md, prof_kseed.ncu-rep (ncu --set full, bench.py --workload C2 --lanes 1)"}}
+        json.dump(tj, open("profiles/traffic.json", "w"), indent=1)
+for extra in ("dp_bench.json", "random_access.json"):
+    if os.path.exists("gpurun_out/" + extra):
+        out.append(f"\n## {extra}\n\n```json\n{open('gpurun_out/' + extra).read().strip()}\n```")
 for path in sorted(glob.glob("gpurun_out/bench_*.json")):
     txt = open(path).read().strip()
     if txt:
