@@ -106,7 +106,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.25)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -203,6 +203,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
 
@@ -257,7 +258,7 @@ def main():
     # N > 1: the one collective of the path -- every rank packs its finished records (device memory) into an outbox and
     # rank 0 gathers them over NCCL once per step (gsalign_b200/gather.py); inside the timed region of `value`
     from gsalign_b200 import gather
-    outbox = {"box": None, "lock": threading.Lock(), "bytes": 0}
+    outbox = {"box": None, "boxes": None, "turn": 0, "free": [None, None], "lock": threading.Lock(), "bytes": 0}
 
     class _DevView:
         def __init__(self, ptr, nbytes):
@@ -290,18 +291,27 @@ def main():
         return ln.timing()
 
     def gather_step():
-        """after every lane finished its contigs: one NCCL gather of this step's records to rank 0"""
-        if world == 1:
+        """after every lane finished its contigs: one NCCL gather of this step's records to rank 0.  Two outboxes alternate,
+        so the gather of step k runs on the master stream while the lanes already fill the other box with step k+1."""
+        if world == 1 or os.environ.get("GSA_BENCH_NO_GATHER"):   # the switch is a diagnosis aid
+            if outbox["box"] is not None:
+                outbox["box"].reset()
             return 0
+        box = outbox["box"]
         for st in streams:
             ev = torch.cuda.Event(); ev.record(st); master.wait_event(ev)
         with torch.cuda.stream(master):
-            inbox = gather.gather_to_root(outbox["box"].buf, outbox["box"].used)
+            inbox = gather.gather_to_root(box.buf, box.used)
         got = sum(int(b.numel()) for b in inbox) if inbox is not None else 0
-        ev = torch.cuda.Event(); ev.record(master)
-        for st in streams:
-            st.wait_event(ev)                      # the outbox is reused by the next step
+        done = torch.cuda.Event(); done.record(master)
+        t = outbox["turn"]
+        outbox["free"][t] = done                   # this box may be refilled once its gather has run
+        t ^= 1
+        outbox["turn"] = t; outbox["box"] = outbox["boxes"][t]
         outbox["box"].reset()
+        if outbox["free"][t] is not None:
+            for st in streams:
+                st.wait_event(outbox["free"][t])
         return got
 
     def contig_host(ln, i):
@@ -321,12 +331,14 @@ def main():
     master = torch.cuda.Stream()
     run_lanes(contig_device)                       # sizes the outbox (N > 1) and warms the allocators
     if world > 1:
-        outbox["box"] = gather.Outbox(int(outbox["bytes"] * 1.1) + (1 << 20), torch.device("cuda", local))
+        outbox["boxes"] = [gather.Outbox(int(outbox["bytes"] * 1.1) + (1 << 20), torch.device("cuda", local)) for _ in range(2)]
+        outbox["box"] = outbox["boxes"][0]
     for _ in range(args.warmup):
         run_lanes(contig_device)
         gather_step()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:   # one sampler per box: every nvidia-smi call takes driver locks the launching threads also need
+        sampler.start()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_seed_ms, k_dp_ms, launches, seed_ms, cluster_ms, fill_ms, dp_cells, n_seeds = [], [], 0, 0.0, 0.0, 0.0, 0, 0
@@ -366,7 +378,8 @@ def main():
     sync_all()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     pool.shutdown()
 
     if world > 1:
@@ -447,6 +460,7 @@ def main():
                                    f"params {w['prm'] or 'reference defaults'}",
                        "parallelism": f"{world} x (full index replica + own query copy), {n_lanes} contigs in flight per GPU; "
                                       + ("no collective (1 GPU)" if world == 1 else f"one NCCL record gather to rank 0 per step ({gathered} bytes) inside the timed region of value"),
+                       "host_cores": os.cpu_count(),
                        "l2": "inputs larger than L2 (index " + f"{(bi.seq_len * 4 + bi.seq_len // 2 + bi.seq_len // 4) / 1e6:.0f} MB resident, query {total_bp / 1e6:.0f} MB); no flush needed"},
             "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": int(total_bp), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / args.steps * 1e3},

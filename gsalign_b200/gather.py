@@ -62,9 +62,9 @@ def gather_to_root(outbox: torch.Tensor, used: int, root: int = 0, group=None):
     """All ranks call this once per job.  Returns on root a list (one entry per rank) of uint8 tensors holding that rank's
     outbox[:used]; elsewhere None.  One size all_gather + one grouped send/recv batch."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=outbox.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([used], dtype=torch.int64, device=outbox.device), group=group)
-    sizes = [int(s.item()) for s in sizes]
+    sizes_t = torch.zeros(world, dtype=torch.int64, device=outbox.device)
+    dist.all_gather_into_tensor(sizes_t, torch.tensor([used], dtype=torch.int64, device=outbox.device), group=group)
+    sizes = [int(x) for x in sizes_t.cpu().tolist()]   # one host sync
     if rank == root:
         inbox = [outbox[:used] if r == root else torch.empty(sizes[r], dtype=torch.uint8, device=outbox.device) for r in range(world)]
         ops = [dist.P2POp(dist.irecv, inbox[r], r, group=group) for r in range(world) if r != root and sizes[r] > 0]
