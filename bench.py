@@ -333,12 +333,12 @@ def main():
     if world > 1:
         outbox["boxes"] = [gather.Outbox(int(outbox["bytes"] * 1.1) + (1 << 20), torch.device("cuda", local)) for _ in range(2)]
         outbox["box"] = outbox["boxes"][0]
+    sampler = ClockSampler(local)
+    if rank == 0:   # one sampler per box (every nvidia-smi call takes driver locks the launching threads also need); it runs
+        sampler.start()   # from the warm-up on: the timed regions are a few tens of ms, one nvidia-smi call takes about as long
     for _ in range(args.warmup):
         run_lanes(contig_device)
         gather_step()
-    sampler = ClockSampler(local)
-    if rank == 0:   # one sampler per box: every nvidia-smi call takes driver locks the launching threads also need
-        sampler.start()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_seed_ms, k_dp_ms, launches, seed_ms, cluster_ms, fill_ms, dp_cells, n_seeds = [], [], 0, 0.0, 0.0, 0.0, 0, 0

@@ -1,9 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --workload C2 --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-D=/tmp/gsa_bench_cache/C2
-( time GSA_TIMING=1 ./bin/GSAlign -i $D/ref -q $D/qry.fa -o /tmp/ours_c2 ) 2>&1 | grep "timing\|real"
-( time GSA_TIMING=1 ./bin/GSAlign -i $D/ref -q $D/qry.fa -o /tmp/ours_c2 ) 2>&1 | grep "timing\|real"
-( time ./oracle/_ref/GSAlign -t 16 -i $D/ref -q $D/qry.fa -o /tmp/ref_c2 ) 2>&1 | grep real
-md5sum /tmp/ours_c2.maf /tmp/ref_c2.maf /tmp/ours_c2.vcf /tmp/ref_c2.vcf
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12
+python bench.py --workload C2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_C2.json 2> gpurun_out/bench_C2.err; cat gpurun_out/bench_C2.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['phases_ms_per_step'], d['roofline']['frac'], d['roofline']['traffic'], d['clocks'])"
