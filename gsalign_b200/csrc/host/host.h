@@ -45,7 +45,8 @@ std::string trim_chromosome_name(std::string name);                        // Tr
 struct Coordinate { bool bDir; int gPos; int ChromosomeIdx; };            // Coordinate_t
 Coordinate gen_coordinate(const HostIndex &ix, int64_t rPos);              // GenCoordinateInfo, src/tools.cpp:120-140
 
-struct Variant { int pos, chr_idx, query_idx; std::string ref_frag, alt_frag; int type; }; // Variant_t
+// Variant_t without its two std::strings: the alleles (REF then ALT) live in EmitState::alleles at `off`
+struct Variant { int32_t chr_idx, pos, type; uint32_t ref_len, alt_len; uint64_t off; };
 
 struct Options {                   // the globals of src/main.cpp:10-12,203-215
 	int threads = 8, out_format = 1, n_gpus = 1, lanes = 4;
@@ -66,7 +67,9 @@ struct ContigResult {
 struct EmitState {                 // running totals of GenomeComparison (src/GSAlign.cpp:14-15)
 	int64_t total_aln_len = 0, total_matches = 0, local_aln_num = 0, dup_num = 0;
 	int iSNV = 0, iInsertion = 0, iDeletion = 0;
-	std::vector<Variant> variants;
+	std::vector<Variant> variants;   // in the order VariantIdentification pushes them (the input order of the final unstable sort)
+	std::string alleles;
+	int threads = 1;                 // -t: host threads the emitters may use (row assembly, variant scan, VCF formatting)
 };
 
 // OutputMAF / OutputAlignment (src/tools.cpp:149-286); they trim a block that runs past its contig end

@@ -203,6 +203,7 @@ int main(int argc, char *argv[])
 	for (int g = 0; g < ngpu; g++) for (gsa_ctx *c : ctx[g]) threads.emplace_back(run_lane, g, c);
 
 	EmitState st;
+	st.threads = std::max(1, o.threads);
 	for (int qi = 0; qi < nq; qi++) {
 		fprintf(stderr, "\tProcess query chromsomoe: %s...\n", query[qi].name.c_str());
 		ContigResult &r = results[(size_t)qi];
