@@ -292,13 +292,9 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 
 // The final order is whatever libstdc++'s (unstable) std::sort makes of the push order under CompByVariantPos
 // (src/SeqVariant.cpp:6-10,126; hazard H5).  Introsort's moves depend on comparison outcomes only, so sorting 12-byte
-// (chr, pos, index) keys with the same comparator yields the same permutation as sorting the records themselves.
-struct VarKey { int32_t chr_idx, pos; uint32_t idx; };
-static bool by_variant_pos(const VarKey &a, const VarKey &b)
-{
-	if (a.chr_idx == b.chr_idx) return a.pos < b.pos;
-	return a.chr_idx < b.chr_idx;
-}
+// (chr, pos, index) keys under a comparator with the same outcomes yields the same permutation as sorting the records.
+struct VarKey { uint64_t key; uint32_t idx; };   // key = chr_idx << 32 | pos (both non-negative): one compare, same outcomes
+static bool by_variant_pos(const VarKey &a, const VarKey &b) { return a.key < b.key; }
 
 static inline char *put_int(char *p, int v)
 { // "%d"
@@ -315,7 +311,7 @@ void output_variants(const Options &o, const HostIndex &ix, EmitState &st)
 	static const char *MutType[3] = {"SUBSTITUTE", "INSERT", "DELETE"};
 	if (st.variants.size() >= 0xFFFFFFFFull) { fprintf(stderr, "too many variants for this build\n"); return; }
 	std::vector<VarKey> keys(st.variants.size());
-	for (size_t i = 0; i < keys.size(); i++) { keys[i].chr_idx = st.variants[i].chr_idx; keys[i].pos = st.variants[i].pos; keys[i].idx = (uint32_t)i; }
+	for (size_t i = 0; i < keys.size(); i++) { keys[i].key = ((uint64_t)(uint32_t)st.variants[i].chr_idx << 32) | (uint32_t)st.variants[i].pos; keys[i].idx = (uint32_t)i; }
 	std::sort(keys.begin(), keys.end(), by_variant_pos);
 	st.iSNV = st.iInsertion = st.iDeletion = 0;
 	FILE *out = fopen(o.vcf_name.c_str(), "w");

@@ -3,8 +3,14 @@
 #define _GNU_SOURCE
 #endif
 #include <string.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
+#include <atomic>
 #include <fstream>
+#include <thread>
 #include "host.h"
 
 static bool read_file(const std::string &path, std::vector<uint8_t> &out)
@@ -115,44 +121,91 @@ bool check_input_file(const char *path)
 	return !s.empty() && s[0] == '>';
 }
 
-bool load_query_file(const char *path, std::vector<QueryChr> &out)
-{ // LoadQueryFile, src/main.cpp:82-114: one bulk read, then line by line with memchr (same acceptance rules)
-	FILE *fp = fopen(path, "rb");
-	if (!fp) return false;
-	std::string buf;
-	{
-		fseek(fp, 0, SEEK_END);
-		long sz = ftell(fp);
-		fseek(fp, 0, SEEK_SET);
-		if (sz > 0) { buf.resize((size_t)sz); if (fread(&buf[0], 1, (size_t)sz, fp) != (size_t)sz) { fclose(fp); return false; } }
-		fclose(fp);
-	}
-	int idx = -1;
-	const char *p = buf.data(), *end = p + buf.size();
-	while (p < end) {
-		const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-		const char *le = nl ? nl : end;
-		size_t len = (size_t)(le - p);
-		if (len > 0) {
-			if (p[0] == '>') {
-				out.push_back(QueryChr()); idx++;
-				out[idx].name = trim_chromosome_name(std::string(p + 1, len - 1));
-				const char *nx = (const char *)memmem(le, (size_t)(end - le), "\n>", 2); // this record ends at the next header
-				out[idx].seq.reserve((size_t)((nx ? nx : end) - le));
-			} else {
-				if (p[len - 1] == '\r') len--;   // CheckQuerySeq, src/main.cpp:66-80
-				for (size_t i = 0; i < len; i++)
-					if (!isalpha((unsigned char)p[i])) {
-						printf("%.*s\n", (int)len, p);
-						fprintf(stderr, "The query sequence contains non-alphabet characters!\n");
-						return false;
-					}
-				if (idx < 0) return false;
-				out[idx].seq.append(p, len);
+// One record of the query FASTA: [beg, end) starts at a '>' header line.  Same acceptance rules as LoadQueryFile /
+// CheckQuerySeq (src/main.cpp:66-114): header trimmed by TrimChromosomeName, empty lines skipped, a trailing '\r' dropped,
+// every other character must be a letter.  Returns the offending line in *bad_line on failure.
+static bool parse_record(const char *beg, const char *end, QueryChr &qc, std::string *bad_line)
+{
+	const char *p = beg;
+	bool header = true;
+	size_t total = 0;
+	for (int pass = 0; pass < 2; pass++) { // pass 0 validates and sizes, pass 1 copies
+		p = beg; header = true;
+		if (pass == 1) qc.seq.resize(total);
+		size_t at = 0;
+		while (p < end) {
+			const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+			const char *le = nl ? nl : end;
+			size_t len = (size_t)(le - p);
+			if (len > 0) {
+				if (header) { if (pass == 0) qc.name = trim_chromosome_name(std::string(p + 1, len - 1)); header = false; }
+				else {
+					if (p[len - 1] == '\r') len--;
+					if (pass == 0) {
+						unsigned bad = 0;
+						for (size_t i = 0; i < len; i++) bad |= (unsigned)((unsigned char)((p[i] | 0x20) - 'a') >= 26); // !isalpha, C locale
+						if (bad) { bad_line->assign(p, len); return false; }
+						total += len;
+					} else { memcpy(&qc.seq[at], p, len); at += len; }
+				}
 			}
+			p = nl ? nl + 1 : end;
 		}
-		p = nl ? nl + 1 : end;
 	}
+	return true;
+}
+
+bool load_query_file(const char *path, std::vector<QueryChr> &out)
+{ // LoadQueryFile, src/main.cpp:82-114: the file is mapped, cut at the header lines and the records are parsed in parallel
+	int fd = open(path, O_RDONLY);
+	if (fd < 0) return false;
+	struct stat sb;
+	if (fstat(fd, &sb) != 0) { close(fd); return false; }
+	size_t size = (size_t)sb.st_size;
+	const char *buf = size ? (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0) : "";
+	close(fd);
+	if (size && buf == (const char *)MAP_FAILED) return false;
+	const char *end = buf + size;
+	// record starts: every '>' that is the first character of a line
+	std::vector<const char *> starts;
+	bool ok = true;
+	const char *p = buf;
+	while (p < end && *p == '\n') p++;                       // leading empty lines are skipped like any other
+	if (p < end && *p != '>') {                              // sequence before any header: the reference validates the line, then fails
+		const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+		std::string line(p, (size_t)((nl ? nl : end) - p));
+		if (!line.empty() && line[line.size() - 1] == '\r') line.resize(line.size() - 1);
+		bool alpha = true;
+		for (char c : line) alpha = alpha && isalpha((unsigned char)c);
+		if (!alpha) { printf("%s\n", line.c_str()); fprintf(stderr, "The query sequence contains non-alphabet characters!\n"); }
+		ok = false;
+	}
+	for (; ok && p < end;) {
+		starts.push_back(p);
+		const char *nx = (const char *)memmem(p, (size_t)(end - p), "\n>", 2);
+		p = nx ? nx + 1 : end;
+	}
+	if (ok) {
+		out.resize(starts.size());
+		std::vector<std::string> bad(starts.size());
+		std::vector<char> good(starts.size(), 1);
+		unsigned hw = std::thread::hardware_concurrency();
+		size_t nth = std::max<size_t>(1, std::min<size_t>(starts.size(), hw ? hw : 4));
+		std::vector<std::thread> th;
+		std::atomic<size_t> next(0);
+		auto work = [&] { for (size_t i; (i = next++) < starts.size();) good[i] = parse_record(starts[i], i + 1 < starts.size() ? starts[i + 1] : end, out[i], &bad[i]); };
+		for (size_t t = 1; t < nth; t++) th.emplace_back(work);
+		work();
+		for (auto &t : th) t.join();
+		for (size_t i = 0; i < starts.size() && ok; i++)
+			if (!good[i]) { // the first bad line in file order, like the serial reader
+				printf("%s\n", bad[i].c_str());
+				fprintf(stderr, "The query sequence contains non-alphabet characters!\n");
+				ok = false;
+			}
+	}
+	if (size) munmap((void *)buf, size);
+	if (!ok) return false;
 	fprintf(stderr, "\tLoad the query sequences (%d %s)\n", (int)out.size(), out.size() > 1 ? "chromosomes" : "chromosome");
 	return !out.empty();
 }

@@ -217,9 +217,15 @@ int main(int argc, char *argv[])
 		}
 		if (n == 0) { r = ContigResult(); continue; }
 		fprintf(stderr, "\t\tProduce %d local alignments (length = %lld), ANI=%.2f%%\n", n, (long long)aln_len, 100 * (1.0 * aln_score / aln_len));
-		if (o.out_format == 1) { fprintf(stderr, "\t\tOutput alignments for query sequence (%s)\n", o.maf.c_str()); output_maf(o, ix, query, qi, r); }
-		if (o.out_format == 2) { fprintf(stderr, "\t\tOutput alignments for query sequence (%s)\n", o.aln.c_str()); output_aln(o, ix, query, qi, r); }
-		if (o.vcf) { fprintf(stderr, "\t\tIdentify sequence variants for query sequence...\n"); variant_identification(ix, query, qi, r, st); }
+		// the alignment file is written by this thread while a helper scans the same records for variants: the scan skips seed
+		// fragments, the only thing the writer touches (iExtension trims the last seed of a block)
+		if (o.out_format == 1 || o.out_format == 2) fprintf(stderr, "\t\tOutput alignments for query sequence (%s)\n", o.out_format == 1 ? o.maf.c_str() : o.aln.c_str());
+		if (o.vcf) fprintf(stderr, "\t\tIdentify sequence variants for query sequence...\n");
+		std::thread var_thread;
+		if (o.vcf) var_thread = std::thread([&] { variant_identification(ix, query, qi, r, st); });
+		if (o.out_format == 1) output_maf(o, ix, query, qi, r);
+		if (o.out_format == 2) output_aln(o, ix, query, qi, r);
+		if (var_thread.joinable()) var_thread.join();
 		fprintf(stderr, "\n");
 		r = ContigResult();
 	}
