@@ -9,9 +9,11 @@
 //     query fragment, columns over the reference fragment; match +1, mismatch -1, any non-ACGT 0;
 //     E(i,j) = max(H(i-1,j)-3, E(i-1,j)-1), F(i,j) = max(H(i,j-1)-3, F(i,j-1)-1), ties open;
 //     H = max(diag+s, E, F) preferring diag, then E, then F; scores fit int16 (|H| <= 2+m+n).
-//   * anti-diagonal wavefront: one CTA per problem, the three live diagonals of H/E/F live in shared memory
-//     as int16 and one direction byte per cell is written diagonal-major (coalesced) to HBM.
-//   * traceback walks the direction bytes backwards exactly like ksw_backtrack (continuation flags,
+//   * ACGT-only pairs (the normal case) go to the packed-int16 DPX wavefront kernel k_dpx (dpx.cu); the problems are
+//     binned by size class on the device (run_dp_binned) and only the per-bin counts come back to the host.
+//   * pairs holding any other letter take the scalar kernel k_dp below: anti-diagonal wavefront, one CTA per problem, the
+//     three live diagonals of H/E/F in shared memory as int16, one direction byte per cell written diagonal-major
+//     (coalesced) to HBM; traceback walks the direction bytes backwards exactly like ksw_backtrack (continuation flags,
 //     leftover rows/columns become one gap) and the CTA reverses the rows in place.
 // Also accumulates AlnBlock_t::aln_len / score per block and applies nothing else: the identity filter and
 // the final block order are O(#blocks) host logic (see gsa_impl_fill at the bottom).

@@ -13,8 +13,9 @@
 //      or containing a non-ACGT base is a guaranteed miss and costs no index access at all),
 //   2. backward-search steps on 32-byte rank blocks only while the interval holds more than one row,
 //   3. one read of the full suffix array, and
-//   4. a streaming comparison of the 2-bit query against the 2-bit text (16 bases per word).
-// One thread walks one chunk; all chunks of the contig are in flight together.
+//   4. a streaming comparison of the 2-bit query against the 2-bit text (32 bases per step).
+// One warp walks one chunk, one lane per 313-bp sub-chunk, speculatively and as a pipelined state machine
+// (see seed_walk_pipe and k_seed below); all chunks of the contig are in flight together.
 #include "fm.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
@@ -131,44 +132,34 @@ __device__ __forceinline__ void vis_mark(uint32_t *vis, uint32_t a, uint32_t b)
 	}
 }
 
-// Walks the chunk's search chain from `start` until it leaves [.., limit); returns the first chain start >= limit.
-//   MODE 1: repair walk -- the true chain from the true entry of a sub-chunk: emits its seeds and stops as soon as it lands
-//           on a start the speculative walk visited (returns UINT_MAX then, the start in `merge`)
-//   (MODE 0 / 2, the straight-line speculative and emitting walks, are what seed_walk_pipe replaces)
-// Misses advance by one position, so a run of guaranteed misses (k-mer cut by a non-ACGT base or by the chunk end)
-// is a run of consecutive visited starts.
-template <int MODE>
-__device__ __forceinline__ uint32_t seed_walk(const DevIndex &ix, const SeedArgs &A, uint32_t start, uint32_t base, uint32_t limit, uint32_t stop,
-                                              uint32_t *vis, const SeedOut &out, uint32_t &merge)
+// The repair walk: the TRUE chain of a chunk from the true entry `start` of a sub-chunk [base, limit), as a straight line
+// (one lane runs it while the others wait, so it only has to be rare).  Emits its seeds unflagged and stops as soon as it
+// lands on a start the speculative walk visited: from there on the speculative chain is the true chain.  Returns
+// UINT_MAX then (the start in `merge`), else the first chain start >= limit.  Misses advance by one position, so a run
+// of guaranteed misses (k-mer cut by a non-ACGT base or by the chunk end) is a run of consecutive starts.
+__device__ __forceinline__ uint32_t seed_walk_repair(const DevIndex &ix, const SeedArgs &A, uint32_t start, uint32_t base, uint32_t limit, uint32_t stop,
+                                                     const uint32_t *vis, const SeedOut &out, uint32_t &merge)
 {
 	const int K = ix.ktab_k;
+	auto visited = [&](uint32_t s) { return (vis[(s - base) >> 5] >> ((s - base) & 31)) & 1; };
 	while (start < limit) {
-		if (MODE == 1 && ((vis[(start - base) >> 5] >> ((start - base) & 31)) & 1)) { merge = start; return 0xFFFFFFFFu; }
-		if (start + K > stop) { // fewer than K (<= MinSeedLength) bases left in the chunk: misses all the way
-			if (MODE == 0) vis_mark(vis, start - base, limit - base);
-			return limit;
-		}
+		if (visited(start)) { merge = start; return 0xFFFFFFFFu; }
+		if (start + K > stop) return limit; // fewer than K (<= MinSeedLength) bases left in the chunk: misses all the way
 		int bad = __clz(gsa_bit_window(A.qinv, start)); // offset of the first non-ACGT base at or after start
-		if (bad < K) { // every search starting in [start, start+bad] misses
+		if (bad < K) { // every search starting in [start, start+bad] misses; any visited start inside the run merges the chains
 			uint32_t ns = min(start + bad + 1, limit);
-			if (MODE == 0) vis_mark(vis, start - base, ns - base);
-			if (MODE == 1) { // any visited start inside the run merges the chains
-				for (uint32_t s2 = start + 1; s2 < ns; s2++) if ((vis[(s2 - base) >> 5] >> ((s2 - base) & 31)) & 1) { merge = s2; return 0xFFFFFFFFu; }
-			}
+			for (uint32_t s2 = start + 1; s2 < ns; s2++) if (visited(s2)) { merge = s2; return 0xFFFFFFFFu; }
 			start = ns;
 			continue;
 		}
-		if (MODE == 0) vis[(start - base) >> 5] |= 1u << ((start - base) & 31);
 		uint32_t lo, size, rpos = 0;
 		int len = seed_search(ix, A.qpk, A.qinv, start, stop, K, lo, size, rpos);
 		if (len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ) {
-			if (MODE >= 1) {
-				unsigned long long slot = atomicAdd(out.count, (unsigned long long)size);
-				if (size == 1) emit_seed(out, slot, (int32_t)start, (int64_t)rpos, len);
-				else
-					for (uint32_t i = 0; i < size; i++)
-						emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - __ldg(ix.sa + lo + i) - (uint32_t)len), len);
-			}
+			unsigned long long slot = atomicAdd(out.count, (unsigned long long)size);
+			if (size == 1) emit_seed(out, slot, (int32_t)start, (int64_t)rpos, len);
+			else
+				for (uint32_t i = 0; i < size; i++)
+					emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - __ldg(ix.sa + lo + i) - (uint32_t)len), len);
 			start += A.sensitive ? 5 : (uint32_t)len + 1;
 		} else start++;
 	}
@@ -411,7 +402,7 @@ k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 #ifdef SEED_PROFILE
 				atomicAdd(&g_seed_prof[7], 1ull);
 #endif
-				ex = seed_walk<1>(ix, A, entry, base, limit, stop, vis, out, merge);
+				ex = seed_walk_repair(ix, A, entry, base, limit, stop, vis, out, merge);
 				if (ex == 0xFFFFFFFFu) ex = spec_exit;
 			}
 		}
