@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--cpu-sample-bp", type=int, default=50_000_000)
     ap.add_argument("--oracle-sample-bp", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dp-stress", action="store_true", help="skip the K3 stress batch (roofline_k3), e.g. under ncu")
     ap.add_argument("--lanes", type=int, default=0, help="contigs in flight per GPU (contexts sharing one index, one host thread each); "
                                                          "0 = min(4, host cores / ranks)")
     args = ap.parse_args()
@@ -429,6 +430,8 @@ def main():
     # ---- K3 roofline: DP-only stress batch against the packed-int16 DPX issue rate measured on this box -----
     roofline_k3 = None
     try:
+        if args.no_dp_stress:
+            raise RuntimeError("skipped (--no-dp-stress)")
         dpx_peak = al.dpx_peak(0)
         rb, ro, qb, qo = synth.make_dp_batch(np.random.default_rng(5), 1024, 1024)
         cells = int(np.sum((ro[1:] - ro[:-1]) * (qo[1:] - qo[:-1])))
