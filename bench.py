@@ -329,7 +329,7 @@ def main():
     # the record gather of N > 1 reads them); CUDA events: every lane's stream starts after e0 and e1 follows all of them ---
     for ln in lanes:
         ln.set_host_results(False)
-    master = torch.cuda.Stream()
+    master = torch.cuda.Stream(priority=-1)        # the gather's NCCL kernels must not queue behind the lanes' compute kernels
     run_lanes(contig_device)                       # sizes the outbox (N > 1) and warms the allocators
     if world > 1:
         outbox["boxes"] = [gather.Outbox(int(outbox["bytes"] * 1.1) + (1 << 20), torch.device("cuda", local)) for _ in range(2)]
