@@ -63,7 +63,7 @@ int gsa_create(int device, gsa_ctx **out)
 	if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
 	if (gsa_ensure_host(ctx, ctx->h_small, 1 << 20) != GSA_OK) { delete ctx; return GSA_ERR_NOMEM; }
-	if (gsa_dpx_init_device(ctx) != GSA_OK || gsa_dp_init_device(ctx) != GSA_OK) { fprintf(stderr, "gsalign_b200: %s\n", ctx->err.c_str()); delete ctx; return GSA_ERR_CUDA; }
+	if (gsa_dpx_init_device(ctx) != GSA_OK) { fprintf(stderr, "gsalign_b200: %s\n", ctx->err.c_str()); delete ctx; return GSA_ERR_CUDA; }
 	*out = ctx;
 	return GSA_OK;
 }

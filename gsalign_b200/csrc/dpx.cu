@@ -1,8 +1,8 @@
 // dpx.cu -- K3's DP kernels: global affine-gap alignment as a register-resident anti-diagonal wavefront on packed
 // int16 pairs (DPX: VIADD.16x2, VIMNMX.S16x2 with predicate outputs), and its traceback.
 //
-// Same recurrence, tie rules and traceback as fill.cu's scalar kernel (ksw_extz2_sse / ksw_backtrack semantics,
-// reference src/ksw2_alignment.cpp:25-249; restated in SURVEY.md 8a A9), for fragment pairs made of ACGT only:
+// Recurrence, tie rules and traceback of ksw_extz2_sse / ksw_backtrack as the reference calls them (global, w = -1;
+// reference src/ksw2_alignment.cpp:25-249; restated in SURVEY.md 8a A9):
 //     E'(i,j) = max(H(i-1,j), E'(i-1,j) - 1)        E' = E + 3 (gap open 2 + extend 1 folded into H)
 //     F'(i,j) = max(H(i,j-1), F'(i,j-1) - 1)
 //     H(i,j)  = max(H(i-1,j-1) + s, E' - 3, F' - 3)  diag first, E only if strictly greater, F only if greater than both
@@ -12,7 +12,9 @@
 // from shared memory, lane 31 writes its own there for the strip below) and one 16-bit shared-memory load of the two
 // reference bases.  Cells before column 0 are fixed points of the recurrence (sentinel base scores -1 against
 // everything: H(i-1,-1) - 1 = H(i,-1)), cells past the last column are garbage nobody reads, so there is no per-step
-// bounds logic.  The match score comes out of one PRMT used as an 8-entry table on q XOR r.  Four decision bits per
+// bounds logic.  The match score comes out of one PRMT used as an 8-entry table on q XOR r (ACGT-only pairs) or, when
+// a pair holds other letters (score 0 against everything), out of per-lane tables indexed by the reference code (HASN
+// variant, one more PRMT per step).  Four decision bits per
 // cell (E>diag, F>both, E extended, F extended) are the VIMNMX predicates, collected over 8 steps into one word per
 // row and written as coalesced 256-byte warp rows to the flag pool (HBM; L2-resident at these sizes).
 // Strips of one problem run one after the other on one warp (small problems, several problems per CTA) or on W warps as
@@ -58,7 +60,7 @@ __device__ __forceinline__ uint32_t vmax_flag(uint32_t a, uint32_t b, uint32_t &
 // W warps per problem and NP problems per CTA (NP > 1 only with W == 1); slot = shared-memory bytes per problem.
 // STAGE: rows are assembled in shared memory and copied out coalesced (small problems); otherwise lane 0 writes them
 // straight to the row pools.
-template <int W, int NP, bool STAGE>
+template <int W, int NP, bool STAGE, bool HASN>
 __global__ void __launch_bounds__(32 * W * NP)
 k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t slot, char *aln1, char *aln2, int32_t *out_len, int64_t *out_start,
       gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
@@ -83,7 +85,10 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 	for (int j = tid; j < m; j += 32 * W) rch[j] = P.ref_chars ? (unsigned char)P.ref_chars[j] : (unsigned char)gsa_text_char(ix, P.rpos + j);
 	if (W == 1) __syncwarp(); else __syncthreads();
 	for (int k = -64 + tid; k < cols; k += 32 * W) {
-		int c0 = (k >= 0 && k < m) ? gsa_nt4(rch[k]) : 4, c1 = (k >= 1 && k <= m) ? gsa_nt4(rch[k - 1]) : 4;
+		// reference codes: 0..3 = ACGT, 4 = sentinel outside the fragment (scores -1 against everything), 5 = any other letter
+		int c0 = 4, c1 = 4;
+		if (k >= 0 && k < m) { c0 = gsa_nt4(rch[k]); if (c0 == 4) c0 = 5; }
+		if (k >= 1 && k <= m) { c1 = gsa_nt4(rch[k - 1]); if (c1 == 4) c1 = 5; }
 		a16[k] = (uint16_t)(c0 | 0x80 | (c1 << 8) | 0x8000);
 		bhe[k] = pack16(-(3 + k), DP_NEG);
 	}
@@ -97,7 +102,12 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 		uint32_t Hl = pack16(-(3 + r0), -(3 + r1));                 // H(i,-1)
 		uint32_t El = pack16(DP_NEG, DP_NEG), Fl = El;
 		uint32_t Dg = pack16(r0 == 0 ? 0 : -(2 + r0), -(2 + r1));   // H(i-1,-1)
-		const uint32_t qw = (uint32_t)(r0 < n ? gsa_nt4(qch[r0]) : 0) | ((uint32_t)(r1 < n ? gsa_nt4(qch[r1]) : 0) << 8);
+		const int q0 = r0 < n ? gsa_nt4(qch[r0]) : 0, q1 = r1 < n ? gsa_nt4(qch[r1]) : 0;
+		const uint32_t qw = (uint32_t)q0 | ((uint32_t)q1 << 8);
+		// HASN: score+3 of this lane's two query bases against reference codes 0..7, one byte each: 4 = match, 2 = mismatch
+		// or sentinel, 3 = either base is not ACGT
+		const uint32_t T0 = q0 < 4 ? 0x02020202u + (2u << (8 * q0)) : 0x03030303u, T1 = q1 < 4 ? 0x02020202u + (2u << (8 * q1)) : 0x03030303u;
+		const uint32_t TN = 0x03030302u;
 		const uint16_t *ap = a16 - 2 * lane;
 		uint2 *fs = fl + (size_t)s * G * 32 + lane;
 		if (W == 1 && s > 0) __syncwarp(); // lane 31's boundary row of the previous strip is complete
@@ -115,7 +125,9 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 				uint32_t rv = __shfl_up_sync(DPX_FULL, __byte_perm(Hl, El, 0x7632), 1);                                   \
 				if (lane == 0) rv = bhe[d];                                                                               \
 				uint32_t up = __byte_perm(rv, Hl, 0x5410), eu = __byte_perm(rv, El, 0x5432);                              \
-				uint32_t s3 = prmt(TA, TB, qw ^ (uint32_t)ap[d]);                                                         \
+				uint32_t s3;                                                                                              \
+				if (HASN) { uint32_t sel = ap[d]; s3 = __byte_perm(prmt(T0, TN, sel), prmt(T1, TN, sel), 0x7610); }       \
+				else s3 = prmt(TA, TB, qw ^ (uint32_t)ap[d]);                                                             \
 				uint32_t E = vmax_flag<(4u << (4 * (k)))>(up, __vadd2(eu, M1), f0, f1);  /* bit 2: E extended */            \
 				uint32_t F = vmax_flag<(8u << (4 * (k)))>(Hl, __vadd2(Fl, M1), f0, f1);  /* bit 3: F extended */            \
 				uint32_t h = vmax_flag<(1u << (4 * (k)))>(__vadd2(Dg, s3), E, f0, f1);   /* bit 0: E beats the diagonal */  \
@@ -158,11 +170,10 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 				int t = (w >> ((d & 7) << 2)) & 15;
 				if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
 				char c1, c2;
-				if (state == 0) {
-					c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--;
-					if (!STAGE) same += gsa_nt4((unsigned char)c1) == gsa_nt4((unsigned char)c2);
-				} else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
+				if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
+				else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
 				else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
+				if (!STAGE) same += gsa_nt4((unsigned char)c1) == gsa_nt4((unsigned char)c2); // nt4 classes: '-' equals a non-ACGT letter (H7)
 				pos--; t1[pos] = c1; t2[pos] = c2;
 			}
 		}
@@ -170,8 +181,8 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 		i = __shfl_sync(DPX_FULL, i, 0); j = __shfl_sync(DPX_FULL, j, 0);
 	}
 	if (lane == 0) {
-		for (; i >= 0; i--) { pos--; t1[pos] = '-'; t2[pos] = (char)qch[i]; }
-		for (; j >= 0; j--) { pos--; t1[pos] = (char)rch[j]; t2[pos] = '-'; }
+		for (; i >= 0; i--) { pos--; t1[pos] = '-'; t2[pos] = (char)qch[i]; if (!STAGE) same += gsa_nt4(qch[i]) == 4; }
+		for (; j >= 0; j--) { pos--; t1[pos] = (char)rch[j]; t2[pos] = '-'; if (!STAGE) same += gsa_nt4(rch[j]) == 4; }
 	}
 	pos = __shfl_sync(DPX_FULL, pos, 0);
 	const int len = m + n - pos;
@@ -194,12 +205,12 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 	}
 }
 
-template <int W, int NP, bool STAGE>
+template <int W, int NP, bool STAGE, bool HASN>
 static int launch_dpx(gsa_ctx *ctx, cudaStream_t stream, uint32_t slot, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
                       int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
 	size_t smem = (size_t)slot * NP;
-	k_dpx<W, NP, STAGE><<<(nprob + NP - 1) / NP, 32 * W * NP, smem, stream>>>(prob, nprob, ctx->ix, flags, slot, a1, a2, out_len, out_start, frag, fblk, bsum);
+	k_dpx<W, NP, STAGE, HASN><<<(nprob + NP - 1) / NP, 32 * W * NP, smem, stream>>>(prob, nprob, ctx->ix, flags, slot, a1, a2, out_len, out_start, frag, fblk, bsum);
 	KERNEL_CHECK(ctx);
 	return GSA_OK;
 }
@@ -209,34 +220,41 @@ static int launch_dpx(gsa_ctx *ctx, cudaStream_t stream, uint32_t slot, const Dp
 int gsa_dpx_init_device(gsa_ctx *ctx)
 {
 	const int big = (int)dpx_layout(DP_MAX_DIM, DP_MAX_DIM, false).total;
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<4, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<8, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<16, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<4, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<8, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<16, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	return GSA_OK; // the S classes stay below the 48 KB default (m <= 1000, n <= 256)
+}
+
+template <bool HASN>
+static int dpx_launch_size(gsa_ctx *ctx, cudaStream_t stream, int size, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
+                           int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+{
+	if (size == DPX_CLS_S1 || size == DPX_CLS_S2) {
+		const uint32_t slot = dpx_layout(max_m, max_n, true).total;
+		if (slot <= 3584) return launch_dpx<1, 2, true, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+		return launch_dpx<1, 1, true, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+	}
+	// warps per problem: one per strip (up to 16) gives the shortest critical path when problems are few; with many
+	// problems in flight fewer warps waste less on the 72-step stagger between consecutive strips
+	const uint32_t slot = dpx_layout(max_m, max_n, false).total;
+	int W = size == DPX_CLS_G4 ? 4 : size == DPX_CLS_G8 ? 8 : 16;
+	while (W > 4 && (long long)nprob * W > 4096) W >>= 1;
+	if (W == 4) return launch_dpx<4, 1, false, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+	if (W == 8) return launch_dpx<8, 1, false, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+	return launch_dpx<16, 1, false, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
 }
 
 int gsa_dpx_launch(gsa_ctx *ctx, cudaStream_t stream, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
                    int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
 	if (nprob <= 0) return GSA_OK;
-	switch (cls) {
-	case DPX_CLS_S1: case DPX_CLS_S2: {
-		const uint32_t slot = dpx_layout(max_m, max_n, true).total;
-		if (slot <= 3584) return launch_dpx<1, 2, true>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
-		return launch_dpx<1, 1, true>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
-	}
-	case DPX_CLS_G4: case DPX_CLS_G8: case DPX_CLS_G16: {
-		// warps per problem: one per strip (up to 16) gives the shortest critical path when problems are few; with many
-		// problems in flight fewer warps waste less on the 72-step stagger between consecutive strips
-		const uint32_t slot = dpx_layout(max_m, max_n, false).total;
-		int W = cls == DPX_CLS_G4 ? 4 : cls == DPX_CLS_G8 ? 8 : 16;
-		while (W > 4 && (long long)nprob * W > 4096) W >>= 1;
-		if (W == 4) return launch_dpx<4, 1, false>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
-		if (W == 8) return launch_dpx<8, 1, false>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
-		return launch_dpx<16, 1, false>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
-	}
-	}
-	return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dpx_launch: bad class %d", cls);
+	if (cls < 0 || cls >= DPX_NCLS) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dpx_launch: bad class %d", cls);
+	if (cls >= DPX_NSIZE) return dpx_launch_size<true>(ctx, stream, cls - DPX_NSIZE, max_m, max_n, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+	return dpx_launch_size<false>(ctx, stream, cls, max_m, max_n, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
 }
 
 // ---- on-box microbenchmark: issue rate of the packed-int16 DPX instructions (the roofline denominator of K3) ------------

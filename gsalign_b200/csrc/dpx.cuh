@@ -16,12 +16,13 @@ struct DpProblem {
 	int32_t cls;           // DPX_CLS_*
 };
 
-// Size classes.  A fragment pair made of ACGT only goes to the packed-int16 wavefront kernel k_dpx (the class picks the
-// number of warps per problem and how the rows are written).  Pairs holding any other
-// letter (score 0 against everything, reference src/ksw2_alignment.cpp:258-262) take the scalar kernel k_dp.
+// Size classes of the packed-int16 wavefront kernel k_dpx (the class picks the number of warps per problem and how the
+// rows are written):
 //   S1 / S2   one warp per problem, strips one after the other (n <= 256; m <= 240 / <= 1000: small shared memory)
 //   G4..G16   one CTA per problem, up to 4 / 8 / 16 warps sweeping consecutive 64-row strips as a pipeline
-enum { DPX_CLS_S1 = 0, DPX_CLS_S2 = 1, DPX_CLS_G4 = 2, DPX_CLS_G8 = 3, DPX_CLS_G16 = 4, DPX_CLS_SCALAR = 5 };
+// Pairs holding any letter outside ACGT (score 0 against everything, reference src/ksw2_alignment.cpp:258-262) run the
+// same kernels in their HASN variant (per-lane score tables instead of the q XOR r table): class = size class + DPX_NSIZE.
+enum { DPX_CLS_S1 = 0, DPX_CLS_S2 = 1, DPX_CLS_G4 = 2, DPX_CLS_G8 = 3, DPX_CLS_G16 = 4, DPX_NSIZE = 5, DPX_NCLS = 10 };
 
 #define DPX_TBW 16   // traceback window, in 8-step groups (one 256-byte flag row each)
 
@@ -53,17 +54,13 @@ __host__ __device__ inline DpxLayout dpx_layout(int m, int n, bool stage)
 
 __host__ __device__ inline int dpx_class(int m, int n, bool has_other)
 {
-	if (has_other) return DPX_CLS_SCALAR;
-	if (n <= 256 && m <= 240) return DPX_CLS_S1;
-	if (n <= 256 && m <= 1000) return DPX_CLS_S2;
-	return n <= 256 ? DPX_CLS_G4 : n <= 512 ? DPX_CLS_G8 : DPX_CLS_G16;
+	int size = (n <= 256 && m <= 240) ? DPX_CLS_S1 : (n <= 256 && m <= 1000) ? DPX_CLS_S2 : n <= 256 ? DPX_CLS_G4 : n <= 512 ? DPX_CLS_G8 : DPX_CLS_G16;
+	return size + (has_other ? DPX_NSIZE : 0);
 }
 
-// bytes of the direction-flag pool a problem needs: 4 bits per cell of every (64-row strip) x (8-step group) tile for the
-// wavefront kernel, one byte per cell of the anti-diagonal band layout for the scalar kernel
-__host__ __device__ inline int64_t dpx_flag_bytes(int m, int n, int cls)
+// bytes of the direction-flag pool a problem needs: 4 bits per cell of every (64-row strip) x (8-step group) tile
+__host__ __device__ inline int64_t dpx_flag_bytes(int m, int n)
 {
-	if (cls == DPX_CLS_SCALAR) { int w = m < n ? m : n; return (((int64_t)(m + n - 1) * w) + 255) & ~255ll; }
 	DpxLayout L = dpx_layout(m, n, false);
 	return 256ll * L.G * L.nstrips;
 }
@@ -74,4 +71,3 @@ __host__ __device__ inline int64_t dpx_flag_bytes(int m, int n, int cls)
 int gsa_dpx_launch(gsa_ctx *ctx, cudaStream_t stream, int cls, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
                    int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum);
 int gsa_dpx_init_device(gsa_ctx *ctx);   // once per context: function attributes of the k_dpx variants (dpx.cu)
-int gsa_dp_init_device(gsa_ctx *ctx);    // same for the scalar kernel (fill.cu)

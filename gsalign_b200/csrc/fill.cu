@@ -9,12 +9,9 @@
 //     query fragment, columns over the reference fragment; match +1, mismatch -1, any non-ACGT 0;
 //     E(i,j) = max(H(i-1,j)-3, E(i-1,j)-1), F(i,j) = max(H(i,j-1)-3, F(i,j-1)-1), ties open;
 //     H = max(diag+s, E, F) preferring diag, then E, then F; scores fit int16 (|H| <= 2+m+n).
-//   * ACGT-only pairs (the normal case) go to the packed-int16 DPX wavefront kernel k_dpx (dpx.cu); the problems are
-//     binned by size class on the device (run_dp_binned) and only the per-bin counts come back to the host.
-//   * pairs holding any other letter take the scalar kernel k_dp below: anti-diagonal wavefront, one CTA per problem, the
-//     three live diagonals of H/E/F in shared memory as int16, one direction byte per cell written diagonal-major
-//     (coalesced) to HBM; traceback walks the direction bytes backwards exactly like ksw_backtrack (continuation flags,
-//     leftover rows/columns become one gap) and the CTA reverses the rows in place.
+//   * the DP itself is the packed-int16 DPX wavefront kernel k_dpx (dpx.cu); the problems are binned by size class (and
+//     by whether they hold letters outside ACGT) on the device (run_dp_binned) and only the per-bin counts come back
+//     to the host.
 // Also accumulates AlnBlock_t::aln_len / score per block and applies nothing else: the identity filter and
 // the final block order are O(#blocks) host logic (see gsa_impl_fill at the bottom).
 #include "dpx.cuh"
@@ -56,7 +53,7 @@ __global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char
 				bool other = false; // any non-ACGT query base in the fragment (the 2-bit reference text holds none)
 				for (uint32_t p = (uint32_t)f.qPos, e = p + (uint32_t)f.qLen; p < e && !other; p += 32) other = (gsa_bit_window(qinv, p) >> (32 - min(32u, e - p))) != 0;
 				cls = (uint8_t)dpx_class(f.rLen, f.qLen, other);
-				fl = dpx_flag_bytes(f.rLen, f.qLen, cls);
+				fl = dpx_flag_bytes(f.rLen, f.qLen);
 			}
 		}
 	}
@@ -106,110 +103,7 @@ __global__ void k_dp_problems(const int32_t *dp_idx, int64_t ndp, const gsa_frag
 	prob[k] = p;
 }
 
-// ---- the DP kernel -----------------------------------------------------------------------------------------
-// Shared memory (dynamic): codes of both fragments (bytes) and 7 int16 arrays over the query rows:
-// H on diagonals d-1 and d-2 and the one being written, E and F on d-1 and the one being written.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_dp(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *flags, char *aln1, char *aln2, int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum, int rows_cap)
-{
-	extern __shared__ int16_t smem[];
-	int pi = blockIdx.x;
-	if (pi >= nprob) return;
-	const DpProblem P = prob[pi];
-	const int m = P.m, n = P.n, tid = threadIdx.x;
-	int16_t *H0 = smem, *H1 = H0 + rows_cap, *H2 = H1 + rows_cap, *E0 = H2 + rows_cap, *E1 = E0 + rows_cap, *F0 = E1 + rows_cap, *F1 = F0 + rows_cap;
-	uint8_t *qc = (uint8_t *)(F1 + rows_cap), *rc = qc + rows_cap; // rc holds m codes (cols_cap == rows_cap)
-	for (int i = tid; i < n; i += THREADS) qc[i] = (uint8_t)gsa_nt4((unsigned char)P.qry_chars[i]);
-	for (int j = tid; j < m; j += THREADS) rc[j] = P.ref_chars ? (uint8_t)gsa_nt4((unsigned char)P.ref_chars[j]) : (uint8_t)gsa_pk_base(ix.txt, (uint32_t)(P.rpos + j));
-	if (THREADS == 32) __syncwarp(); else __syncthreads();
-	const int w = min(m, n);
-	uint8_t *fl = flags + P.flag_off;
-	// Hd1 = diagonal d-1, Hd2 = diagonal d-2, Hn = diagonal d (being written); same for E/F
-	int16_t *Hd2 = H0, *Hd1 = H1, *Hn = H2, *Ed1 = E0, *En = E1, *Fd1 = F0, *Fn = F1;
-	for (int d = 0; d < m + n - 1; d++) {
-		int i_lo = max(0, d - m + 1), i_hi = min(n - 1, d);
-		uint8_t *fd = fl + (int64_t)d * w - i_lo;
-		for (int i = i_lo + tid; i <= i_hi; i += THREADS) {
-			int j = d - i;
-			int a = qc[i], b = rc[j];
-			int s = (a > 3 || b > 3) ? 0 : (a == b ? 1 : -1);
-			int hdiag, hup, eup, hleft, fleft;
-			if (i == 0) { hup = -(2 + (j + 1)); eup = DP_NEG; hdiag = j == 0 ? 0 : -(2 + j); }
-			else { hup = Hd1[i - 1]; eup = Ed1[i - 1]; hdiag = j == 0 ? -(2 + i) : Hd2[i - 1]; }
-			if (j == 0) { hleft = -(2 + (i + 1)); fleft = DP_NEG; }
-			else { hleft = Hd1[i]; fleft = Fd1[i]; }
-			int eo = hup - 3, ee = eup - 1, fo = hleft - 3, fe = fleft - 1;
-			int ye = ee > eo, yf = fe > fo;      // strict: a tie opens a new gap
-			int e = ye ? ee : eo, f = yf ? fe : fo;
-			int h = hdiag + s, dir = 0;
-			if (e > h) { h = e; dir = 1; }        // E only if strictly greater than diag
-			if (f > h) { h = f; dir = 2; }        // F only if strictly greater than both
-			Hn[i] = (int16_t)h; En[i] = (int16_t)e; Fn[i] = (int16_t)f;
-			fd[i] = (uint8_t)(dir | (ye << 3) | (yf << 4));
-		}
-		if (THREADS == 32) __syncwarp(); else __syncthreads();
-		int16_t *t = Hd2; Hd2 = Hd1; Hd1 = Hn; Hn = t;
-		t = Ed1; Ed1 = En; En = t;
-		t = Fd1; Fd1 = Fn; Fn = t;
-	}
-	__threadfence_block();
-	// ---- traceback (ksw_backtrack, src/ksw2_alignment.cpp:25-68), rows are produced back to front
-	__shared__ int sL, sSame;
-	char *o1 = aln1 + P.out_off, *o2 = aln2 + P.out_off;
-	if (tid == 0) {
-		int i = n - 1, j = m - 1, state = 0, cont = 0, L = 0;
-		while (i >= 0 && j >= 0) {
-			int d = i + j, i_lo = max(0, d - m + 1);
-			int t = fl[(int64_t)d * w + (i - i_lo)];
-			if (state == 0 || !cont) state = t & 3;
-			char c1, c2;
-			if (state == 0) { c1 = P.ref_chars ? P.ref_chars[j] : "ACGT"[rc[j]]; c2 = P.qry_chars[i]; i--; j--; }
-			else if (state == 1) { c1 = '-'; c2 = P.qry_chars[i]; cont = (t >> 3) & 1; i--; }
-			else { c1 = P.ref_chars ? P.ref_chars[j] : "ACGT"[rc[j]]; c2 = '-'; cont = (t >> 4) & 1; j--; }
-			o1[L] = c1; o2[L] = c2; L++;
-		}
-		for (; i >= 0; i--, L++) { o1[L] = '-'; o2[L] = P.qry_chars[i]; }
-		for (; j >= 0; j--, L++) { o1[L] = P.ref_chars ? P.ref_chars[j] : "ACGT"[rc[j]]; o2[L] = '-'; }
-		sL = L; sSame = 0;
-	}
-	__syncthreads();
-	const int L = sL;
-	int same = 0;
-	for (int k = tid; k < L / 2; k += THREADS) {
-		char a = o1[k], b = o1[L - 1 - k]; o1[k] = b; o1[L - 1 - k] = a;
-		a = o2[k]; b = o2[L - 1 - k]; o2[k] = b; o2[L - 1 - k] = a;
-	}
-	__syncthreads();
-	// CountIdenticalPairs (src/ProcessCandidateAlignment.cpp:38-47): nt4 classes, so '-' == N == 4
-	for (int k = tid; k < L; k += THREADS) same += gsa_nt4((unsigned char)o1[k]) == gsa_nt4((unsigned char)o2[k]);
-	if (same) atomicAdd(&sSame, same);
-	__syncthreads();
-	if (tid == 0) {
-		if (out_len) { out_len[P.frag] = L; out_start[P.frag] = P.out_off; }
-		if (frag) {
-			frag[P.frag].aln_off = P.out_off; frag[P.frag].aln_len = L;
-			int b = fblk[P.frag];
-			atomicAdd(bsum + 2 * b, (unsigned)L); atomicAdd(bsum + 2 * b + 1, (unsigned)sSame);
-		}
-	}
-}
-
-static size_t dp_smem_bytes(int rows_cap) { return (size_t)rows_cap * (7 * sizeof(int16_t) + 2); }
-
-// launches the DP over problems [0,nprob) whose max(m,n) <= dim_cap
-template <int THREADS>
-static int launch_dp(gsa_ctx *ctx, const DpProblem *prob, int nprob, int dim_cap, uint8_t *flags, char *a1, char *a2, int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
-{
-	if (nprob <= 0) return GSA_OK;
-	int rows_cap = (dim_cap + 15) & ~15;
-	size_t smem = dp_smem_bytes(rows_cap);
-	k_dp<THREADS><<<nprob, THREADS, smem, ctx->stream>>>(prob, nprob, ctx->ix, flags, a1, a2, out_len, out_start, frag, fblk, bsum, rows_cap);
-	KERNEL_CHECK(ctx);
-	return GSA_OK;
-}
-
-struct Ws3 {
+struct Ws3 { // scratch slots of the context, handed out in order
 	gsa_ctx *ctx; int next = 0; int rc = GSA_OK;
 	explicit Ws3(gsa_ctx *c) : ctx(c) {}
 	template <typename T> T *get(int64_t n)
@@ -222,32 +116,20 @@ struct Ws3 {
 	}
 };
 
-int gsa_dp_init_device(gsa_ctx *ctx)
-{ // see gsa_dpx_init_device: set once, to the largest request
-	const int big = (int)dp_smem_bytes((DP_MAX_DIM + 15) & ~15);
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-	return GSA_OK;
-}
-
 // ---- device-side binning ------------------------------------------------------------------------------------------------
 // Problems are ordered by (bin, size descending) with one radix sort; only the per-bin counts come back to the host.
-// Bins 0..5: ACGT-only pairs for the packed-int16 wavefront kernel (dpx.cu), one launch per size class; the next five:
-// pairs holding other letters for the scalar kernel, by max(m,n) so that small ones get small shared memory; last: too long.
-#define DP_BIN_SCALAR DPX_CLS_SCALAR
-#define DP_BIN_TOOLONG (DP_BIN_SCALAR + 5)
+// Bins = the classes of dpx.cuh (size class x {ACGT only, other letters}), one launch each; last bin: too long.
+#define DP_BIN_TOOLONG DPX_NCLS
 #define DP_NBINS (DP_BIN_TOOLONG + 1)
-struct DpStats { unsigned int count[DP_NBINS]; int max_m[DPX_CLS_SCALAR], max_n[DPX_CLS_SCALAR]; unsigned long long cells; };
+struct DpStats { unsigned int count[DP_NBINS]; int max_m[DPX_NCLS], max_n[DPX_NCLS]; unsigned long long cells; };
 
 __global__ void k_dp_keys(const DpProblem *prob, int n, uint32_t *key, uint32_t *idx, DpStats *st)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	int m = prob[i].m, q = prob[i].n, cls = prob[i].cls, big = max(m, q), bin;
-	if (big > DP_MAX_DIM) bin = DP_BIN_TOOLONG;
-	else if (cls < DPX_CLS_SCALAR) { bin = cls; atomicMax(&st->max_m[cls], m); atomicMax(&st->max_n[cls], q); }
-	else bin = DP_BIN_SCALAR + (big <= 32 ? 0 : big <= 128 ? 1 : big <= 512 ? 2 : big <= 2048 ? 3 : 4);
+	if (big > DP_MAX_DIM || cls < 0 || cls >= DPX_NCLS) bin = DP_BIN_TOOLONG;
+	else { bin = cls; atomicMax(&st->max_m[cls], m); atomicMax(&st->max_n[cls], q); }
 	atomicAdd(&st->count[bin], 1u);
 	atomicAdd(&st->cells, (unsigned long long)m * (unsigned long long)q);
 	key[i] = ((uint32_t)bin << 12) | (uint32_t)(4095 - min(4095, (m + q) >> 2));
@@ -289,25 +171,16 @@ static int run_dp_binned(gsa_ctx *ctx, Ws3 &ws, const DpProblem *d_prob, DpProbl
 	// the many small ones
 	size_t off[DP_NBINS + 1]; off[0] = 0;
 	for (int b = 0; b < DP_NBINS; b++) off[b + 1] = off[b] + st->count[b];
-	const bool side = (st->count[DPX_CLS_G8] + st->count[DPX_CLS_G16]) > 0;
+	const bool side = (st->count[DPX_CLS_G8] + st->count[DPX_CLS_G16] + st->count[DPX_NSIZE + DPX_CLS_G8] + st->count[DPX_NSIZE + DPX_CLS_G16]) > 0;
 	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0)); }
-	const int order[DPX_CLS_SCALAR] = {DPX_CLS_G16, DPX_CLS_G8, DPX_CLS_G4, DPX_CLS_S2, DPX_CLS_S1};
-	for (int cls : order) {
-		cudaStream_t st_cls = cls >= DPX_CLS_G8 ? ctx->stream2 : ctx->stream;
-		GSA_TRY(gsa_dpx_launch(ctx, st_cls, cls, std::max(1, st->max_m[cls]), std::max(1, st->max_n[cls]), d_sorted + off[cls], (int)st->count[cls], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
-	}
-	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
-	size_t beg = off[DP_BIN_SCALAR];
-	const int caps[] = {32, 128, 512, 2048, DP_MAX_DIM};
-	for (int c = 0; c < 5; c++) {
-		int cnt = (int)st->count[DP_BIN_SCALAR + c];
-		if (cnt > 0) {
-			if (c == 0) GSA_TRY(launch_dp<32>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
-			else if (c == 1) GSA_TRY(launch_dp<64>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
-			else GSA_TRY(launch_dp<256>(ctx, d_sorted + beg, cnt, caps[c], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
+	const int order[DPX_NSIZE] = {DPX_CLS_G16, DPX_CLS_G8, DPX_CLS_G4, DPX_CLS_S2, DPX_CLS_S1};
+	for (int size : order)
+		for (int hasn = 0; hasn < 2; hasn++) {
+			const int cls = size + hasn * DPX_NSIZE;
+			cudaStream_t st_cls = size >= DPX_CLS_G8 ? ctx->stream2 : ctx->stream;
+			GSA_TRY(gsa_dpx_launch(ctx, st_cls, cls, std::max(1, st->max_m[cls]), std::max(1, st->max_n[cls]), d_sorted + off[cls], (int)st->count[cls], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
 		}
-		beg += cnt;
-	}
+	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
 	if (e1) CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
 	return GSA_OK;
 }
@@ -444,11 +317,11 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 		if (p.m <= 0 || p.n <= 0) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_dp_batch: empty fragment in pair %d", i);
 		p.ref_chars = d_ref + ref_off[i]; p.qry_chars = d_qry + qry_off[i]; p.rpos = 0; p.flag_off = fbytes; p.out_off = ref_off[i] + qry_off[i];
 		if (std::max(p.m, p.n) > DP_MAX_DIM) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_dp_batch: fragment longer than %d in pair %d", DP_MAX_DIM, i);
-		bool other = false; // any letter outside ACGT/acgt sends the pair to the scalar kernel
+		bool other = false; // any letter outside ACGT/acgt: the HASN variant of the kernels
 		for (int64_t k = ref_off[i]; k < ref_off[i + 1] && !other; k++) { char c = ref[k] & 0xDF; other = !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
 		for (int64_t k = qry_off[i]; k < qry_off[i + 1] && !other; k++) { char c = qry[k] & 0xDF; other = !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
 		p.frag = i; p.cls = dpx_class(p.m, p.n, other);
-		fbytes += dpx_flag_bytes(p.m, p.n, p.cls);
+		fbytes += dpx_flag_bytes(p.m, p.n);
 	}
 	uint8_t *flags = ws.get<uint8_t>(fbytes + 256);
 	if (ws.rc) return ws.rc;

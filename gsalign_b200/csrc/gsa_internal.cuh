@@ -72,7 +72,7 @@ struct gsa_ctx {
 	cudaStream_t stream = nullptr;
 	cudaStream_t stream2 = nullptr; // side stream (forked from / joined to `stream` with ev_fork / ev_join)
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-	cudaEvent_t ev[12] = {};        // 0/1 h2d, 2/3 seed, 4/5 cluster, 6/7 fill, 8/9 k_seed, 10/11 k_dp
+	cudaEvent_t ev[12] = {};        // 0/1 h2d, 2/3 seed, 4/5 cluster, 6/7 fill, 8/9 k_seed, 10/11 the DP launches
 	bool own_stream = true; bool dp_timed = false;
 	std::string err;
 	gsa_params prm;

@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 400 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_pipeline.py -k "rearranged" -x -q > gpurun_out/sanitizer_seams.log 2>&1; echo "memcheck seams rc=$?"; tail -4 gpurun_out/sanitizer_seams.log
-timeout 400 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_lanes.py -x -q > gpurun_out/sanitizer_lanes.log 2>&1; echo "memcheck lanes rc=$?"; tail -4 gpurun_out/sanitizer_lanes.log
-timeout 400 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_pipeline.py -k "dpx_classes" -x -q > gpurun_out/sanitizer_race.log 2>&1; echo "racecheck dpx rc=$?"; tail -8 gpurun_out/sanitizer_race.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python tools/bench_dp.py --sizes 64,256,1024 --cells 2e9 2>&1 | cut -c1-110 | head -3
+python bench.py --workload C3s --steps 3 --warmup 3 --no-cpu-baseline --no-dp-stress 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['phases_ms_per_step'])"
