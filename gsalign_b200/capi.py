@@ -55,7 +55,7 @@ class Timing(C.Structure):
 
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
-           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device", "gsa_set_host_results"]
+           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device", "gsa_set_host_results", "gsa_dp_batch_identity"]
 
 
 def load_library() -> C.CDLL:
@@ -224,6 +224,24 @@ class Aligner:
                                         qb.ctypes.data_as(C.c_char_p), _p(qo, C.c_int64), o1.ctypes.data_as(C.c_char_p),
                                         o2.ctypes.data_as(C.c_char_p), _p(ol, C.c_int32), C.byref(ms)))
         return o1, o2, ol, ms.value
+
+    def dp_batch_identity(self, refs, qrys):
+        """refs/qrys: lists of bytes.  Returns list of (row1, row2, identical columns)."""
+        n = len(refs)
+        ro = np.zeros(n + 1, dtype=np.int64); qo = np.zeros(n + 1, dtype=np.int64)
+        ro[1:] = np.cumsum([len(x) for x in refs]); qo[1:] = np.cumsum([len(x) for x in qrys])
+        rb = np.frombuffer(b"".join(refs) + b"\0", dtype=np.uint8); qb = np.frombuffer(b"".join(qrys) + b"\0", dtype=np.uint8)
+        tot = int(ro[-1] + qo[-1]) + 1
+        o1 = np.zeros(tot, dtype=np.uint8); o2 = np.zeros(tot, dtype=np.uint8)
+        ol = np.zeros(max(n, 1), dtype=np.int32); oi = np.zeros(max(n, 1), dtype=np.int32)
+        self._chk(self.lib.gsa_dp_batch_identity(self.ctx, C.c_int32(n), rb.ctypes.data_as(C.c_char_p), _p(ro, C.c_int64),
+                                                 qb.ctypes.data_as(C.c_char_p), _p(qo, C.c_int64), o1.ctypes.data_as(C.c_char_p),
+                                                 o2.ctypes.data_as(C.c_char_p), _p(ol, C.c_int32), _p(oi, C.c_int32)))
+        res = []
+        for i in range(n):
+            off = int(ro[i] + qo[i]); L = int(ol[i])
+            res.append((o1[off:off + L].tobytes(), o2[off:off + L].tobytes(), int(oi[i])))
+        return res
 
     def dp_batch(self, refs, qrys):
         """refs/qrys: lists of bytes.  Returns (list of (row1,row2)), kernel_ms."""

@@ -279,7 +279,15 @@ int gsa_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *
 {
 	if (!ctx || n_pairs < 0) return GSA_ERR_ARG;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-	return gsa_impl_dp_batch(ctx, n_pairs, ref, ref_off, qry, qry_off, out1, out2, out_len, kernel_ms);
+	return gsa_impl_dp_batch(ctx, n_pairs, ref, ref_off, qry, qry_off, out1, out2, out_len, nullptr, kernel_ms);
+}
+
+int gsa_dp_batch_identity(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
+                          const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, int32_t *out_identical)
+{
+	if (!ctx || n_pairs < 0 || !out_identical) return GSA_ERR_ARG;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	return gsa_impl_dp_batch(ctx, n_pairs, ref, ref_off, qry, qry_off, out1, out2, out_len, out_identical, nullptr);
 }
 
 } // extern "C"

@@ -296,7 +296,7 @@ __global__ void k_batch_left_align(const DpProblem *prob, int n, const int32_t *
 
 // ---- stand-alone DP batch (dump hook / DP stress bench) -----------------------------------------------------
 int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
-                      const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms)
+                      const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, int32_t *out_identical, float *kernel_ms)
 {
 	if (kernel_ms) *kernel_ms = 0;
 	if (n_pairs == 0) return GSA_OK;
@@ -307,6 +307,10 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 	char *d_t1 = ws.get<char>(rb + qb + 1), *d_t2 = ws.get<char>(rb + qb + 1);
 	int32_t *d_len = ws.get<int32_t>(n_pairs);
 	int64_t *d_start = ws.get<int64_t>(n_pairs);
+	// with out_identical every pair is its own "block": the kernels' per-block sums then are the per-pair column counts
+	gsa_frag *d_frag = out_identical ? ws.get<gsa_frag>(n_pairs) : nullptr;
+	int32_t *d_fblk = out_identical ? ws.get<int32_t>(n_pairs) : nullptr;
+	unsigned int *d_bsum = out_identical ? ws.get<unsigned int>(2 * (int64_t)n_pairs) : nullptr;
 	DpProblem *d_prob = ws.get<DpProblem>(n_pairs), *d_sorted = ws.get<DpProblem>(n_pairs);
 	if (ws.rc) return ws.rc;
 	std::vector<DpProblem> hp((size_t)n_pairs);
@@ -330,14 +334,24 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_prob, hp.data(), hp.size() * sizeof(DpProblem), cudaMemcpyHostToDevice, ctx->stream));
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0); cudaEventCreate(&e1);
-	int rc = run_dp_binned(ctx, ws, d_prob, d_sorted, n_pairs, flags, d_t1, d_t2, d_len, d_start, nullptr, nullptr, nullptr, e0, e1);
+	if (out_identical) {
+		std::vector<int32_t> ident((size_t)n_pairs);
+		for (int i = 0; i < n_pairs; i++) ident[(size_t)i] = i;
+		CUDA_TRY(ctx, cudaMemcpyAsync(d_fblk, ident.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(ctx, cudaMemsetAsync(d_bsum, 0, (size_t)n_pairs * 8, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // ident is a local
+	}
+	int rc = run_dp_binned(ctx, ws, d_prob, d_sorted, n_pairs, flags, d_t1, d_t2, d_len, d_start, d_frag, d_fblk, d_bsum, e0, e1);
 	if (rc == GSA_OK) {
 		k_batch_left_align<<<gsa_grid(n_pairs, 8), 256, 0, ctx->stream>>>(d_prob, n_pairs, d_len, d_start, d_t1, d_t2, d_o1, d_o2);
 		KERNEL_CHECK(ctx);
 		CUDA_TRY(ctx, cudaMemcpyAsync(out1, d_o1, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(out2, d_o2, (size_t)(rb + qb), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(out_len, d_len, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		std::vector<unsigned int> hb;
+		if (out_identical) { hb.resize(2 * (size_t)n_pairs); CUDA_TRY(ctx, cudaMemcpyAsync(hb.data(), d_bsum, hb.size() * 4, cudaMemcpyDeviceToHost, ctx->stream)); }
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		for (int i = 0; out_identical && i < n_pairs; i++) out_identical[i] = (int32_t)hb[2 * (size_t)i + 1];
 		if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
 	}
 	cudaEventDestroy(e0); cudaEventDestroy(e1);

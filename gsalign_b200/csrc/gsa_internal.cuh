@@ -159,4 +159,4 @@ void gsa_host_remove_bad(std::vector<BlockHdr> &vec);
 int gsa_host_chr_idx(const gsa_ctx *ctx, int64_t rpos, int64_t *end_out);
 int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out);
 int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
-                      const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms);
+                      const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, int32_t *out_identical, float *kernel_ms);

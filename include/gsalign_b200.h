@@ -174,6 +174,12 @@ int64_t gsa_dump_blocks(gsa_ctx *ctx, int32_t stage, int64_t *out);
 int gsa_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
                  const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, float *kernel_ms);
 
+/* Same, and out_identical[i] = number of identical columns of pair i as CountIdenticalPairs counts them
+ * (src/ProcessCandidateAlignment.cpp:38-47: nst_nt4_table classes, so '-' equals any non-ACGT letter), i.e. what
+ * gsa_fill adds to AlnBlock_t::score for a gap fragment. */
+int gsa_dp_batch_identity(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
+                          const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, int32_t *out_identical);
+
 /* On-box microbenchmark of the packed-int16 DPX issue rate, the roofline denominator of K3:
  * which 0 = VIADDMNMX.S16x2 (__viaddmax_s16x2), 1 = VIMNMX.S16x2, 2 = VIADD.16x2, 3 = VIMNMX3.S16x2.
  * Result in 1e9 thread-level instructions per second (each works on two int16 lanes). */

@@ -194,3 +194,34 @@ def test_dpx_classes_vs_oracle(oracle):
     for a, b, (x, y) in zip(refs, qrys, res):
         assert (x, y) == oracle.dp_align(a, b), (len(a), len(b))
     al.close()
+
+
+def _nt4(ch):
+    return {65: 0, 97: 0, 67: 1, 99: 1, 71: 2, 103: 2, 84: 3, 116: 3}.get(ch, 4)
+
+
+def test_dpx_other_letters_all_classes(oracle):
+    """pairs holding N / IUPAC letters (score 0 against everything) in every size class of the HASN variant, rows vs the oracle
+    and identical-column counts vs CountIdenticalPairs' rule (nt4 classes: '-' equals a non-ACGT letter, hazard H7)"""
+    import random
+    from gsalign_b200 import capi
+    rng = random.Random(23)
+    refs, qrys = [], []
+    for m, n in [(1, 1), (9, 64), (64, 65), (130, 120), (200, 250), (700, 200), (300, 320), (520, 500), (1100, 1000), (2600, 2500), (5, 3000), (3000, 5)]:
+        a = bytearray(rng.choice(b"ACGT") for _ in range(m))
+        b = bytearray(_mutate(rng, bytes(a), 0.05, 0.02)) if min(m, n) > 8 and abs(m - n) < 0.3 * m else bytearray(rng.choice(b"ACGT") for _ in range(n))
+        for s, frac in ((a, 0.02), (b, 0.06)):                    # sprinkle other letters, and one run of N in the query
+            for i in range(len(s)):
+                if rng.random() < frac:
+                    s[i] = rng.choice(b"NnRYKM")
+        if len(b) > 40:
+            b[10:30] = b"N" * 20
+        if not any(_nt4(c) == 4 for c in a + b):
+            b[0] = ord("N")
+        refs.append(bytes(a)); qrys.append(bytes(b))
+    al = capi.Aligner(0)
+    res = al.dp_batch_identity(refs, qrys)
+    for a, b, (x, y, same) in zip(refs, qrys, res):
+        assert (x, y) == oracle.dp_align(a, b), (len(a), len(b))
+        assert same == sum(_nt4(c1) == _nt4(c2) for c1, c2 in zip(x, y)), (len(a), len(b))
+    al.close()
