@@ -23,7 +23,7 @@
 //   sa    the FULL suffix array, u32 per row (n < 2^32 in this build): sa[row] = start of the suffix.
 //   kbits one bit per k-mer, k = min(MinSeedLength, 16): set iff the k-mer occurs in T (T is its own reverse complement).
 //         A search whose first k bases do not occur cannot yield a seed: zero index accesses for it.
-//   ktab  for every k-mer w (k = ktab_k, code = bases big-endian): the row interval {lo, size} of
+//   ktab  for every k-mer w (k = ktab_k, code = bases big-endian; when size == 1 lo is SA[row] itself): the row interval {lo, size} of
 //         revcomp(w); size 0 = w does not occur in T.
 // ----------------------------------------------------------------------------------------------
 struct DevIndex {

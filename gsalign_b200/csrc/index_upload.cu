@@ -101,6 +101,9 @@ __global__ void k_build_ktab(DevIndex ix, int k, uint2 *ktab, uint32_t ncodes)
 		gsa_occ2(ix, c, lo - 1, lo + size - 1, o1, o2);
 		lo = ix.L2[c] + o1 + 1; size = o2 - o1;
 	}
+	// a k-mer that occurs once needs no rank step, only its position: the entry carries SA[lo] itself and the search
+	// goes from the table straight to the text (size == 1 <=> .x is a suffix-array value, not a row)
+	if (size == 1) lo = __ldg(ix.sa + lo);
 	ktab[code] = make_uint2(lo, size);
 }
 

@@ -91,6 +91,7 @@ __device__ __forceinline__ int seed_search(const DevIndex &ix, const uint32_t *_
 	uint2 iv = __ldg(ix.ktab + code);
 	lo = iv.x; size = iv.y;
 	if (size == 0) return 0;
+	const bool lo_is_sa = size == 1; // a k-mer occurring once: the table holds its suffix-array value, not its row
 	uint32_t pos = start + K;
 	// 2. backward search while the interval holds several rows
 	while (size > 1 && pos < stop) {
@@ -104,7 +105,7 @@ __device__ __forceinline__ int seed_search(const DevIndex &ix, const uint32_t *_
 	// 3/4. unique: locate once, then compare the 2-bit query against the 2-bit text
 	if (size == 1) {
 		uint32_t m = pos - start;
-		uint32_t p = ix.n - __ldg(ix.sa + lo) - m;  // start of the match in T
+		uint32_t p = ix.n - (lo_is_sa ? lo : __ldg(ix.sa + lo)) - m;  // start of the match in T
 		rpos = p;
 		uint32_t tpos = p + m;
 		while (pos < stop && tpos < ix.n) {
@@ -243,7 +244,11 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 		} else if (st == ST_KTAB) {
 			lo = kt_lo; size = kt_size;
 			if (size == 0) { pos = start; fin = true; }
-			else { pos = start + K; st = ST_BWD_ISSUE; }
+			else if (size == 1) { // the table entry is the suffix-array value: straight to the text
+				pos = start + K;
+				rpos = ix.n - lo - (uint32_t)K; tpos = rpos + (uint32_t)K;
+				st = ST_CMP_ISSUE;
+			} else { pos = start + K; st = ST_BWD_ISSUE; }
 		} else if (st == ST_BWD) {
 			uint32_t o1 = bw_c1 + gsa_block_count(bw_s1, c, (int)(r1 & 63) + 1) - (uint32_t)(c == 0 && r1 >= ix.primary);
 			uint32_t o2 = bw_c2 + gsa_block_count(bw_s2, c, (int)(r2 & 63) + 1) - (uint32_t)(c == 0 && r2 >= ix.primary);
