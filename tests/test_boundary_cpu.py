@@ -171,3 +171,45 @@ def test_two_rank_gloo_record_gather():
     for r in range(2):
         assert got[r] == res[r][1]
     assert sorted(c for r in range(2) for c, _ in got[r]) == list(range(6))
+
+
+_LOADER_HARNESS = r'''
+#include "host.h"
+int main(int argc, char **argv)
+{
+	std::vector<QueryChr> q;
+	bool ok = load_query_file(argv[1], q);
+	printf("ok=%d n=%zu\n", ok ? 1 : 0, q.size());
+	for (auto &c : q) printf("[%s] %zu %s\n", c.name.c_str(), c.seq.size(), c.seq.c_str());
+	return 0;
+}
+'''
+
+
+def test_query_fasta_reader_edge_cases(tmp_path):
+    """the CLI's parallel, memory-mapped FASTA reader keeps LoadQueryFile's rules (reference src/main.cpp:35-114): header
+    trimming, CR stripping, empty lines and records, no trailing newline, sequence before a header, non-letters"""
+    import subprocess
+    host = os.path.join(ROOT, "gsalign_b200", "csrc", "host")
+    src = tmp_path / "ld.cpp"
+    src.write_text(_LOADER_HARNESS)
+    exe = str(tmp_path / "ld")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", host, "-o", exe, str(src), os.path.join(host, "io.cpp"), "-lpthread"], check=True)
+
+    def run(text: bytes):
+        f = tmp_path / "q.fa"
+        f.write_bytes(text)
+        r = subprocess.run([exe, str(f)], capture_output=True, text=True)
+        return r.stdout.splitlines(), r.stderr
+
+    out, _ = run(b"\n\n>chr1 some comment\nACGTNNacgt\r\n\nGGGG\n>chr2|x:1\nTTTT\n>empty\n>last\nAC")
+    assert out == ["ok=1 n=4", "[chr1] 14 ACGTNNacgtGGGG", "[chr2-x] 4 TTTT", "[empty] 0 ", "[last] 2 AC"]
+    out, _ = run(b"ACGT\n>chr1\nAC\n")                       # sequence before any header
+    assert out[0] == "ok=0 n=0"
+    out, err = run(b">c\nAC1GT\n")                           # a non-letter: the line is echoed, the load fails
+    assert out[0] == "AC1GT" and "ok=0" in out[1] and "non-alphabet" in err
+    out, err = run(b">c\nACGT\n>d\nAC>GT\n")                 # '>' inside a sequence line is a non-letter too
+    assert out[0] == "AC>GT" and "ok=0" in out[1]
+    big = b">a\n" + b"ACGT" * 50_000 + b"\n" + b"".join(b">s%d\n%s\n" % (i, b"GATTACA" * (i + 1)) for i in range(40))
+    out, _ = run(big)
+    assert out[0] == "ok=1 n=41" and out[1].startswith("[a] 200000 ACGTACGT") and out[41] == "[s39] 280 " + "GATTACA" * 40
