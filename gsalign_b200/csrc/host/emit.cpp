@@ -1,10 +1,19 @@
 // emit.cpp -- MAF / ALN / VCF emitters of bin/GSAlign, byte-compatible with the reference
 // (src/tools.cpp:3-44,142-286 and src/SeqVariant.cpp:6-143; format hazards H3-H8, H15 of SURVEY.md).
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <functional>
 #include <thread>
 #include "host.h"
+
+// fragments per thread chunk (row assembly, variant scan) and VCF records per formatting batch; GSA_EMIT_CHUNK shrinks
+// them so that the tests reach the multi-threaded paths on small inputs
+static int64_t emit_chunk()
+{
+	static const int64_t v = [] { const char *e = getenv("GSA_EMIT_CHUNK"); int64_t x = e ? atoll(e) : 0; return x > 0 ? x : (int64_t)65536; }();
+	return v;
+}
 
 // runs fn(k) for k in [0, n) on up to `threads` host threads (k = chunk index; the caller splits its range)
 static void parallel_chunks(int n, int threads, const std::function<void(int)> &fn)
@@ -75,7 +84,7 @@ static void build_rows(const QueryChr &qc, const ContigResult &r, const gsa_bloc
 	a1.resize((size_t)b.aln_len + 1); a2.resize((size_t)b.aln_len + 1);
 	a1[(size_t)b.aln_len] = a2[(size_t)b.aln_len] = '\0';
 	const int64_t nf = b.n_frags;
-	int nch = (int)std::max<int64_t>(1, std::min<int64_t>(threads, nf / 65536));
+	int nch = (int)std::max<int64_t>(1, std::min<int64_t>(threads, nf / emit_chunk()));
 	std::vector<size_t> start((size_t)nch + 1, 0);
 	std::vector<int64_t> g1((size_t)nch, 0), g2((size_t)nch, 0);
 	auto frag_len = [&](int64_t t) { const gsa_frag &f = r.frags[(size_t)t]; return (size_t)(f.bSeed ? f.qLen : f.aln_len); };
@@ -272,7 +281,7 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 		// fragments are independent: big blocks are scanned by several threads and their records appended in fragment order,
 		// i.e. in exactly the order the serial loop pushes them (the order matters: the final sort is unstable)
 		const int64_t nf = b.n_frags;
-		const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(st.threads, nf / 65536));
+		const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(st.threads, nf / emit_chunk()));
 		std::vector<std::vector<Variant> > part((size_t)nch);
 		std::vector<std::string> pool((size_t)nch);
 		std::vector<VarCounts> cnt((size_t)nch);
@@ -324,7 +333,7 @@ void output_variants(const Options &o, const HostIndex &ix, EmitState &st)
 	fprintf(out, "#CHROM	POS	ID	REF	ALT	QUAL	FILTER	INFO\n");
 	// records are formatted into per-thread buffers, a batch at a time, and written in order.  "%s" of an allele stops at a
 	// NUL, which an allele cannot hold (query letters are alphabetic, reference letters ACGT), so lengths can be used as they are.
-	const size_t batch = 1u << 20;
+	const size_t batch = (size_t)emit_chunk() * 16;
 	const int nth = std::max(1, st.threads);
 	std::vector<std::string> buf((size_t)nth);
 	for (size_t b0 = 0; b0 < keys.size(); b0 += batch * (size_t)nth) {

@@ -1,0 +1,78 @@
+"""Host logic on CPU: the CLI's MAF / ALN / VCF emitters (gsalign_b200/csrc/host/emit.cpp, multi-threaded) fed with the
+alignment records of the UNMODIFIED reference (its own containers, through oracle/_ref/libgsref.so) must write the files the
+reference CLI writes, byte for byte.  No GPU involved: this pins the emitters independently of the kernels."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+HOST = os.path.join(ROOT, "gsalign_b200", "csrc", "host")
+
+FRAG = np.dtype([("rPos", "<i8"), ("qPos", "<i4"), ("qLen", "<i4"), ("rLen", "<i4"), ("bSeed", "<i4"), ("aln_off", "<i8"), ("aln_len", "<i4"), ("reserved", "<i4")])
+BLOCK = np.dtype([("score", "<i4"), ("aln_len", "<i4"), ("bDup", "<i4"), ("n_frags", "<i4"), ("frag_beg", "<i8")])
+
+
+def _records(ref_contig):
+    """one contig of tests/ref_worker.py's result -> the byte stream tests/emit_harness.cpp reads"""
+    ref_aln, k = {}, 0
+    for b in ref_contig["stages"][4]:            # aln strings come in stage-4 order (before the identity filter)
+        for f in b[3]:
+            if f[0] == 0:
+                ref_aln[(f[1], f[2], f[3], f[4])] = (ref_contig["aln"][k], ref_contig["aln"][k + 1]); k += 2
+    final = ref_contig["stages"][5]
+    blocks = np.zeros(len(final), dtype=BLOCK)
+    frags, a1, a2 = [], bytearray(), bytearray()
+    for bi, (score, aln_len, dup, fr) in enumerate(final):
+        blocks[bi] = (score, aln_len, dup, len(fr), len(frags))
+        for (seed, q, r, ql, rl) in fr:
+            if seed:
+                frags.append((r, q, ql, rl, 1, 0, ql, 0))
+            else:
+                x, y = ref_aln[(q, r, ql, rl)]
+                assert len(x) == len(y)
+                frags.append((r, q, ql, rl, 0, len(a1), len(x), 0))
+                a1 += x; a2 += y
+    fa = np.array(frags, dtype=FRAG) if frags else np.zeros(0, dtype=FRAG)
+    return struct.pack("<i", len(final)) + blocks.tobytes() + struct.pack("<q", len(fa)) + fa.tobytes() + struct.pack("<q", len(a1)) + bytes(a1) + bytes(a2)
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("emit") / "emit_harness")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", HOST, "-o", exe, os.path.join(HERE, "emit_harness.cpp"), os.path.join(HOST, "emit.cpp"),
+                    os.path.join(HOST, "io.cpp"), "-lpthread"], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("fmt,threads,prm,flags", [(1, 1, {}, []), (1, 5, {}, []), (2, 3, {}, ["-fmt", "2"]),
+                                                   (1, 4, dict(min_seed_len=10, sensitive=1, min_block_score=50), ["-sen"])])
+def test_emitters_match_reference_cli(workdir, harness, fmt, threads, prm, flags):
+    from conftest import build_index
+    from test_gpu_pipeline import make_rearranged, run_reference
+    exe = os.path.join(orc.REF_DIR, "GSAlign")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/GSAlign not built")
+    d = make_rearranged(workdir)
+    prefix, qry = os.path.join(d, "ref"), os.path.join(d, "qry.fa")
+    build_index(os.path.join(d, "ref.fa"), prefix)
+    tag = f"{fmt}_{threads}_{'sen' if prm else 'def'}"
+    ref = run_reference(prefix, qry, os.path.join(d, f"emit_ref_{tag}.pkl"), **prm)
+    rec = os.path.join(d, f"records_{tag}.bin")
+    with open(rec, "wb") as f:
+        for c in ref:
+            f.write(_records(c))
+    ours, theirs = os.path.join(d, f"emit_ours_{tag}"), os.path.join(d, f"emit_ref_{tag}")
+    env = dict(os.environ, GSA_EMIT_CHUNK="40")   # small chunks: the blocks here have a few thousand fragments, the threads must all get some
+    subprocess.run([harness, prefix, qry, rec, ours, str(fmt), str(threads)], check=True, stderr=subprocess.DEVNULL, env=env)
+    subprocess.run([exe, "-t", "1", "-i", prefix, "-q", qry, "-o", theirs] + flags, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ext = ".maf" if fmt == 1 else ".aln"
+    for e in (ext, ".vcf"):
+        with open(ours + e, "rb") as a, open(theirs + e, "rb") as b:
+            assert a.read() == b.read(), e
+    assert os.path.getsize(ours + ".vcf") > 1000 and os.path.getsize(ours + ext) > 100_000
