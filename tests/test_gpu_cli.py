@@ -75,8 +75,10 @@ def test_multi_gpu_flag_same_bytes(workdir):
     n = min(2, torch.cuda.device_count())
     run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "g1"])
     run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "g2", "-gpus", str(n)])
+    run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "g3", "-lanes", "1", "-t", "16"])   # one contig in flight, 16 emitter threads
     for ext in ("maf", "vcf"):
-        assert filecmp.cmp(os.path.join(d, f"g1.{ext}"), os.path.join(d, f"g2.{ext}"), shallow=False)
+        for other in ("g2", "g3"):
+            assert filecmp.cmp(os.path.join(d, f"g1.{ext}"), os.path.join(d, f"{other}.{ext}"), shallow=False), (other, ext)
 
 
 def _index_equal(d, fasta):
