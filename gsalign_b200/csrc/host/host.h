@@ -10,12 +10,19 @@
 #include "../../../include/gsalign_b200.h"
 
 struct HostIndex {                 // bwaidx_t as loaded by bwa_idx_load (reference src/bwt_index.cpp:147-159)
-	std::vector<uint32_t> bwt;
+	// .bwt / .sa / .pac are mapped, not copied: the arrays below point into the mappings (private, so that sa[0] can be
+	// set to -1 like bwt_restore_sa does) and go to the GPU straight from the page cache
+	const uint32_t *bwt = nullptr; uint64_t bwt_size = 0;   // words after the 5 x u64 header
 	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0;
-	std::vector<uint64_t> sa;
+	const uint64_t *sa = nullptr; uint64_t n_sa = 0;        // sa[0] = (uint64_t)-1
 	int sa_intv = 32;
-	std::vector<uint8_t> pac;
+	const uint8_t *pac = nullptr;
 	int64_t l_pac = 0;
+	struct Mapping { void *p = nullptr; size_t n = 0; } maps[3];
+	HostIndex() {}
+	HostIndex(const HostIndex &) = delete;
+	HostIndex &operator=(const HostIndex &) = delete;
+	~HostIndex();
 	std::vector<std::string> names; // ChromosomeVec[i].name
 	std::vector<int64_t> offset;    // FowardLocation
 	std::vector<int32_t> len;

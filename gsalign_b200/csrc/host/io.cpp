@@ -13,38 +13,44 @@
 #include <thread>
 #include "host.h"
 
-static bool read_file(const std::string &path, std::vector<uint8_t> &out)
+// maps a whole file privately (copy-on-write); returns false when it cannot be opened or is empty
+static bool map_file(const std::string &path, HostIndex::Mapping &m)
 {
-	FILE *fp = fopen(path.c_str(), "rb");
-	if (!fp) return false;
-	fseek(fp, 0, SEEK_END);
-	long n = ftell(fp);
-	fseek(fp, 0, SEEK_SET);
-	out.resize((size_t)n);
-	size_t got = n > 0 ? fread(out.data(), 1, (size_t)n, fp) : 0;
-	fclose(fp);
-	return got == (size_t)n;
+	int fd = open(path.c_str(), O_RDONLY);
+	if (fd < 0) return false;
+	struct stat sb;
+	if (fstat(fd, &sb) != 0 || sb.st_size <= 0) { close(fd); return false; }
+	void *p = mmap(nullptr, (size_t)sb.st_size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if (p == MAP_FAILED) return false;
+	m.p = p; m.n = (size_t)sb.st_size;
+	return true;
+}
+
+HostIndex::~HostIndex()
+{
+	for (Mapping &m : maps) if (m.p) munmap(m.p, m.n);
 }
 
 // bwt_restore_bwt / bwt_restore_sa / bns_restore_core (reference src/bwt_index.cpp:15-121)
 bool HostIndex::load(const std::string &prefix, std::string &err)
 {
-	std::vector<uint8_t> raw;
-	if (!read_file(prefix + ".bwt", raw) || raw.size() < 40) { err = "cannot read " + prefix + ".bwt"; return false; }
-	const uint64_t *h = (const uint64_t *)raw.data();
+	for (Mapping &m : maps) if (m.p) { munmap(m.p, m.n); m = Mapping(); }
+	if (!map_file(prefix + ".bwt", maps[0]) || maps[0].n < 40) { err = "cannot read " + prefix + ".bwt"; return false; }
+	const uint64_t *h = (const uint64_t *)maps[0].p;
 	primary = h[0]; L2[0] = 0; for (int i = 1; i < 5; i++) L2[i] = h[i];
 	seq_len = L2[4];
-	bwt.resize((raw.size() - 40) / 4);
-	memcpy(bwt.data(), raw.data() + 40, bwt.size() * 4);
-	if (!read_file(prefix + ".sa", raw) || raw.size() < 56) { err = "cannot read " + prefix + ".sa"; return false; }
-	h = (const uint64_t *)raw.data();
+	bwt = (const uint32_t *)((const char *)maps[0].p + 40); bwt_size = (maps[0].n - 40) / 4;
+	if (!map_file(prefix + ".sa", maps[1]) || maps[1].n < 56) { err = "cannot read " + prefix + ".sa"; return false; }
+	h = (const uint64_t *)maps[1].p;
 	sa_intv = (int)h[5];                       // hazard H13: the reference reads this u64 into an int
 	if (sa_intv <= 0) { err = "bad sa_intv in " + prefix + ".sa"; return false; }
-	uint64_t n_sa = (seq_len + (uint64_t)sa_intv) / (uint64_t)sa_intv;
-	if (raw.size() < 56 + (n_sa - 1) * 8) { err = prefix + ".sa is truncated"; return false; }
-	sa.resize(n_sa);
-	sa[0] = (uint64_t)-1;
-	memcpy(sa.data() + 1, raw.data() + 56, (n_sa - 1) * 8);
+	n_sa = (seq_len + (uint64_t)sa_intv) / (uint64_t)sa_intv;
+	if (maps[1].n < 56 + (n_sa - 1) * 8) { err = prefix + ".sa is truncated"; return false; }
+	// the samples follow a 7-word header: seen from its last word the file IS the array, once that word is sa[0] = -1
+	uint64_t *sa_w = (uint64_t *)((char *)maps[1].p + 48);
+	sa_w[0] = (uint64_t)-1;
+	sa = sa_w;
 	FILE *fp = fopen((prefix + ".ann").c_str(), "r");
 	if (!fp) { err = "cannot read " + prefix + ".ann"; return false; }
 	long long xx; int n_seqs; unsigned seed;
@@ -61,8 +67,8 @@ bool HostIndex::load(const std::string &prefix, std::string &err)
 		offset.push_back(xx); len.push_back(l);
 	}
 	fclose(fp);
-	if (!read_file(prefix + ".pac", raw) || (int64_t)raw.size() < l_pac / 4 + 1) { err = "cannot read " + prefix + ".pac"; return false; }
-	pac.assign(raw.begin(), raw.begin() + (size_t)(l_pac / 4 + 1));
+	if (!map_file(prefix + ".pac", maps[2]) || (int64_t)maps[2].n < l_pac / 4 + 1) { err = "cannot read " + prefix + ".pac"; return false; }
+	pac = (const uint8_t *)maps[2].p;
 	// RestoreReferenceInfo (reference src/bwt_index.cpp:229-253): locations are cumulative lengths
 	chr_loc.clear();
 	int64_t total = 0;
@@ -78,10 +84,10 @@ bool HostIndex::load(const std::string &prefix, std::string &err)
 
 void HostIndex::view(gsa_index_view *v) const
 {
-	v->bwt = bwt.data(); v->bwt_size = bwt.size(); v->primary = primary;
+	v->bwt = bwt; v->bwt_size = bwt_size; v->primary = primary;
 	for (int i = 0; i < 5; i++) v->L2[i] = L2[i];
-	v->seq_len = seq_len; v->sa = sa.data(); v->n_sa = sa.size(); v->sa_intv = sa_intv;
-	v->pac = pac.data(); v->l_pac = l_pac; v->n_contigs = (int32_t)names.size();
+	v->seq_len = seq_len; v->sa = sa; v->n_sa = n_sa; v->sa_intv = sa_intv;
+	v->pac = pac; v->l_pac = l_pac; v->n_contigs = (int32_t)names.size();
 	v->contig_off = offset.data(); v->contig_len = len.data();
 }
 
