@@ -55,7 +55,8 @@ class Timing(C.Structure):
 
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
-           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device", "gsa_set_host_results", "gsa_dp_batch_identity"]
+           "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device", "gsa_set_host_results", "gsa_dp_batch_identity",
+           "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes"]
 
 
 def load_library() -> C.CDLL:
@@ -65,6 +66,7 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     lib.gsa_last_error.restype = C.c_char_p
     lib.gsa_dump_blocks.restype = C.c_int64
+    lib.gsa_index_bytes.restype = C.c_int64
     return lib
 
 
@@ -82,8 +84,9 @@ def _as_array(ptr, n, dtype):
 class Aligner:
     """One context per GPU; mirrors the per-contig loop of GenomeComparison (reference src/GSAlign.cpp:473)."""
 
-    def __init__(self, device: int = 0, owner: "Aligner | None" = None):
-        """owner: create a lane on the owner's GPU that shares its uploaded index (gsa_create_shared)"""
+    def __init__(self, device: int = 0, owner: "Aligner | None" = None, wide: bool = False):
+        """owner: create a lane on the owner's GPU that shares its uploaded index (gsa_create_shared);
+        wide: force the 64-bit row layout of the device index whatever the text size (gsa_set_wide_index)"""
         self.lib = load_library()
         self.ctx = C.c_void_p()
         self._owner = owner
@@ -96,6 +99,15 @@ class Aligner:
             if rc != 0:
                 raise GsaError(f"gsa_create(device={device}) failed with {rc}: no usable B200; there is no CPU fallback")
         self._keep = None
+        if wide:
+            self._chk(self.lib.gsa_set_wide_index(self.ctx, C.c_int(1)))
+
+    def clone_index_from(self, src: "Aligner"):
+        """replica of src's device index on this context's GPU, copied GPU to GPU (gsa_index_clone)"""
+        self._chk(self.lib.gsa_index_clone(self.ctx, src.ctx))
+
+    def index_bytes(self) -> int:
+        return int(self.lib.gsa_index_bytes(self.ctx))
 
     def close(self):
         if self.ctx:

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <chrono>
+#include <algorithm>
 
 int gsa_fail(gsa_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -16,7 +17,8 @@ int gsa_fail(gsa_ctx *ctx, int code, const char *fmt, ...)
 int gsa_ensure(gsa_ctx *ctx, DevBuf &b, size_t bytes)
 {
 	if (bytes <= b.cap && b.p) return GSA_OK;
-	size_t want = bytes + bytes / 4 + 256; // grow-only, with slack so that similar contigs do not reallocate
+	// grow-only, with slack so that similar contigs do not reallocate; the slack is capped: index structures are tens of GB
+	size_t want = bytes + std::min<size_t>(bytes / 4, (size_t)256 << 20) + 256;
 	if (b.p) { cudaError_t e = cudaFree(b.p); b.p = nullptr; b.cap = 0; if (e != cudaSuccess) return gsa_fail(ctx, GSA_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e)); }
 	cudaError_t e = cudaMalloc(&b.p, want);
 	if (e != cudaSuccess) { b.p = nullptr; return gsa_fail(ctx, GSA_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); }
@@ -123,6 +125,31 @@ int gsa_index_upload(gsa_ctx *ctx, const gsa_index_view *view)
 	if (!ctx) return GSA_ERR_ARG;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	return gsa_impl_index_upload(ctx, view);
+}
+
+int gsa_set_wide_index(gsa_ctx *ctx, int enable)
+{
+	if (!ctx) return GSA_ERR_ARG;
+	ctx->force_wide = enable != 0;
+	return GSA_OK;
+}
+
+int gsa_index_clone(gsa_ctx *dst, gsa_ctx *src)
+{
+	if (!dst || !src || dst == src) return GSA_ERR_ARG;
+	// the source's prefix table and presence bitmap travel with the copy
+	CUDA_TRY(src, cudaSetDevice(src->device));
+	int k = src->prm.min_seed_len < GSA_KTAB_MAX_K ? src->prm.min_seed_len : GSA_KTAB_MAX_K;
+	GSA_TRY(gsa_impl_build_ktab(src, k));
+	GSA_TRY(gsa_impl_build_kbits(src, src->prm.min_seed_len));
+	CUDA_TRY(src, cudaStreamSynchronize(src->stream));
+	return gsa_impl_index_clone(dst, src);
+}
+
+int64_t gsa_index_bytes(const gsa_ctx *ctx)
+{
+	if (!ctx || !ctx->have_index) return 0;
+	return (int64_t)(ctx->d_occ.cap + ctx->d_txt.cap + ctx->d_sa.cap + ctx->d_ktab.cap + ctx->d_kbits.cap);
 }
 
 int gsa_set_stream(gsa_ctx *ctx, void *cuda_stream)

@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, cons
 	if (r1 - q1 == r2 - q2) { // same diagonal: linear identity (ref text never holds N)
 		int idy = 0;
 		for (int k = lane; k < q_len; k += 32) {
-			int a = gsa_pk_base(ix.txt, (uint32_t)(r1 + k)), c = gsa_nt4(seq[q1 + k]);
+			int a = gsa_pk_base(ix.txt, (uint64_t)(r1 + k)), c = gsa_nt4(seq[q1 + k]);
 			idy += (a == c || c == 4);
 		}
 		for (int o = 16; o > 0; o >>= 1) idy += __shfl_xor_sync(0xffffffffu, idy, o);
@@ -512,9 +512,9 @@ __global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, cons
 			}
 		} else if (lane == 1 && r_len >= 5) { // reference k-mers (no N in the text)
 			uint32_t wid = 0;
-			for (int k = 0; k < 5; k++) wid = (wid << 2) + (uint32_t)gsa_pk_base(ix.txt, (uint32_t)(r1 + k));
+			for (int k = 0; k < 5; k++) wid = (wid << 2) + (uint32_t)gsa_pk_base(ix.txt, (uint64_t)(r1 + k));
 			h2[wid]++;
-			for (int k = 5; k < r_len; k++) { wid = ((wid & 0xFF) << 2) + (uint32_t)gsa_pk_base(ix.txt, (uint32_t)(r1 + k)); h2[wid]++; }
+			for (int k = 5; k < r_len; k++) { wid = ((wid & 0xFF) << 2) + (uint32_t)gsa_pk_base(ix.txt, (uint64_t)(r1 + k)); h2[wid]++; }
 		}
 		__syncwarp();
 		int common = 0;
@@ -860,9 +860,10 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 	GSA_TRY(gsa_ensure(ctx, ctx->d_frag, (size_t)(nfr + 1) * sizeof(gsa_frag)));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_fblk, (size_t)(nfr + 1) * 4));
 	LAUNCH(k_np_write, total, d_npb, nblk, total, cq, cr, cl, npoff, (gsa_frag *)ctx->d_frag.p, (int32_t *)ctx->d_fblk.p, d_fbeg);
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small.p, d_fbeg, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, (size_t)nblk * 8)); // O(#blocks): a fixed-size buffer overflows on highly fragmented contigs
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_fbeg, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-	const int64_t *fb = (const int64_t *)ctx->h_small.p;
+	const int64_t *fb = (const int64_t *)ctx->h_stage.p;
 	for (int k = 0; k < nblk; k++) {
 		ctx->final_blocks[k].frag_beg = fb[k];
 		ctx->final_blocks[k].n_frags = (int32_t)((k + 1 < nblk ? fb[k + 1] : nfr) - fb[k]);

@@ -43,7 +43,7 @@ __global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char
 			if (f.qLen == f.rLen) {
 				for (int k = 0; k < f.qLen && mm <= 5; k++) {
 					int b = gsa_nt4(seq[f.qPos + k]);
-					if (b != 4 && b != gsa_pk_base(ix.txt, (uint32_t)(f.rPos + k))) mm++;
+					if (b != 4 && b != gsa_pk_base(ix.txt, (uint64_t)(f.rPos + k))) mm++;
 				}
 				if (mm <= 5) ty = FT_COPY;
 			}

@@ -21,49 +21,82 @@ __device__ __forceinline__ uint32_t gsa_block_count(uint4 s, int c, int m)
 	return __popcll(hi) + __popcll(lo & (~0ull << (128 - 2 * m)));
 }
 
+// ---- row width --------------------------------------------------------------------------------------------------
+// W = false: rows, suffix-array values and text positions are u32 (|T| < 2^32); W = true: u64 (DevIndex::wide).
+template <bool W> struct RowT { typedef uint32_t t; typedef uint2 ktab_t; };
+template <> struct RowT<true> { typedef uint64_t t; typedef ulonglong2 ktab_t; };
+
 // Occ(c, r): occurrences of c among the BWT characters of rows 0..r (inclusive), '$' row excluded.
-// One 32-byte sector: two 128-bit loads from the same sector.
-__device__ __forceinline__ uint32_t gsa_occ(const DevIndex &ix, int c, uint32_t r)
+// One 32-byte sector: two 128-bit loads from the same sector.  Per-base counts fit u32 in both widths.
+template <bool W>
+__device__ __forceinline__ uint32_t gsa_occ(const DevIndex &ix, int c, typename RowT<W>::t r)
 {
 	const uint4 *blk = ix.occ + 2 * (size_t)(r >> 6);
 	uint4 cnt = __ldg(blk), sym = __ldg(blk + 1);
 	uint32_t base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
-	return base + gsa_block_count(sym, c, (int)(r & 63) + 1) - (uint32_t)(c == 0 && r >= ix.primary);
+	return base + gsa_block_count(sym, c, (int)(r & 63) + 1) - (uint32_t)(c == 0 && r >= (typename RowT<W>::t)ix.primary);
 }
 
 // Occ(c, r1) and Occ(c, r2) for r1 <= r2; shares the block when both rows fall in the same one
-__device__ __forceinline__ void gsa_occ2(const DevIndex &ix, int c, uint32_t r1, uint32_t r2, uint32_t &o1, uint32_t &o2)
+template <bool W>
+__device__ __forceinline__ void gsa_occ2(const DevIndex &ix, int c, typename RowT<W>::t r1, typename RowT<W>::t r2, uint32_t &o1, uint32_t &o2)
 {
+	typedef typename RowT<W>::t row_t;
+	const row_t primary = (row_t)ix.primary;
 	const uint4 *b1 = ix.occ + 2 * (size_t)(r1 >> 6);
 	uint4 cnt = __ldg(b1), sym = __ldg(b1 + 1);
 	uint32_t base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
-	o1 = base + gsa_block_count(sym, c, (int)(r1 & 63) + 1) - (uint32_t)(c == 0 && r1 >= ix.primary);
+	o1 = base + gsa_block_count(sym, c, (int)(r1 & 63) + 1) - (uint32_t)(c == 0 && r1 >= primary);
 	if ((r1 >> 6) != (r2 >> 6)) {
 		const uint4 *b2 = ix.occ + 2 * (size_t)(r2 >> 6);
 		cnt = __ldg(b2); sym = __ldg(b2 + 1);
 		base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
 	}
-	o2 = base + gsa_block_count(sym, c, (int)(r2 & 63) + 1) - (uint32_t)(c == 0 && r2 >= ix.primary);
+	o2 = base + gsa_block_count(sym, c, (int)(r2 & 63) + 1) - (uint32_t)(c == 0 && r2 >= primary);
 }
 
 // BWT character of row r (0..3; the '$' row reads as 0 -- callers special-case primary)
-__device__ __forceinline__ int gsa_bwt_char(const DevIndex &ix, uint32_t r)
+template <typename I>
+__device__ __forceinline__ int gsa_bwt_char(const DevIndex &ix, I r)
 {
 	const uint32_t *w = (const uint32_t *)(ix.occ + 2 * (size_t)(r >> 6) + 1);
-	return (int)(__ldg(w + ((r & 63) >> 4)) >> ((~r & 15) << 1)) & 3;
+	return (int)(__ldg(w + ((r & 63) >> 4)) >> ((~(uint32_t)r & 15) << 1)) & 3;
+}
+
+// SA[row]; the WIDE layout keeps 6 rows per 32-byte sector: {u32 lo[6]; u8 hi[6]; u8 pad[2]}
+#define GSA_SA_GROUP 6
+template <bool W>
+__device__ __forceinline__ typename RowT<W>::t gsa_sa_read(const DevIndex &ix, typename RowT<W>::t row)
+{
+	if (!W) return __ldg((const uint32_t *)ix.sa + row);
+	const uint64_t g = (uint64_t)row / GSA_SA_GROUP; const uint32_t k = (uint32_t)((uint64_t)row - g * GSA_SA_GROUP);
+	const uint32_t *grp = (const uint32_t *)ix.sa + g * 8;
+	uint32_t lo = __ldg(grp + k), hi = (__ldg(grp + 6 + (k >> 2)) >> ((k & 3) << 3)) & 0xFFu;
+	return (typename RowT<W>::t)(((uint64_t)hi << 32) | lo);
+}
+template <bool W>
+__device__ __forceinline__ void gsa_sa_write(void *sa, typename RowT<W>::t row, typename RowT<W>::t v)
+{
+	if (!W) { ((uint32_t *)sa)[row] = (uint32_t)v; return; }
+	const uint64_t g = (uint64_t)row / GSA_SA_GROUP; const uint32_t k = (uint32_t)((uint64_t)row - g * GSA_SA_GROUP);
+	uint32_t *grp = (uint32_t *)sa + g * 8;
+	grp[k] = (uint32_t)v;
+	((uint8_t *)(grp + 6))[k] = (uint8_t)((uint64_t)v >> 32);
 }
 
 // base i of a 2-bit MSB-first packed stream
-__device__ __forceinline__ int gsa_pk_base(const uint32_t *pk, uint32_t i)
+template <typename I>
+__device__ __forceinline__ int gsa_pk_base(const uint32_t *pk, I i)
 {
-	return (int)(__ldg(pk + (i >> 4)) >> ((~i & 15) << 1)) & 3;
+	return (int)(__ldg(pk + (i >> 4)) >> ((~(uint32_t)i & 15) << 1)) & 3;
 }
 
 // 16 bases starting at base i (MSB first); the stream must be padded by one word
-__device__ __forceinline__ uint32_t gsa_pk_window(const uint32_t *pk, uint32_t i)
+template <typename I>
+__device__ __forceinline__ uint32_t gsa_pk_window(const uint32_t *pk, I i)
 {
 	uint32_t w0 = __ldg(pk + (i >> 4)), w1 = __ldg(pk + (i >> 4) + 1);
-	return __funnelshift_l(w1, w0, (i & 15) << 1);
+	return __funnelshift_l(w1, w0, ((uint32_t)i & 15) << 1);
 }
 
 // 32 flag bits starting at bit i of an MSB-first bitmap (padded by one word)
@@ -75,7 +108,7 @@ __device__ __forceinline__ uint32_t gsa_bit_window(const uint32_t *bm, uint32_t 
 
 __device__ __forceinline__ char gsa_text_char(const DevIndex &ix, int64_t pos)
 {
-	return "ACGT"[gsa_pk_base(ix.txt, (uint32_t)pos)];
+	return "ACGT"[gsa_pk_base(ix.txt, (uint64_t)pos)];
 }
 
 // ---- warp-aggregated atomics -----------------------------------------------------------------------------------

@@ -15,28 +15,35 @@
 
 // ----------------------------------------------------------------------------------------------
 // Device index.  rows 0..n of the sorted suffix matrix of T$ (T = F . revcomp(F), |T| = n = 2N).
+// Two row widths (the reference's bwtint_t is 64 bit everywhere, src/structure.h:28-38): texts below 2^32 symbols use
+// 32-bit rows and suffix-array values (NARROW), larger ones -- human-size genomes, n = 6.2e9 at config C4 -- the WIDE
+// layout.  Kernels that walk rows are compiled for both (template <bool W>, fm.cuh); everything else only addresses the
+// text and takes 64-bit positions.
 //   occ   one 32-byte block per 64 rows: {u32 cnt[4]; u32 sym[4]}.  sym holds the BWT characters of the
 //         block's rows, 2 bit each, MSB first (row 64b at bits 31..30 of sym[0]); the row whose BWT
 //         character is '$' (primary) stores 0 and is corrected at query time.  cnt[c] = number of c among
-//         rows [0, 64b) INCLUDING that placeholder.  One rank query = one 32-byte sector.
+//         rows [0, 64b) INCLUDING that placeholder (per-base counts stay below 2^32 in both widths: checked at upload).
+//         One rank query = one 32-byte sector.
 //   txt   T itself, 2 bit per base, MSB first in u32 words (16 bases per word), padded with 2 words.
-//   sa    the FULL suffix array, u32 per row (n < 2^32 in this build): sa[row] = start of the suffix.
+//   sa    the FULL suffix array: sa[row] = start of the suffix.  NARROW: u32 per row.  WIDE: 32-byte groups of 6 rows,
+//         {u32 lo[6]; u8 hi[6]; u8 pad[2]} (40-bit values, 5.33 B per row: 33 GB at n = 6.2e9) -- one sector per locate.
 //   kbits one bit per k-mer, k = min(MinSeedLength, 16): set iff the k-mer occurs in T (T is its own reverse complement).
 //         A search whose first k bases do not occur cannot yield a seed: zero index accesses for it.
 //   ktab  for every k-mer w (k = ktab_k, code = bases big-endian; when size == 1 lo is SA[row] itself): the row interval {lo, size} of
-//         revcomp(w); size 0 = w does not occur in T.
+//         revcomp(w); size 0 = w does not occur in T.  NARROW: uint2, WIDE: ulonglong2.
 // ----------------------------------------------------------------------------------------------
 struct DevIndex {
 	const uint4 *occ;
 	const uint32_t *txt;
-	const uint32_t *sa;
-	const uint2 *ktab;
+	const void *sa;
+	const void *ktab;
 	const uint32_t *kbits; // presence bitmap of the kbits_k-mers of T (bit `code`): a clear bit = the search cannot reach kbits_k bases
-	uint32_t L2[5];
-	uint32_t primary;
-	uint32_t n;        // 2N
+	uint64_t L2[5];
+	uint64_t primary;
+	uint64_t n;        // 2N
 	int ktab_k;
 	int kbits_k;
+	int wide;          // 1 = WIDE layout of sa / ktab, 64-bit rows
 };
 
 struct DevBuf {
@@ -80,6 +87,7 @@ struct gsa_ctx {
 
 	// index
 	bool have_index = false;
+	int force_wide = 0;            // gsa_set_wide_index / GSA_FORCE_WIDE: use the WIDE layout whatever the text size (tests)
 	bool shares_index = false;     // lane created by gsa_create_shared: occ/txt/sa (and possibly ktab) belong to the owner
 	DevIndex ix;
 	int64_t N = 0;                 // GenomeSize
@@ -147,6 +155,7 @@ static inline unsigned gsa_grid(int64_t n, int block) { return (unsigned)((n + b
 
 // phase entry points implemented per translation unit
 int gsa_impl_index_upload(gsa_ctx *ctx, const gsa_index_view *v);
+int gsa_impl_index_clone(gsa_ctx *dst, gsa_ctx *src);
 int gsa_impl_build_ktab(gsa_ctx *ctx, int k);
 int gsa_impl_build_kbits(gsa_ctx *ctx, int k);
 int gsa_impl_pack_query(gsa_ctx *ctx);

@@ -141,11 +141,19 @@ int main(int argc, char *argv[])
 		if (!ix.load(prefix, err)) { idx_err = "\n\nError! Please check your input! (" + err + ")\n"; return; }
 		tick("index files loaded");
 		gsa_index_view view; ix.view(&view);
-		for (int g = 0; g < n_dev; g++) {
+		// GPU 0 gets the index files and derives the HBM layout; the other GPUs receive a copy of the finished layout over
+		// NVLink (the derived structures are several times the size of the files), all of them at the same time
+		for (int g = 0; g < n_dev; g++)
 			if (gsa_create(g, &owners[g]) != 0) { idx_err = "FatalError: cannot open CUDA device " + std::to_string(g) + " (this build has no CPU path)\n"; return; }
-			if (gsa_set_params(owners[g], &prm) != 0 || gsa_index_upload(owners[g], &view) != 0) { idx_err = std::string("FatalError: ") + gsa_last_error(owners[g]) + "\n"; return; }
-		}
+		if (gsa_set_params(owners[0], &prm) != 0 || gsa_index_upload(owners[0], &view) != 0) { idx_err = std::string("FatalError: ") + gsa_last_error(owners[0]) + "\n"; return; }
 		tick("index uploaded");
+		std::vector<std::thread> cl;
+		std::vector<std::string> cl_err((size_t)n_dev);
+		for (int g = 1; g < n_dev; g++)
+			cl.emplace_back([&, g] { if (gsa_set_params(owners[g], &prm) != 0 || gsa_index_clone(owners[g], owners[0]) != 0) cl_err[(size_t)g] = gsa_last_error(owners[g]); });
+		for (auto &t : cl) t.join();
+		for (int g = 1; g < n_dev; g++) if (!cl_err[(size_t)g].empty()) { idx_err = "FatalError: " + cl_err[(size_t)g] + "\n"; return; }
+		if (n_dev > 1) tick("index replicated");
 	});
 	std::vector<QueryChr> query;
 	bool query_ok = check_input_file(o.query) && load_query_file(o.query, query);
@@ -192,9 +200,9 @@ int main(int argc, char *argv[])
 			{ std::unique_lock<std::mutex> lk(mu); if (cursor[g] >= work[g].size()) return; qi = work[g][cursor[g]++]; }
 			gsa_alignment al;
 			int rc = gsa_align_contig(c, query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al);
+			if (rc == 0) results[qi].assign(al); // the copy out of the pinned buffers runs outside the lock: slot qi is this lane's alone
 			std::unique_lock<std::mutex> lk(mu);
 			if (rc != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(c)); failed = true; }
-			else results[qi].assign(al);
 			done[qi] = 1;
 			cv.notify_all();
 		}
@@ -207,8 +215,9 @@ int main(int argc, char *argv[])
 	for (int qi = 0; qi < nq; qi++) {
 		fprintf(stderr, "\tProcess query chromsomoe: %s...\n", query[qi].name.c_str());
 		ContigResult &r = results[(size_t)qi];
-		{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[qi] != 0; }); }
-		if (failed) break;
+		bool stop;
+		{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[qi] != 0; }); stop = failed; }
+		if (stop) break;
 		int n = 0; int64_t aln_score = 0, aln_len = 0;
 		for (const gsa_block &b : r.blocks) { // src/GSAlign.cpp:529-539 (the identity filter itself ran inside gsa_fill)
 			if (b.bDup) st.dup_num++;
@@ -231,11 +240,18 @@ int main(int argc, char *argv[])
 	}
 	for (auto &t : threads) t.join();
 	tick("align + emit");
+	if (failed) { // a device or limit failure mid-run: no partial files are left behind and the exit code says so (the reference's
+		// always-0 convention covers usage errors, not an aborted run)
+		if (!o.maf.empty()) remove(o.maf.c_str());
+		if (!o.aln.empty()) remove(o.aln.c_str());
+		fflush(NULL);
+		_exit(1);
+	}
 	if (st.local_aln_num > 0)
 		fprintf(stderr, "\tAlignment#=%d (total alignment length=%lld) ANI=%.2f%%, unique alignment#=%d\n", (int)st.local_aln_num, (long long)st.total_aln_len,
 		        100 * (1.0 * st.total_matches / st.total_aln_len), (int)(st.local_aln_num - st.dup_num));
 	fprintf(stderr, "\tIt took %lld seconds for genome sequence alignment.\n", (long long)(time(NULL) - t_start));
-	if (o.vcf && !failed) {
+	if (o.vcf) {
 		fprintf(stderr, "\nGSAlign identifies %d SNVs, %d insertions, and %d deletions [%s].\n\n", st.iSNV, st.iInsertion, st.iDeletion, o.vcf_name.c_str());
 		output_variants(o, ix, st);
 	}

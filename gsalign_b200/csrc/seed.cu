@@ -18,6 +18,7 @@
 // (see seed_walk_pipe and k_seed below); all chunks of the contig are in flight together.
 #include "fm.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <stdlib.h>
 #include <algorithm>
 
 // ---- K0: 2-bit packing of the query + invalid-base bitmap -----------------------------------------
@@ -83,12 +84,21 @@ __device__ __forceinline__ void emit_seed(const SeedOut &o, unsigned long long s
 // One search (BWT_Search semantics) from `start` inside a chunk ending at `stop`; the first K bases are known to be
 // ACGT and inside the chunk.  Returns the match length; lo/size = row interval of revcomp(match); rpos = start of the
 // match in T when it is unique.
-__device__ __forceinline__ int seed_search(const DevIndex &ix, const uint32_t *__restrict__ qpk, const uint32_t *__restrict__ qinv,
-                                           uint32_t start, uint32_t stop, int K, uint32_t &lo, uint32_t &size, uint32_t &rpos)
+template <bool W>
+__device__ __forceinline__ typename RowT<W>::ktab_t ktab_read(const DevIndex &ix, uint32_t code)
 {
+	return __ldg((const typename RowT<W>::ktab_t *)ix.ktab + code);
+}
+
+template <bool W>
+__device__ __forceinline__ int seed_search(const DevIndex &ix, const uint32_t *__restrict__ qpk, const uint32_t *__restrict__ qinv,
+                                           uint32_t start, uint32_t stop, int K, typename RowT<W>::t &lo, typename RowT<W>::t &size, typename RowT<W>::t &rpos)
+{
+	typedef typename RowT<W>::t row_t;
+	const row_t n = (row_t)ix.n;
 	// 1. prefix table
 	uint32_t code = gsa_pk_window(qpk, start) >> (32 - 2 * K);
-	uint2 iv = __ldg(ix.ktab + code);
+	typename RowT<W>::ktab_t iv = ktab_read<W>(ix, code);
 	lo = iv.x; size = iv.y;
 	if (size == 0) return 0;
 	const bool lo_is_sa = size == 1; // a k-mer occurring once: the table holds its suffix-array value, not its row
@@ -98,21 +108,21 @@ __device__ __forceinline__ int seed_search(const DevIndex &ix, const uint32_t *_
 		if ((__ldg(qinv + (pos >> 5)) >> (~pos & 31)) & 1) break;
 		int c = 3 - gsa_pk_base(qpk, pos);
 		uint32_t o1, o2;
-		gsa_occ2(ix, c, lo - 1, lo + size - 1, o1, o2);
+		gsa_occ2<W>(ix, c, lo - 1, lo + size - 1, o1, o2);
 		if (o2 == o1) break;
-		lo = ix.L2[c] + o1 + 1; size = o2 - o1; pos++;
+		lo = (row_t)ix.L2[c] + o1 + 1; size = o2 - o1; pos++;
 	}
 	// 3/4. unique: locate once, then compare the 2-bit query against the 2-bit text
 	if (size == 1) {
 		uint32_t m = pos - start;
-		uint32_t p = ix.n - (lo_is_sa ? lo : __ldg(ix.sa + lo)) - m;  // start of the match in T
+		row_t p = n - (lo_is_sa ? lo : gsa_sa_read<W>(ix, lo)) - m;  // start of the match in T
 		rpos = p;
-		uint32_t tpos = p + m;
-		while (pos < stop && tpos < ix.n) {
+		row_t tpos = p + m;
+		while (pos < stop && tpos < n) {
 			uint32_t x = gsa_pk_window(qpk, pos) ^ gsa_pk_window(ix.txt, tpos);
 			uint32_t iw = gsa_bit_window(qinv, pos);
 			int ext = min(min(__clz(x) >> 1, __clz(iw)), 16);   // first mismatch / first non-ACGT
-			uint32_t lim = min(stop - pos, ix.n - tpos);
+			uint32_t lim = (uint32_t)min((row_t)(stop - pos), n - tpos);
 			if ((uint32_t)ext >= lim) { pos += lim; break; }
 			pos += ext; tpos += ext;
 			if (ext < 16) break;
@@ -138,6 +148,7 @@ __device__ __forceinline__ void vis_mark(uint32_t *vis, uint32_t a, uint32_t b)
 // lands on a start the speculative walk visited: from there on the speculative chain is the true chain.  Returns
 // UINT_MAX then (the start in `merge`), else the first chain start >= limit.  Misses advance by one position, so a run
 // of guaranteed misses (k-mer cut by a non-ACGT base or by the chunk end) is a run of consecutive starts.
+template <bool W>
 __device__ __forceinline__ uint32_t seed_walk_repair(const DevIndex &ix, const SeedArgs &A, uint32_t start, uint32_t base, uint32_t limit, uint32_t stop,
                                                      const uint32_t *vis, const SeedOut &out, uint32_t &merge)
 {
@@ -153,14 +164,14 @@ __device__ __forceinline__ uint32_t seed_walk_repair(const DevIndex &ix, const S
 			start = ns;
 			continue;
 		}
-		uint32_t lo, size, rpos = 0;
-		int len = seed_search(ix, A.qpk, A.qinv, start, stop, K, lo, size, rpos);
+		typename RowT<W>::t lo, size, rpos = 0;
+		int len = seed_search<W>(ix, A.qpk, A.qinv, start, stop, K, lo, size, rpos);
 		if (len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ) {
 			unsigned long long slot = atomicAdd(out.count, (unsigned long long)size);
 			if (size == 1) emit_seed(out, slot, (int32_t)start, (int64_t)rpos, len);
 			else
-				for (uint32_t i = 0; i < size; i++)
-					emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - __ldg(ix.sa + lo + i) - (uint32_t)len), len);
+				for (uint32_t i = 0; i < (uint32_t)size; i++)
+					emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - (uint64_t)gsa_sa_read<W>(ix, lo + i) - (uint32_t)len), len);
 			start += A.sensitive ? 5 : (uint32_t)len + 1;
 		} else start++;
 	}
@@ -202,23 +213,27 @@ struct ChunkQuery {
 };
 
 // Records every visited start of [base, limit) in vis and emits every seed it finds flagged SEED_SPEC.
+template <bool W>
 __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const SeedArgs &A, const ChunkQuery &Q, uint32_t start, uint32_t base, uint32_t limit, uint32_t stop,
                                                    uint32_t *vis, const SeedOut &out, bool active)
 {
+	typedef typename RowT<W>::t row_t;
 	const int K = ix.ktab_k, KB = ix.kbits_k, KMIN = A.min_seed_len, lane = threadIdx.x & 31;
 	const uint32_t *occw = (const uint32_t *)ix.occ;
+	const row_t n = (row_t)ix.n, primary = (row_t)ix.primary;
 	// the walk may start a little before `base` (pre-roll, see k_seed): starts below base are neither recorded nor emitted
 	auto mark = [&](uint32_t a, uint32_t b) { a = max(a, base); if (a < b) vis_mark(vis, a - base, b - base); };
 	uint32_t look = 0; // candidates of the presence lookahead in flight
 	bool retry = false; // the previous search of this lane failed: misses come in runs (two differences closer than MinSeedLength)
 	int st = (active && start < limit) ? ST_NEXT : ST_DONE;
-	uint32_t lo = 0, size = 0, pos = 0, tpos = 0, rpos = 0, r1 = 0, r2 = 0;
+	row_t lo = 0, size = 0, tpos = 0, rpos = 0, r1 = 0, r2 = 0;
+	uint32_t pos = 0;
 	int c = 0;
 	// pending loads: one register set per kind of access.  Lanes in different states issue their loads from different
 	// branches of the same trip; if two branches loaded into the same register the second would have to wait for the first
 	// (write-after-write on the warp's scoreboard) and the branches' DRAM latencies would add up again.
 	uint4 bw_s1 = make_uint4(0, 0, 0, 0), bw_s2 = bw_s1; uint32_t bw_c1 = 0, bw_c2 = 0; // rank step: symbols + count of both blocks
-	uint32_t kt_lo = 0, kt_size = 0, sa_v = 0, tx0 = 0, tx1 = 0, tx2 = 0;                  // prefix table entry, SA entry, text words
+	row_t kt_lo = 0, kt_size = 0, sa_v = 0; uint32_t tx0 = 0, tx1 = 0, tx2 = 0;            // prefix table entry, SA entry, text words
 	uint32_t pr[SEED_LOOK] = {0, 0, 0, 0, 0, 0, 0, 0};                                      // presence words
 	while (__any_sync(0xffffffffu, st != ST_DONE)) {
 		bool fin = false;
@@ -237,7 +252,7 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 			mark(start, start + min(f + 1, look));
 			start += f;
 			if (f < look) {
-				uint2 iv = __ldg(ix.ktab + (win48(w0, w1, w2, o + f) >> (32 - 2 * K)));
+				typename RowT<W>::ktab_t iv = ktab_read<W>(ix, win48(w0, w1, w2, o + f) >> (32 - 2 * K));
 				kt_lo = iv.x; kt_size = iv.y;
 				st = ST_KTAB;
 			} else st = ST_NEXT;
@@ -246,25 +261,25 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 			if (size == 0) { pos = start; fin = true; }
 			else if (size == 1) { // the table entry is the suffix-array value: straight to the text
 				pos = start + K;
-				rpos = ix.n - lo - (uint32_t)K; tpos = rpos + (uint32_t)K;
+				rpos = n - lo - (uint32_t)K; tpos = rpos + (uint32_t)K;
 				st = ST_CMP_ISSUE;
 			} else { pos = start + K; st = ST_BWD_ISSUE; }
 		} else if (st == ST_BWD) {
-			uint32_t o1 = bw_c1 + gsa_block_count(bw_s1, c, (int)(r1 & 63) + 1) - (uint32_t)(c == 0 && r1 >= ix.primary);
-			uint32_t o2 = bw_c2 + gsa_block_count(bw_s2, c, (int)(r2 & 63) + 1) - (uint32_t)(c == 0 && r2 >= ix.primary);
+			uint32_t o1 = bw_c1 + gsa_block_count(bw_s1, c, (int)(r1 & 63) + 1) - (uint32_t)(c == 0 && r1 >= primary);
+			uint32_t o2 = bw_c2 + gsa_block_count(bw_s2, c, (int)(r2 & 63) + 1) - (uint32_t)(c == 0 && r2 >= primary);
 			if (o2 == o1) st = ST_AFTER_BWD;
-			else { lo = ix.L2[c] + o1 + 1; size = o2 - o1; pos++; st = ST_BWD_ISSUE; }
+			else { lo = (row_t)ix.L2[c] + o1 + 1; size = o2 - o1; pos++; st = ST_BWD_ISSUE; }
 		} else if (st == ST_SA) {
 			uint32_t m = pos - start;
-			rpos = ix.n - sa_v - m; tpos = rpos + m;
+			rpos = n - sa_v - m; tpos = rpos + m;
 			st = ST_CMP_ISSUE;
 		} else if (st == ST_CMP) { // 32 bases per trip: the text words were loaded last trip, the query sits in L1
-			uint32_t sh = (tpos & 15) << 1;
+			uint32_t sh = ((uint32_t)tpos & 15) << 1;
 			uint32_t t0 = __funnelshift_l(tx1, tx0, sh), t1 = __funnelshift_l(tx2, tx1, sh);
 			uint32_t x0 = Q.window(pos) ^ t0, x1 = Q.window(pos + 16) ^ t1;
 			uint32_t ext = x0 ? (uint32_t)(__clz(x0) >> 1) : 16u + (uint32_t)(__clz(x1) >> 1);
 			ext = min(ext, (uint32_t)__clz(Q.inv_window(pos)));         // first non-ACGT base
-			uint32_t lim = min(stop - pos, ix.n - tpos);
+			uint32_t lim = (uint32_t)min((row_t)(stop - pos), n - tpos);
 			if (ext >= lim) { pos += lim; fin = true; }
 			else { pos += ext; tpos += ext; if (ext < 32) fin = true; else st = ST_CMP_ISSUE; }
 		}
@@ -280,11 +295,11 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 			} else st = ST_AFTER_BWD;
 		}
 		if (st == ST_AFTER_BWD) {
-			if (size == 1) { sa_v = __ldg(ix.sa + lo); st = ST_SA; }
+			if (size == 1) { sa_v = gsa_sa_read<W>(ix, lo); st = ST_SA; }
 			else fin = true;
 		}
 		if (st == ST_CMP_ISSUE) {
-			if (pos < stop && tpos < ix.n) {
+			if (pos < stop && tpos < n) {
 				const uint32_t *tw = ix.txt + (tpos >> 4);
 				tx0 = __ldg(tw); tx1 = __ldg(tw + 1); tx2 = __ldg(tw + 2);
 				st = ST_CMP;
@@ -298,7 +313,7 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 #endif
 			len = (int)(pos - start);
 			hit = len >= A.min_seed_len && size <= GSA_MAX_SEED_FREQ;
-			if (hit && start >= base) n_emit = size;
+			if (hit && start >= base) n_emit = (uint32_t)size;
 		}
 		if (__any_sync(0xffffffffu, n_emit != 0)) { // one counter update per warp: exclusive scan of the lanes' seed counts
 			uint32_t incl = n_emit;
@@ -311,8 +326,8 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 				unsigned long long slot = wbase + incl - n_emit;
 				if (size == 1) emit_seed(out, slot, (int32_t)start, (int64_t)rpos, len | SEED_SPEC);
 				else
-					for (uint32_t i = 0; i < size; i++)
-						emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - __ldg(ix.sa + lo + i) - (uint32_t)len), len | SEED_SPEC);
+					for (uint32_t i = 0; i < (uint32_t)size; i++)
+						emit_seed(out, slot + i, (int32_t)start, (int64_t)(ix.n - (uint64_t)gsa_sa_read<W>(ix, lo + i) - (uint32_t)len), len | SEED_SPEC);
 			}
 		}
 		if (fin) {
@@ -340,7 +355,7 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 				}
 				if (!retry || !ix.kbits) { // straight to the prefix table
 					mark(start, start + 1);
-					uint2 iv = __ldg(ix.ktab + (Q.window(start) >> (32 - 2 * K)));
+					typename RowT<W>::ktab_t iv = ktab_read<W>(ix, Q.window(start) >> (32 - 2 * K));
 					kt_lo = iv.x; kt_size = iv.y;
 					st = ST_KTAB;
 					break;
@@ -369,6 +384,7 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 //           entry).  From the merge point on the speculative chain IS the true chain, so the lane's speculative seeds
 //           are valid from there on and void before: the merge point goes to merge_from[] and k_seed_keys drops the rest.
 // Results are exactly the serial chain's; every search of the true chain is done once.
+template <bool W>
 __global__ void __launch_bounds__(32 * SEED_WARPS)
 k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 {
@@ -392,7 +408,7 @@ k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 	// pre-roll: start a little before the sub-chunk so that the walk has usually fallen in step with the true chain by
 	// the time it reaches `base` (chains merge at the first start they share); saves most of the serial repair walks
 	const uint32_t pre = min((uint32_t)(A.sensitive ? SEED_PREROLL_SEN : SEED_PREROLL), base - cs);
-	uint32_t spec_exit = seed_walk_pipe(ix, A, Q, base - pre, base, limit, stop, vis, out, base < limit);
+	uint32_t spec_exit = seed_walk_pipe<W>(ix, A, Q, base - pre, base, limit, stop, vis, out, base < limit);
 	__syncwarp();
 #ifdef SEED_PROFILE
 	long long t1 = clock64();
@@ -407,7 +423,7 @@ k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 #ifdef SEED_PROFILE
 				atomicAdd(&g_seed_prof[7], 1ull);
 #endif
-				ex = seed_walk_repair(ix, A, entry, base, limit, stop, vis, out, merge);
+				ex = seed_walk_repair<W>(ix, A, entry, base, limit, stop, vis, out, merge);
 				if (ex == 0xFFFFFFFFu) ex = spec_exit;
 			}
 		}
@@ -429,24 +445,36 @@ extern "C" int gsa_seed_profile(unsigned long long *out16, int reset)
 }
 #endif
 
-// sort key: ((PosDiff + 2^31) << 31) | qPos -- a strict total order on seeds, identical to CompByPosDiff
-// (reference src/ProcessCandidateAlignment.cpp:3-7).  PosDiff + 2^31 < 2^33 because |T| < 2^32 here.
+// sort key: ((PosDiff + qlen) << qbits) | qPos -- a strict total order on seeds, identical to CompByPosDiff
+// (reference src/ProcessCandidateAlignment.cpp:3-7).  0 < PosDiff + qlen <= |T| + qlen needs pdbits bits and the all-ones
+// value of that field is never a real one, so the void seeds (below) sort behind every real seed.  When pdbits + qbits
+// exceeds 64 (|T| + qlen >= 2^33 with a contig above 1 Gbp) the two fields are sorted in two stable passes instead:
+// which = 1 emits the qPos key, which = 2 the PosDiff key.
 // Raw seeds flagged SEED_SPEC count only from their sub-chunk's merge point on (see k_seed); the others get the largest
 // key, sort to the end and are dropped.  *n_valid receives the number of real seeds.
 __global__ void k_seed_keys(const int32_t *q, const int64_t *r, const int32_t *len, const uint32_t *merge_from, uint64_t *key, uint32_t *val, int64_t n,
-                            unsigned long long *n_valid)
+                            unsigned long long *n_valid, uint32_t qlen, int qbits, int which)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	bool ok = false;
 	if (i < n) {
 		uint32_t qi = (uint32_t)q[i], chunk = qi / GSA_SEED_CHUNK, sub = (qi - chunk * GSA_SEED_CHUNK) / SEED_SUB;
 		ok = !(len[i] & SEED_SPEC) || qi >= merge_from[chunk * 32 + sub];
-		uint64_t pd = (uint64_t)(r[i] - q[i] + (1ll << 31));
-		key[i] = ok ? (pd << 31) | (uint64_t)qi : ~0ull;
+		uint64_t pd = (uint64_t)(r[i] - q[i] + (int64_t)qlen);
+		uint64_t k = which == 0 ? (pd << qbits) | (uint64_t)qi : which == 1 ? (uint64_t)qi : pd;
+		key[i] = ok ? k : ~0ull;
 		val[i] = (uint32_t)i;
 	}
+	if (!n_valid) return;
 	unsigned m = __ballot_sync(0xffffffffu, ok);
 	if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
+}
+
+// second pass of the two-pass sort: the PosDiff key of the seeds in their qPos order
+__global__ void k_seed_keys2(const uint32_t *perm, const uint64_t *pdkey, uint64_t *key, int64_t n)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) key[i] = pdkey[perm[i]];
 }
 
 __global__ void k_seed_gather(const uint32_t *perm, const int32_t *q, const int64_t *r, const int32_t *l,
@@ -485,7 +513,8 @@ int gsa_impl_seed(gsa_ctx *ctx)
 			SeedArgs sa; sa.qpk = (const uint32_t *)ctx->d_qpk.p; sa.qinv = (const uint32_t *)ctx->d_qinv.p; sa.qlen = ctx->qlen; sa.nchunks = nchunks;
 			sa.qpk_words = 2 * ((ctx->qlen >> 5) + 2); sa.qinv_words = (ctx->qlen >> 5) + 2;
 			sa.min_seed_len = ctx->prm.min_seed_len; sa.sensitive = ctx->prm.sensitive;
-			k_seed<<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so, (uint32_t *)ctx->d_tmp[7].p);
+			if (ctx->ix.wide) k_seed<true><<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so, (uint32_t *)ctx->d_tmp[7].p);
+			else k_seed<false><<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so, (uint32_t *)ctx->d_tmp[7].p);
 			KERNEL_CHECK(ctx);
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
 		}
@@ -504,15 +533,36 @@ int gsa_impl_seed(gsa_ctx *ctx)
 		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[4], (size_t)nraw * 8)); // keys out
 		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[5], (size_t)nraw * 4)); // vals in
 		GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[6], (size_t)nraw * 4)); // vals out
+		uint64_t *k_in = (uint64_t *)ctx->d_tmp[3].p, *k_out = (uint64_t *)ctx->d_tmp[4].p; uint32_t *v_in = (uint32_t *)ctx->d_tmp[5].p, *v_out = (uint32_t *)ctx->d_tmp[6].p;
+		int qbits = 1, pdbits = 1;
+		while ((1ull << qbits) < (uint64_t)ctx->qlen) qbits++;
+		while ((1ull << pdbits) <= ctx->ix.n + ctx->qlen + 1) pdbits++;
+		auto sort_pairs = [&](uint64_t *ki, uint64_t *ko, uint32_t *vi, uint32_t *vo, int bits) -> int {
+			size_t tmp_bytes = 0;
+			cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ki, ko, vi, vo, nraw, 0, bits, ctx->stream);
+			GSA_TRY(gsa_ensure(ctx, ctx->d_cub, tmp_bytes));
+			CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, tmp_bytes, ki, ko, vi, vo, nraw, 0, bits, ctx->stream));
+			ctx->tm.launches += 4; // cub radix sort passes (histogram / onesweep family)
+			return GSA_OK;
+		};
+		const bool two_pass = pdbits + qbits > 64 || getenv("GSA_SEED_SORT_2PASS") != nullptr;
 		k_seed_keys<<<gsa_grid(nraw, 256), 256, 0, ctx->stream>>>((int32_t *)ctx->d_tmp[0].p, (int64_t *)ctx->d_tmp[1].p, (int32_t *)ctx->d_tmp[2].p, (const uint32_t *)ctx->d_tmp[7].p,
-		                                                         (uint64_t *)ctx->d_tmp[3].p, (uint32_t *)ctx->d_tmp[5].p, nraw, d_count + 1);
+		                                                         k_in, v_in, nraw, d_count + 1, ctx->qlen, qbits, two_pass ? 1 : 0);
 		KERNEL_CHECK(ctx);
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small.p, d_count + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
-		size_t tmp_bytes = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint64_t *)ctx->d_tmp[3].p, (uint64_t *)ctx->d_tmp[4].p, (uint32_t *)ctx->d_tmp[5].p, (uint32_t *)ctx->d_tmp[6].p, nraw, 0, 64, ctx->stream);
-		GSA_TRY(gsa_ensure(ctx, ctx->d_cub, tmp_bytes));
-		CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, tmp_bytes, (uint64_t *)ctx->d_tmp[3].p, (uint64_t *)ctx->d_tmp[4].p, (uint32_t *)ctx->d_tmp[5].p, (uint32_t *)ctx->d_tmp[6].p, nraw, 0, 64, ctx->stream));
-		ctx->tm.launches += 4; // cub radix sort passes (upsweep/scan/downsweep family)
+		if (!two_pass) GSA_TRY(sort_pairs(k_in, k_out, v_in, v_out, pdbits + qbits));
+		else { // stable LSD: by qPos first, then by PosDiff
+			GSA_TRY(sort_pairs(k_in, k_out, v_in, v_out, 32));
+			GSA_TRY(gsa_ensure(ctx, ctx->d_tmp[8], (size_t)nraw * 8));
+			uint64_t *pdk = (uint64_t *)ctx->d_tmp[8].p;
+			k_seed_keys<<<gsa_grid(nraw, 256), 256, 0, ctx->stream>>>((int32_t *)ctx->d_tmp[0].p, (int64_t *)ctx->d_tmp[1].p, (int32_t *)ctx->d_tmp[2].p, (const uint32_t *)ctx->d_tmp[7].p,
+			                                                         pdk, v_in, nraw, nullptr, ctx->qlen, qbits, 2);
+			KERNEL_CHECK(ctx);
+			k_seed_keys2<<<gsa_grid(nraw, 256), 256, 0, ctx->stream>>>(v_out, pdk, k_in, nraw);
+			KERNEL_CHECK(ctx);
+			GSA_TRY(sort_pairs(k_in, k_out, v_out, v_in, 64));
+			CUDA_TRY(ctx, cudaMemcpyAsync(v_out, v_in, (size_t)nraw * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		n = (int64_t)*(unsigned long long *)ctx->h_small.p;
 	}

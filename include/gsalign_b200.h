@@ -117,6 +117,15 @@ const char *gsa_last_error(const gsa_ctx *ctx);
  * 229-264): re-lays the index out in HBM (32-byte rank blocks, 2-bit text, full suffix array,
  * k-mer prefix table).  The view may be freed after the call returns. */
 int gsa_index_upload(gsa_ctx *ctx, const gsa_index_view *view);
+/* The device index has two row widths, like the reference's 64-bit bwtint_t (src/structure.h:28-38) allows: texts below
+ * 2^32 symbols use 32-bit rows, larger ones (human-size genomes) 64-bit rows with a 40-bit suffix array.  enable = 1
+ * forces the wide layout whatever the text size (parity tests run both); call before gsa_index_upload. */
+int gsa_set_wide_index(gsa_ctx *ctx, int enable);
+/* A replica of src's device index (derived structures included) on dst's GPU, copied GPU to GPU over NVLink instead of
+ * being uploaded and re-derived once per GPU.  dst must be a context created with gsa_create on another device. */
+int gsa_index_clone(gsa_ctx *dst, gsa_ctx *src);
+/* bytes of HBM the index of this context occupies (rank blocks + text + suffix array + prefix table + presence bits) */
+int64_t gsa_index_bytes(const gsa_ctx *ctx);
 int gsa_set_params(gsa_ctx *ctx, const gsa_params *prm);
 /* run on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g. to time with the caller's events */
 int gsa_set_stream(gsa_ctx *ctx, void *cuda_stream);

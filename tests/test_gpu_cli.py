@@ -24,8 +24,9 @@ def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
-def run(exe, cwd, args):
-    subprocess.run([exe] + args, cwd=cwd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+def run(exe, cwd, args, env=None):
+    e = dict(os.environ, **env) if env else None
+    subprocess.run([exe] + args, cwd=cwd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=e)
 
 
 def test_ecoli_golden_md5(ecoli, workdir):
@@ -81,20 +82,34 @@ def test_multi_gpu_flag_same_bytes(workdir):
             assert filecmp.cmp(os.path.join(d, f"g1.{ext}"), os.path.join(d, f"{other}.{ext}"), shallow=False), (other, ext)
 
 
-def _index_equal(d, fasta):
-    run(REF_INDEX, d, [fasta, "ri"])
-    run(OUR_INDEX, d, [fasta, "oi"])
+def _index_equal(d, fasta, block=None):
+    """block: None = the prefix-doubling sorter (texts < 2^31 symbols); a number = the blockwise sorter every larger text
+    takes, forced here with at most that many suffixes per block (GSA_INDEX_BLOCK)"""
+    if not os.path.exists(os.path.join(d, "ri.sa")):
+        run(REF_INDEX, d, [fasta, "ri"])
+    run(OUR_INDEX, d, [fasta, "oi"], env={"GSA_INDEX_BLOCK": str(block)} if block else None)
     for ext in ("pac", "ann", "amb", "bwt", "sa"):
         assert filecmp.cmp(os.path.join(d, "ri." + ext), os.path.join(d, "oi." + ext), shallow=False), ext
+        os.remove(os.path.join(d, "oi." + ext))
 
 
-def test_index_builder_bytes_ecoli(ecoli):
+@pytest.mark.parametrize("block", [None, 300_000, 1 << 30], ids=["doubling", "blocks300k", "oneblock"])
+def test_index_builder_bytes_ecoli(ecoli, block):
     if not os.path.exists(REF_INDEX):
         pytest.skip("oracle/_ref/bwt_index not built")
-    _index_equal(ecoli["dir"], "ecoli.fa")
+    _index_equal(ecoli["dir"], "ecoli.fa", block)
 
 
-def test_index_builder_bytes_adversarial(workdir):
+def test_wide_rows_cli_same_bytes(ecoli):
+    """GSA_FORCE_WIDE=1: the 64-bit row layout of the device index (what a human-size reference gets) through the whole CLI"""
+    cwd = os.path.dirname(ecoli["dir"])
+    run(OURS, cwd, ["-t", "4", "-i", "test/ecoli", "-q", "test/ecoli.mut", "-o", "test/wide"], env={"GSA_FORCE_WIDE": "1", "GSA_SEED_SORT_2PASS": "1"})
+    assert md5(os.path.join(ecoli["dir"], "wide.maf")) == ECOLI_MD5["maf"]
+    assert md5(os.path.join(ecoli["dir"], "wide.vcf")) == ECOLI_MD5["vcf"]
+
+
+@pytest.mark.parametrize("block", [None, 4_000], ids=["doubling", "blocks4k"])
+def test_index_builder_bytes_adversarial(workdir, block):
     """N runs, IUPAC codes, lower case, comments, CRLF, long exact repeats, tiny contigs"""
     if not os.path.exists(REF_INDEX):
         pytest.skip("oracle/_ref/bwt_index not built")
@@ -114,4 +129,4 @@ def test_index_builder_bytes_adversarial(workdir):
             for i in range(0, len(s), 61):
                 f.write(bytes(s[i:i + 61]) + eol)
             f.write(b"\n")
-    _index_equal(d, "adv.fa")
+    _index_equal(d, "adv.fa", block)

@@ -74,9 +74,10 @@ def ecoli_ref(ecoli, workdir):
     return run_reference(ecoli["prefix"], ecoli["query_path"], os.path.join(workdir, "ecoli_ref.pkl"))
 
 
-def test_ecoli_all_seams(ecoli, ecoli_ref):
+@pytest.mark.parametrize("wide", [False, True], ids=["rows32", "rows64"])
+def test_ecoli_all_seams(ecoli, ecoli_ref, wide):
     from gsalign_b200 import capi
-    a = capi.Aligner(0)
+    a = capi.Aligner(0, wide=wide)
     a.upload_index(ecoli["index"])
     a.lib.gsa_set_dump(a.ctx, 1)
     assert check_contig(a, ecoli["query"], ecoli_ref[0]) == 1
@@ -110,15 +111,21 @@ def make_rearranged(workdir, seed=7, n=600_000):
     return d
 
 
+@pytest.mark.parametrize("wide", [False, True], ids=["rows32", "rows64"])
 @pytest.mark.parametrize("prm", [dict(), dict(min_seed_len=10, sensitive=1, min_block_score=50)])
-def test_rearranged_all_seams(workdir, prm):
+def test_rearranged_all_seams(workdir, prm, wide):
     from conftest import build_index
     from gsalign_b200 import bwaidx, capi, synth
     d = make_rearranged(workdir)
     build_index(os.path.join(d, "ref.fa"), os.path.join(d, "ref"))
     tag = "sen" if prm else "def"
-    ref = run_reference(os.path.join(d, "ref"), os.path.join(d, "qry.fa"), os.path.join(d, f"ref_{tag}.pkl"), **prm)
-    a = capi.Aligner(0)
+    pkl = os.path.join(d, f"ref_{tag}.pkl")
+    if os.path.exists(pkl):
+        with open(pkl, "rb") as f:
+            ref = pickle.load(f)
+    else:
+        ref = run_reference(os.path.join(d, "ref"), os.path.join(d, "qry.fa"), pkl, **prm)
+    a = capi.Aligner(0, wide=wide)
     a.upload_index(bwaidx.load(os.path.join(d, "ref")))
     a.lib.gsa_set_dump(a.ctx, 1)
     cprm = dict(prm)

@@ -7,10 +7,11 @@ import orc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def aligner(ecoli):
+@pytest.fixture(scope="module", params=[False, True], ids=["rows32", "rows64"])
+def aligner(ecoli, request):
+    """both row widths of the device index: 32-bit rows (texts < 2^32 symbols) and the 64-bit layout human-size texts use"""
     from gsalign_b200 import capi
-    a = capi.Aligner(0)
+    a = capi.Aligner(0, wide=request.param)
     a.upload_index(ecoli["index"])
     yield a
     a.close()
