@@ -56,7 +56,7 @@ class Timing(C.Structure):
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
            "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device", "gsa_set_host_results", "gsa_dp_batch_identity",
-           "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes"]
+           "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes", "gsa_index_selfcheck"]
 
 
 def load_library() -> C.CDLL:
@@ -105,6 +105,11 @@ class Aligner:
     def clone_index_from(self, src: "Aligner"):
         """replica of src's device index on this context's GPU, copied GPU to GPU (gsa_index_clone)"""
         self._chk(self.lib.gsa_index_clone(self.ctx, src.ctx))
+
+    def index_selfcheck(self, n_samples: int = 1 << 20) -> int:
+        bad = C.c_int64()
+        self._chk(self.lib.gsa_index_selfcheck(self.ctx, C.c_int64(n_samples), C.byref(bad)))
+        return bad.value
 
     def index_bytes(self) -> int:
         return int(self.lib.gsa_index_bytes(self.ctx))

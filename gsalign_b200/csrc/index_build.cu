@@ -411,6 +411,13 @@ __global__ void k_ibw_emit(const uint32_t *txt, const uint64_t *pos, uint32_t m,
 	if (v) atomicOr(brow + w, v);
 }
 
+// row 0 is the suffix "$" (SA = n): its BWT character is the last base of the text
+__global__ void k_ibw_row0(const uint32_t *txt, uint64_t n, uint32_t *brow)
+{
+	const uint64_t p = n - 1;
+	brow[0] |= ((txt[p >> 4] >> ((~(uint32_t)p & 15) << 1)) & 3u) << 30;
+}
+
 // the '$'-less BWT in the BWA layout: symbol x = character of row x + (x >= primary); one thread per 128-symbol block
 // writes its 8 words in place and its per-base counts
 __global__ void k_ibw_bwt_block(const uint32_t *brow, uint64_t n, uint64_t primary, uint32_t *out, unsigned long long *cnt, uint64_t nblk)
@@ -574,6 +581,8 @@ static int build_blockwise(const uint8_t *h_pac, int64_t N, uint64_t cap, std::v
 		row_base += m;
 		bin = hi;
 	}
+	k_ibw_row0<<<1, 1>>>(txt, n, brow);
+	IB_LAUNCH_CHECK();
 	IB_CHECK(cudaDeviceSynchronize());
 	if (row_base != n + 1) { fprintf(stderr, "[gsa_index] internal error: %llu rows sorted, expected %llu\n", (unsigned long long)row_base, (unsigned long long)(n + 1)); return -2; }
 	unsigned long long primary = 0;

@@ -265,3 +265,53 @@ int gsa_impl_index_clone(gsa_ctx *dst, gsa_ctx *src)
 	dst->have_index = true;
 	return GSA_OK;
 }
+
+// ---- self-check of the device index (debug hook; used on texts too large for the reference's indexer to cross-check) ------
+// For pseudo-random rows r: (1) suffix SA[r] sorts before suffix SA[r+1] (direct text comparison, '$' smallest),
+// (2) the BWT character stored for r is T[SA[r] - 1], (3) SA[LF(r)] = SA[r] - 1 (rank counts + L2 + SA agree).
+template <bool W>
+__global__ void k_index_selfcheck(DevIndex ix, uint64_t n_samples, unsigned long long *bad)
+{
+	typedef typename RowT<W>::t row_t;
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_samples) return;
+	uint64_t h = (i + 1) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+	const row_t r = (row_t)(h % ix.n);                 // rows 0 .. n-1, so r + 1 exists
+	const uint64_t a = gsa_sa_read<W>(ix, r), b = gsa_sa_read<W>(ix, r + 1);
+	unsigned fail = 0;
+	if (a > ix.n || b >= ix.n || a == b) fail |= 1;
+	else {
+		for (uint64_t k = 0; k < 4096; k++) {
+			if (a + k >= ix.n) break;                    // a ran into '$' first: smaller, fine
+			if (b + k >= ix.n) { fail |= 2; break; }
+			int ca = gsa_pk_base(ix.txt, a + k), cb = gsa_pk_base(ix.txt, b + k);
+			if (ca != cb) { if (ca > cb) fail |= 2; break; }
+		}
+		if (a > 0 && r != (row_t)ix.primary) {
+			int c = gsa_bwt_char(ix, r);
+			if (c != gsa_pk_base(ix.txt, a - 1)) fail |= 4;
+			row_t lf = (row_t)ix.L2[c] + gsa_occ<W>(ix, c, r);
+			if ((uint64_t)gsa_sa_read<W>(ix, lf) != a - 1) fail |= 8;
+		}
+		if ((a == 0) != (r == (row_t)ix.primary)) fail |= 16;
+	}
+	if (fail) atomicAdd(bad, 1ull);
+}
+
+extern "C" int gsa_index_selfcheck(gsa_ctx *ctx, int64_t n_samples, int64_t *n_bad)
+{
+	if (!ctx || !n_bad || n_samples <= 0) return GSA_ERR_ARG;
+	if (!ctx->have_index) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_index_selfcheck: no index");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_counter, 1024));
+	unsigned long long *d_bad = (unsigned long long *)ctx->d_counter.p + 100;
+	CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, 8, ctx->stream));
+	if (ctx->ix.wide) k_index_selfcheck<true><<<gsa_grid(n_samples, 256), 256, 0, ctx->stream>>>(ctx->ix, (uint64_t)n_samples, d_bad);
+	else k_index_selfcheck<false><<<gsa_grid(n_samples, 256), 256, 0, ctx->stream>>>(ctx->ix, (uint64_t)n_samples, d_bad);
+	KERNEL_CHECK(ctx);
+	unsigned long long h = 0;
+	CUDA_TRY(ctx, cudaMemcpyAsync(&h, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	*n_bad = (int64_t)h;
+	return GSA_OK;
+}

@@ -177,6 +177,11 @@ int gsa_fetch_seeds(gsa_ctx *ctx, int32_t *qPos, int64_t *rPos, int32_t *len);
  * Pass out = NULL to get the length in int64 words. */
 int64_t gsa_dump_blocks(gsa_ctx *ctx, int32_t stage, int64_t *out);
 
+/* Debug hook: checks n_samples pseudo-random rows of the uploaded device index for internal consistency (suffix order of
+ * neighbouring rows by direct text comparison, BWT character = T[SA-1], SA[LF(row)] = SA[row]-1); *n_bad = violations.
+ * Validates an index whose text is too large for the reference's own indexer to cross-check in test time. */
+int gsa_index_selfcheck(gsa_ctx *ctx, int64_t n_samples, int64_t *n_bad);
+
 /* Stand-alone batch of global alignments through K3's DP kernel (ksw2_alignment semantics):
  * pair i aligns ref[ref_off[i] .. ref_off[i+1]) with qry[qry_off[i] .. qry_off[i+1]); rows are written
  * to out1/out2 at out_off[i] = ref_off[i] + qry_off[i], lengths to out_len.  Host pointers. */
