@@ -56,7 +56,10 @@ class Timing(C.Structure):
 EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "gsa_set_params", "gsa_default_params",
            "gsa_contig_begin", "gsa_contig_begin_device", "gsa_seed", "gsa_cluster", "gsa_fill", "gsa_align_contig",
            "gsa_get_timing", "gsa_fetch_seeds", "gsa_dump_blocks", "gsa_dp_batch", "gsa_set_stream", "gsa_set_dump", "gsa_dpx_peak", "gsa_create_shared", "gsa_result_device", "gsa_set_host_results", "gsa_dp_batch_identity",
-           "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes", "gsa_index_selfcheck"]
+           "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes", "gsa_index_selfcheck",
+           "gsa_comm_unique_id", "gsa_comm_init_rank", "gsa_comm_init_all", "gsa_comm_destroy", "gsa_outbox_reset", "gsa_outbox_reserve",
+           "gsa_outbox_append", "gsa_outbox_bytes", "gsa_gather_records", "gsa_gather_records_all", "gsa_gather_wait", "gsa_inbox_device",
+           "gsa_inbox_host", "gsa_record_next"]
 
 
 def load_library() -> C.CDLL:
@@ -67,6 +70,7 @@ def load_library() -> C.CDLL:
     lib.gsa_last_error.restype = C.c_char_p
     lib.gsa_dump_blocks.restype = C.c_int64
     lib.gsa_index_bytes.restype = C.c_int64
+    lib.gsa_outbox_bytes.restype = C.c_int64
     return lib
 
 
@@ -219,6 +223,50 @@ class Aligner:
         al = Alignment()
         self._chk(self.lib.gsa_result_device(self.ctx, C.byref(al)))
         return al
+
+    # ---- multi-GPU record gather (gather.cu) ----------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().gsa_comm_unique_id(buf, C.c_int32(128))
+        if rc != 0:
+            raise GsaError(f"gsa_comm_unique_id failed with {rc} (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init_rank(self, uid: bytes, rank: int, n_ranks: int):
+        self._chk(self.lib.gsa_comm_init_rank(self.ctx, C.c_char_p(uid), C.c_int32(rank), C.c_int32(n_ranks)))
+
+    def outbox_reset(self):
+        self._chk(self.lib.gsa_outbox_reset(self.ctx))
+
+    def outbox_append(self, lane: "Aligner", contig: int):
+        rc = self.lib.gsa_outbox_append(self.ctx, lane.ctx, C.c_int64(contig))
+        if rc != 0:
+            raise GsaError(f"gsa_outbox_append failed with {rc}: {self.lib.gsa_last_error(lane.ctx).decode()} / {self.lib.gsa_last_error(self.ctx).decode()}")
+
+    def outbox_bytes(self) -> int:
+        return int(self.lib.gsa_outbox_bytes(self.ctx))
+
+    def gather_records(self, root: int = 0):
+        self._chk(self.lib.gsa_gather_records(self.ctx, C.c_int32(root)))
+
+    def gather_wait(self):
+        self._chk(self.lib.gsa_gather_wait(self.ctx))
+
+    def inbox_records(self, rank: int):
+        """on the root after gather_records + gather_wait: the records of `rank` as a list of
+        (contig, blocks, frags, aln1, aln2) numpy copies"""
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._chk(self.lib.gsa_inbox_host(self.ctx, C.c_int32(rank), C.byref(ptr), C.byref(nbytes)))
+        out, off, contig, al = [], C.c_int64(0), C.c_int64(), Alignment()
+        while True:
+            rc = self.lib.gsa_record_next(ptr, nbytes, C.byref(off), C.byref(contig), C.byref(al))
+            if rc < 0:
+                raise GsaError("malformed outbox image")
+            if rc == 0:
+                break
+            out.append((contig.value,) + self._alignment(al))
+        return out
 
     def timing(self) -> Timing:
         t = Timing()

@@ -108,7 +108,14 @@ void gsa_destroy(gsa_ctx *ctx)
 	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	for (DevBuf &b : ctx->d_tmp) if (b.p) cudaFree(b.p);
-	HostBuf *hb[] = {&ctx->h_small, &ctx->h_stage, &ctx->h_frag, &ctx->h_aln1, &ctx->h_aln2, &ctx->h_blocks};
+	gsa_comm_destroy(ctx);
+	DevBuf *gb[] = {&ctx->d_outbox, &ctx->d_sizes};
+	for (DevBuf *b : gb) if (b->p) cudaFree(b->p);
+	for (DevBuf &b : ctx->d_inbox) if (b.p) cudaFree(b.p);
+	if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);
+	if (ctx->ev_outbox) cudaEventDestroy(ctx->ev_outbox);
+	if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+	HostBuf *hb[] = {&ctx->h_small, &ctx->h_stage, &ctx->h_frag, &ctx->h_aln1, &ctx->h_aln2, &ctx->h_blocks, &ctx->h_inbox, &ctx->h_rec};
 	for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
 	for (int i = 0; i < 12; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);

@@ -1,0 +1,330 @@
+// gather.cu -- the one collective of the path: finished alignment records of every GPU are packed
+// into a per-GPU outbox in HBM and gathered to the root GPU with grouped ncclSend / ncclRecv over NVLink; the root
+// owns the emitters (reference: the append-only tail of the contig loop, src/GSAlign.cpp:523-548).  Nothing else
+// crosses GPUs.  Two ways to build the communicator: one process per GPU (a 128-byte ncclUniqueId handed round by
+// the host however it likes: gsa_comm_init_rank) or one process driving all GPUs (bin/GSAlign -gpus N:
+// gsa_comm_init_all).
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2): the library loads -- and the single-GPU path runs -- where NCCL is
+// absent, and inside a process that already holds a libnccl (PyTorch bundles its own) the same copy is used.
+//
+// Outbox image of one GPU (little-endian, sections padded to 16 bytes), one record per finished contig:
+//     int64[4]   {contig index, n_blocks, n_frags, aln_bytes}
+//     gsa_block[n_blocks]  gsa_frag[n_frags]  aln1[aln_bytes]  aln2[aln_bytes]
+#include "gsa_internal.cuh"
+#include <dlfcn.h>
+#include <string.h>
+#include <mutex>
+
+// ---- the few NCCL entry points used, bound by name -------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;   // ncclSuccess = 0
+enum { NCCL_UINT8 = 1, NCCL_INT64 = 4 }; // ncclDataType_t values (nccl.h): ncclUint8 = 1, ncclInt64 = 4
+
+struct NcclApi {
+	void *h = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	std::string err;
+};
+
+static NcclApi *nccl_api()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		const char *names[] = {"libnccl.so.2", "libnccl.so"};
+		for (const char *n : names) if ((api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+		if (!api.h) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+#define BIND(field, sym) do { *(void **)(&api.field) = dlsym(api.h, sym); if (!api.field) { api.err = std::string("libnccl lacks ") + sym; return; } } while (0)
+		BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommInitAll, "ncclCommInitAll");
+		BIND(CommDestroy, "ncclCommDestroy"); BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd");
+		BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv"); BIND(AllGather, "ncclAllGather"); BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+	});
+	return &api;
+}
+
+#define NCCL_TRY(ctx, api, call)                                                                                   \
+	do {                                                                                                           \
+		ncclResult_t _r = (call);                                                                                  \
+		if (_r != 0) return gsa_fail((ctx), GSA_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, (api)->GetErrorString(_r)); \
+	} while (0)
+
+static inline int64_t pad16(int64_t n) { return (n + 15) & ~(int64_t)15; }
+static const int64_t REC_HDR = 32;
+
+static int comm_common_init(gsa_ctx *ctx)
+{
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if (!ctx->comm_stream) {
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi); // the gather must not queue behind the lanes' compute kernels
+		CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+	}
+	if (!ctx->ev_gather) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_sizes, 16 * 1024));
+	return GSA_OK;
+}
+
+extern "C" {
+
+int gsa_comm_unique_id(void *id, int32_t id_bytes)
+{
+	NcclApi *api = nccl_api();
+	if (!api->err.empty()) { fprintf(stderr, "gsalign_b200: %s\n", api->err.c_str()); return GSA_ERR_CUDA; }
+	if (!id || id_bytes < (int32_t)sizeof(ncclUniqueId)) return GSA_ERR_ARG;
+	ncclUniqueId u;
+	if (api->GetUniqueId(&u) != 0) return GSA_ERR_CUDA;
+	memcpy(id, &u, sizeof(u));
+	return GSA_OK;
+}
+
+int gsa_comm_init_rank(gsa_ctx *ctx, const void *id, int32_t rank, int32_t n_ranks)
+{
+	if (!ctx || !id || rank < 0 || rank >= n_ranks || n_ranks > 1024) return GSA_ERR_ARG;
+	NcclApi *api = nccl_api();
+	if (!api->err.empty()) return gsa_fail(ctx, GSA_ERR_CUDA, "%s", api->err.c_str());
+	GSA_TRY(comm_common_init(ctx));
+	ncclUniqueId u; memcpy(&u, id, sizeof(u));
+	ncclComm_t c = nullptr;
+	NCCL_TRY(ctx, api, api->CommInitRank(&c, n_ranks, u, rank));
+	ctx->nccl_comm = c; ctx->comm_rank = rank; ctx->comm_size = n_ranks;
+	return GSA_OK;
+}
+
+int gsa_comm_init_all(gsa_ctx *const *ctxs, int32_t n)
+{
+	if (!ctxs || n < 1 || n > 64) return GSA_ERR_ARG;
+	NcclApi *api = nccl_api();
+	if (!api->err.empty()) return gsa_fail(ctxs[0], GSA_ERR_CUDA, "%s", api->err.c_str());
+	int devs[64]; ncclComm_t comms[64];
+	for (int i = 0; i < n; i++) { if (!ctxs[i]) return GSA_ERR_ARG; devs[i] = ctxs[i]->device; GSA_TRY(comm_common_init(ctxs[i])); }
+	NCCL_TRY(ctxs[0], api, api->CommInitAll(comms, n, devs));
+	for (int i = 0; i < n; i++) { ctxs[i]->nccl_comm = comms[i]; ctxs[i]->comm_rank = i; ctxs[i]->comm_size = n; }
+	return GSA_OK;
+}
+
+int gsa_comm_destroy(gsa_ctx *ctx)
+{
+	if (!ctx) return GSA_ERR_ARG;
+	if (ctx->nccl_comm) { cudaSetDevice(ctx->device); nccl_api()->CommDestroy((ncclComm_t)ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+	return GSA_OK;
+}
+
+int gsa_outbox_reset(gsa_ctx *owner)
+{
+	if (!owner) return GSA_ERR_ARG;
+	std::lock_guard<std::mutex> lk(owner->outbox_mu);
+	owner->outbox_used = 0;
+	return GSA_OK;
+}
+
+int64_t gsa_outbox_bytes(gsa_ctx *owner)
+{
+	if (!owner) return 0;
+	std::lock_guard<std::mutex> lk(owner->outbox_mu);
+	return owner->outbox_used;
+}
+
+int gsa_outbox_reserve(gsa_ctx *owner, int64_t bytes)
+{
+	if (!owner || bytes < 0) return GSA_ERR_ARG;
+	std::lock_guard<std::mutex> lk(owner->outbox_mu);
+	if (owner->outbox_used != 0) return gsa_fail(owner, GSA_ERR_ARG, "gsa_outbox_reserve: outbox in use");
+	CUDA_TRY(owner, cudaSetDevice(owner->device));
+	return gsa_ensure(owner, owner->d_outbox, (size_t)bytes + 64);
+}
+
+// Packs the result of the last gsa_fill() of `lane` (a context on the owner's GPU, possibly the owner itself) into the
+// owner's outbox, asynchronously on the lane's stream: fragments and rows are copied device to device, the O(#blocks)
+// headers come from the host.
+int gsa_outbox_append(gsa_ctx *owner, gsa_ctx *lane, int64_t contig)
+{
+	if (!owner || !lane || owner->device != lane->device) return GSA_ERR_ARG;
+	if (!lane->have_cluster) return gsa_fail(lane, GSA_ERR_ARG, "gsa_outbox_append: call gsa_fill first");
+	CUDA_TRY(lane, cudaSetDevice(lane->device));
+	const int64_t nb = (int64_t)lane->out_blocks.size(), nf = nb ? lane->n_frags : 0, ab = nb ? lane->aln_bytes : 0;
+	const int64_t need = REC_HDR + pad16(nb * (int64_t)sizeof(gsa_block)) + pad16(nf * (int64_t)sizeof(gsa_frag)) + 2 * pad16(ab);
+	int64_t off;
+	{
+		std::lock_guard<std::mutex> lk(owner->outbox_mu);
+		if ((size_t)(owner->outbox_used + need) > owner->d_outbox.cap) {
+			// grow: wait for the copies in flight, move the image (rare: capacities are remembered across steps)
+			for (cudaEvent_t e : owner->outbox_pending) CUDA_TRY(owner, cudaEventSynchronize(e));
+			DevBuf bigger;
+			GSA_TRY(gsa_ensure(owner, bigger, (size_t)(2 * (owner->outbox_used + need)) + (64u << 20)));
+			if (owner->outbox_used) CUDA_TRY(owner, cudaMemcpy(bigger.p, owner->d_outbox.p, (size_t)owner->outbox_used, cudaMemcpyDeviceToDevice));
+			if (owner->d_outbox.p) CUDA_TRY(owner, cudaFree(owner->d_outbox.p));
+			owner->d_outbox = bigger;
+		}
+		off = owner->outbox_used;
+		owner->outbox_used += need;
+		if (!lane->ev_outbox) CUDA_TRY(lane, cudaEventCreateWithFlags(&lane->ev_outbox, cudaEventDisableTiming));
+		bool known = false;
+		for (cudaEvent_t e : owner->outbox_pending) known |= e == lane->ev_outbox;
+		if (!known) owner->outbox_pending.push_back(lane->ev_outbox);
+	}
+	char *dst = (char *)owner->d_outbox.p + off;
+	if (owner->ev_gather) CUDA_TRY(lane, cudaStreamWaitEvent(lane->stream, owner->ev_gather, 0)); // the previous gather has left the outbox
+	// header + block headers travel in one small pinned staging block of the lane
+	const size_t hb = (size_t)(REC_HDR + nb * (int64_t)sizeof(gsa_block));
+	GSA_TRY(gsa_ensure_host(lane, lane->h_rec, hb));
+	int64_t *hdr = (int64_t *)lane->h_rec.p;
+	hdr[0] = contig; hdr[1] = nb; hdr[2] = nf; hdr[3] = ab;
+	if (nb) memcpy((char *)lane->h_rec.p + REC_HDR, lane->out_blocks.data(), (size_t)nb * sizeof(gsa_block));
+	CUDA_TRY(lane, cudaMemcpyAsync(dst, lane->h_rec.p, hb, cudaMemcpyHostToDevice, lane->stream));
+	char *p = dst + REC_HDR + pad16(nb * (int64_t)sizeof(gsa_block));
+	if (nf) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_frag.p, (size_t)nf * sizeof(gsa_frag), cudaMemcpyDeviceToDevice, lane->stream));
+	p += pad16(nf * (int64_t)sizeof(gsa_frag));
+	if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln1.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
+	p += pad16(ab);
+	if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln2.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
+	CUDA_TRY(lane, cudaEventRecord(lane->ev_outbox, lane->stream));
+	// the staging block is reused by the next append of this lane: the H2D above must have left it
+	CUDA_TRY(lane, cudaEventSynchronize(lane->ev_outbox));
+	return GSA_OK;
+}
+
+// the communication stream waits for every lane's last append
+static int outbox_join(gsa_ctx *owner)
+{
+	std::lock_guard<std::mutex> lk(owner->outbox_mu);
+	for (cudaEvent_t e : owner->outbox_pending) CUDA_TRY(owner, cudaStreamWaitEvent(owner->comm_stream, e, 0));
+	return GSA_OK;
+}
+
+static int ensure_inbox(gsa_ctx *root, int n)
+{
+	if ((int)root->d_inbox.size() < n) { root->d_inbox.resize((size_t)n); root->inbox_bytes.resize((size_t)n, 0); }
+	return GSA_OK;
+}
+
+// One process per GPU: every rank calls this once per job.  The outbox fill levels travel first (one 8-byte all-gather,
+// read back on the communication stream only: the lanes' streams are never drained), then one grouped send/recv batch
+// moves the images to the root.
+int gsa_gather_records(gsa_ctx *owner, int32_t root)
+{
+	if (!owner) return GSA_ERR_ARG;
+	if (!owner->nccl_comm) return gsa_fail(owner, GSA_ERR_ARG, "gsa_gather_records: call gsa_comm_init_rank first");
+	NcclApi *api = nccl_api();
+	CUDA_TRY(owner, cudaSetDevice(owner->device));
+	const int n = owner->comm_size, me = owner->comm_rank;
+	if (root < 0 || root >= n) return GSA_ERR_ARG;
+	GSA_TRY(outbox_join(owner));
+	int64_t *d_sz = (int64_t *)owner->d_sizes.p;     // [0] = mine, [8 ..] = everybody's
+	int64_t *h_sz = (int64_t *)owner->h_small.p + 4096;
+	h_sz[0] = gsa_outbox_bytes(owner);
+	CUDA_TRY(owner, cudaMemcpyAsync(d_sz, h_sz, 8, cudaMemcpyHostToDevice, owner->comm_stream));
+	NCCL_TRY(owner, api, api->AllGather(d_sz, d_sz + 8, 1, NCCL_INT64, (ncclComm_t)owner->nccl_comm, owner->comm_stream));
+	CUDA_TRY(owner, cudaMemcpyAsync(h_sz + 8, d_sz + 8, (size_t)n * 8, cudaMemcpyDeviceToHost, owner->comm_stream));
+	CUDA_TRY(owner, cudaStreamSynchronize(owner->comm_stream));
+	if (me == root) {
+		GSA_TRY(ensure_inbox(owner, n));
+		for (int r = 0; r < n; r++) {
+			owner->inbox_bytes[(size_t)r] = h_sz[8 + r];
+			if (r != root && h_sz[8 + r] > 0) GSA_TRY(gsa_ensure(owner, owner->d_inbox[(size_t)r], (size_t)h_sz[8 + r]));
+		}
+		NCCL_TRY(owner, api, api->GroupStart());
+		for (int r = 0; r < n; r++)
+			if (r != root && h_sz[8 + r] > 0) NCCL_TRY(owner, api, api->Recv(owner->d_inbox[(size_t)r].p, (size_t)h_sz[8 + r], NCCL_UINT8, r, (ncclComm_t)owner->nccl_comm, owner->comm_stream));
+		NCCL_TRY(owner, api, api->GroupEnd());
+	} else if (h_sz[8 + me] > 0) {
+		NCCL_TRY(owner, api, api->Send(owner->d_outbox.p, (size_t)h_sz[8 + me], NCCL_UINT8, root, (ncclComm_t)owner->nccl_comm, owner->comm_stream));
+	}
+	CUDA_TRY(owner, cudaEventRecord(owner->ev_gather, owner->comm_stream)); // gsa_gather_wait / the next step's appends order after it
+	return GSA_OK;
+}
+
+// One process driving all GPUs: the same exchange issued for every rank inside one NCCL group (sizes are known on the host).
+int gsa_gather_records_all(gsa_ctx *const *ctxs, int32_t n, int32_t root)
+{
+	if (!ctxs || n < 1 || root < 0 || root >= n) return GSA_ERR_ARG;
+	NcclApi *api = nccl_api();
+	gsa_ctx *R = ctxs[root];
+	if (!R->nccl_comm) return gsa_fail(R, GSA_ERR_ARG, "gsa_gather_records_all: call gsa_comm_init_all first");
+	GSA_TRY(ensure_inbox(R, n));
+	for (int r = 0; r < n; r++) {
+		CUDA_TRY(ctxs[r], cudaSetDevice(ctxs[r]->device));
+		GSA_TRY(outbox_join(ctxs[r]));
+		R->inbox_bytes[(size_t)r] = gsa_outbox_bytes(ctxs[r]);
+	}
+	CUDA_TRY(R, cudaSetDevice(R->device));
+	for (int r = 0; r < n; r++) if (r != root && R->inbox_bytes[(size_t)r] > 0) GSA_TRY(gsa_ensure(R, R->d_inbox[(size_t)r], (size_t)R->inbox_bytes[(size_t)r]));
+	NCCL_TRY(R, api, api->GroupStart());
+	for (int r = 0; r < n; r++) {
+		const size_t b = (size_t)R->inbox_bytes[(size_t)r];
+		if (r == root || b == 0) continue;
+		NCCL_TRY(R, api, api->Send(ctxs[r]->d_outbox.p, b, NCCL_UINT8, root, (ncclComm_t)ctxs[r]->nccl_comm, ctxs[r]->comm_stream));
+		NCCL_TRY(R, api, api->Recv(R->d_inbox[(size_t)r].p, b, NCCL_UINT8, r, (ncclComm_t)R->nccl_comm, R->comm_stream));
+	}
+	NCCL_TRY(R, api, api->GroupEnd());
+	for (int r = 0; r < n; r++) { CUDA_TRY(ctxs[r], cudaSetDevice(ctxs[r]->device)); CUDA_TRY(ctxs[r], cudaEventRecord(ctxs[r]->ev_gather, ctxs[r]->comm_stream)); }
+	return GSA_OK;
+}
+
+// blocks the host until this rank's part of the last gather has run
+int gsa_gather_wait(gsa_ctx *owner)
+{
+	if (!owner || !owner->comm_stream) return GSA_ERR_ARG;
+	CUDA_TRY(owner, cudaSetDevice(owner->device));
+	CUDA_TRY(owner, cudaStreamSynchronize(owner->comm_stream));
+	return GSA_OK;
+}
+
+// On the root after a gather: the image of `rank`'s outbox where it arrived (device pointer; the root's own image is its outbox).
+int gsa_inbox_device(gsa_ctx *root, int32_t rank, const void **dev_ptr, int64_t *bytes)
+{
+	if (!root || !dev_ptr || !bytes || rank < 0 || rank >= (int)root->inbox_bytes.size()) return GSA_ERR_ARG;
+	*bytes = root->inbox_bytes[(size_t)rank];
+	*dev_ptr = rank == root->comm_rank ? root->d_outbox.p : root->d_inbox[(size_t)rank].p;
+	return GSA_OK;
+}
+
+// ... copied to pinned host memory for the emitters (valid until the next call on this context)
+int gsa_inbox_host(gsa_ctx *root, int32_t rank, const void **host_ptr, int64_t *bytes)
+{
+	const void *d = nullptr;
+	GSA_TRY(gsa_inbox_device(root, rank, &d, bytes));
+	CUDA_TRY(root, cudaSetDevice(root->device));
+	GSA_TRY(gsa_ensure_host(root, root->h_inbox, (size_t)*bytes + 16));
+	if (*bytes) CUDA_TRY(root, cudaMemcpyAsync(root->h_inbox.p, d, (size_t)*bytes, cudaMemcpyDeviceToHost, root->comm_stream));
+	CUDA_TRY(root, cudaStreamSynchronize(root->comm_stream));
+	*host_ptr = root->h_inbox.p;
+	return GSA_OK;
+}
+
+// Host-side walk over an outbox image: fills *out with pointers into the image for the record at *offset and advances it.
+// Returns 1 while there is a record, 0 at the end, < 0 on a malformed image.
+int gsa_record_next(const void *image, int64_t bytes, int64_t *offset, int64_t *contig, gsa_alignment *out)
+{
+	if (!image || !offset || !contig || !out) return GSA_ERR_ARG;
+	int64_t o = *offset;
+	if (o >= bytes) return 0;
+	if (o + REC_HDR > bytes) return GSA_ERR_ARG;
+	const char *base = (const char *)image;
+	int64_t h[4]; memcpy(h, base + o, sizeof(h)); o += REC_HDR;
+	const int64_t nb = h[1], nf = h[2], ab = h[3];
+	if (nb < 0 || nf < 0 || ab < 0) return GSA_ERR_ARG;
+	const int64_t end = o + pad16(nb * (int64_t)sizeof(gsa_block)) + pad16(nf * (int64_t)sizeof(gsa_frag)) + 2 * pad16(ab);
+	if (end > bytes) return GSA_ERR_ARG;
+	memset(out, 0, sizeof(*out));
+	*contig = h[0];
+	out->n_blocks = (int32_t)nb; out->blocks = (const gsa_block *)(base + o); o += pad16(nb * (int64_t)sizeof(gsa_block));
+	out->n_frags = nf; out->frags = (const gsa_frag *)(base + o); o += pad16(nf * (int64_t)sizeof(gsa_frag));
+	out->aln_bytes = ab; out->aln1 = base + o; o += pad16(ab);
+	out->aln2 = base + o; o += pad16(ab);
+	*offset = o;
+	return 1;
+}
+
+} // extern "C"

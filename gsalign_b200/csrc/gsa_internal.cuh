@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/gsalign_b200.h"
@@ -130,6 +131,18 @@ struct gsa_ctx {
 	DevBuf d_bsum;                 // per block {aln_len, score}
 	HostBuf h_frag, h_aln1, h_aln2, h_blocks;
 	std::vector<gsa_block> out_blocks;
+
+	// multi-GPU record gather (gather.cu): the outbox of this GPU (owner context) and, on the root, the arrived images
+	void *nccl_comm = nullptr; int comm_rank = 0, comm_size = 0;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_gather = nullptr;       // end of this rank's part of the last gather (the next step's appends order after it)
+	cudaEvent_t ev_outbox = nullptr;       // per lane: its last append
+	DevBuf d_outbox, d_sizes;
+	int64_t outbox_used = 0;
+	std::mutex outbox_mu;                  // lanes of one GPU append from their own host threads
+	std::vector<cudaEvent_t> outbox_pending;
+	std::vector<DevBuf> d_inbox; std::vector<int64_t> inbox_bytes;
+	HostBuf h_inbox, h_rec;
 };
 
 int gsa_fail(gsa_ctx *ctx, int code, const char *fmt, ...);

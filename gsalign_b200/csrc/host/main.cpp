@@ -185,6 +185,14 @@ int main(int argc, char *argv[])
 		for (int l = 1; l < nl; l++)
 			if (gsa_create_shared(ctx[g][0], &ctx[g][l]) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(ctx[g][0])); return 0; }
 	}
+	// several GPUs: the finished records stay in HBM, are packed into one outbox per GPU and collected on GPU 0 by a single
+	// NCCL gather over NVLink once every contig is aligned (GSA_GATHER=host: every GPU copies its records to the host itself)
+	const char *gmode = getenv("GSA_GATHER");
+	const bool nccl_gather = ngpu > 1 && !(gmode && strcmp(gmode, "host") == 0);
+	if (nccl_gather) {
+		if (gsa_comm_init_all(owners.data(), ngpu) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(owners[0])); return 1; }
+		for (int g = 0; g < ngpu; g++) for (gsa_ctx *c : ctx[g]) gsa_set_host_results(c, 0);
+	}
 	tick("lanes ready");
 
 	// ---- GenomeComparison ------------------------------------------------------------------------------------------------
@@ -200,15 +208,44 @@ int main(int argc, char *argv[])
 			{ std::unique_lock<std::mutex> lk(mu); if (cursor[g] >= work[g].size()) return; qi = work[g][cursor[g]++]; }
 			gsa_alignment al;
 			int rc = gsa_align_contig(c, query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al);
-			if (rc == 0) results[qi].assign(al); // the copy out of the pinned buffers runs outside the lock: slot qi is this lane's alone
+			if (rc == 0 && nccl_gather) rc = gsa_outbox_append(owners[g], c, qi);
+			else if (rc == 0) results[qi].assign(al); // the copy out of the pinned buffers runs outside the lock: slot qi is this lane's alone
 			std::unique_lock<std::mutex> lk(mu);
 			if (rc != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(c)); failed = true; }
-			done[qi] = 1;
+			if (!nccl_gather || rc != 0) done[qi] = 1;
 			cv.notify_all();
 		}
 	};
 	std::vector<std::thread> threads;
 	for (int g = 0; g < ngpu; g++) for (gsa_ctx *c : ctx[g]) threads.emplace_back(run_lane, g, c);
+	std::thread collector;
+	if (nccl_gather) { // the collector: all lanes, then the one gather, then the images come to the host rank by rank
+		collector = std::thread([&] {
+			for (auto &t : threads) t.join();
+			bool bad;
+			{ std::unique_lock<std::mutex> lk(mu); bad = failed; }
+			if (!bad && (gsa_gather_records_all(owners.data(), ngpu, 0) != 0 || gsa_gather_wait(owners[0]) != 0)) bad = true;
+			for (int r = 0; r < ngpu && !bad; r++) {
+				const void *img = nullptr; int64_t bytes = 0, off = 0, contig = 0;
+				if (gsa_inbox_host(owners[0], r, &img, &bytes) != 0) { bad = true; break; }
+				std::vector<std::thread> cp; std::vector<int64_t> got;
+				gsa_alignment al; int rc;
+				while ((rc = gsa_record_next(img, bytes, &off, &contig, &al)) == 1) {
+					if (contig < 0 || contig >= nq) { rc = -1; break; }
+					got.push_back(contig);
+					cp.emplace_back([&results, contig, al] { results[(size_t)contig].assign(al); });
+				}
+				for (auto &t : cp) t.join();
+				if (rc < 0) { bad = true; break; }
+				std::unique_lock<std::mutex> lk(mu);
+				for (int64_t qi : got) done[(size_t)qi] = 1;
+				cv.notify_all();
+			}
+			std::unique_lock<std::mutex> lk(mu);
+			if (bad) { if (!failed) fprintf(stderr, "FatalError: record gather: %s\n", gsa_last_error(owners[0])); failed = true; for (auto &d : done) d = 1; }
+			cv.notify_all();
+		});
+	}
 
 	EmitState st;
 	st.threads = std::max(1, o.threads);
@@ -238,7 +275,8 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "\n");
 		r = ContigResult();
 	}
-	for (auto &t : threads) t.join();
+	if (nccl_gather) collector.join(); // the collector has joined the lanes
+	else for (auto &t : threads) t.join();
 	tick("align + emit");
 	if (failed) { // a device or limit failure mid-run: no partial files are left behind and the exit code says so (the reference's
 		// always-0 convention covers usage errors, not an aborted run)

@@ -182,6 +182,37 @@ int64_t gsa_dump_blocks(gsa_ctx *ctx, int32_t stage, int64_t *out);
  * Validates an index whose text is too large for the reference's own indexer to cross-check in test time. */
 int gsa_index_selfcheck(gsa_ctx *ctx, int64_t n_samples, int64_t *n_bad);
 
+/* --- multi-GPU: the record gather (reference: query contigs are independent and their records are only
+ * appended in contig order, src/GSAlign.cpp:483-548) -----------------------------------------------------------------
+ * Query contigs are dealt to GPUs, every GPU holds an index replica, and the finished records of all GPUs are collected
+ * on the root GPU by ONE gather per job: grouped ncclSend / ncclRecv over NVLink.  NCCL is bound at run time (dlopen);
+ * these calls fail with GSA_ERR_CUDA where it is absent, everything else works without it.
+ * Outbox image (little-endian, every section padded to 16 bytes), one record per finished contig:
+ *   int64[4] {contig, n_blocks, n_frags, aln_bytes}, gsa_block[n_blocks], gsa_frag[n_frags], aln1[aln_bytes], aln2[aln_bytes] */
+/* one process per GPU: rank 0 makes the 128-byte id, the host hands it to every rank (MPI, torch.distributed, a file ...) */
+int gsa_comm_unique_id(void *id, int32_t id_bytes);
+int gsa_comm_init_rank(gsa_ctx *ctx, const void *id, int32_t rank, int32_t n_ranks);
+/* one process driving n GPUs (bin/GSAlign -gpus n): ctxs[i] = the owner context of GPU i, rank i */
+int gsa_comm_init_all(gsa_ctx *const *ctxs, int32_t n);
+int gsa_comm_destroy(gsa_ctx *ctx);
+/* the outbox of a GPU lives in its owner context; lanes append their last gsa_fill() result (device to device, on the
+ * lane's stream, thread-safe) under the caller's contig index */
+int gsa_outbox_reset(gsa_ctx *owner);
+int gsa_outbox_reserve(gsa_ctx *owner, int64_t bytes);
+int gsa_outbox_append(gsa_ctx *owner, gsa_ctx *lane, int64_t contig);
+int64_t gsa_outbox_bytes(gsa_ctx *owner);
+/* the gather: collective over the communicator (every rank calls it once per job) / the same for all ranks of a
+ * single-process communicator.  Asynchronous on a communication stream; gsa_gather_wait blocks until it has run. */
+int gsa_gather_records(gsa_ctx *owner, int32_t root);
+int gsa_gather_records_all(gsa_ctx *const *ctxs, int32_t n, int32_t root);
+int gsa_gather_wait(gsa_ctx *owner);
+/* on the root: rank r's image where it arrived (device) / copied to pinned host memory (valid until the next call) */
+int gsa_inbox_device(gsa_ctx *root, int32_t rank, const void **dev_ptr, int64_t *bytes);
+int gsa_inbox_host(gsa_ctx *root, int32_t rank, const void **host_ptr, int64_t *bytes);
+/* host-side walk over an image: returns 1 and fills *contig / *out (pointers into the image) for the record at *offset,
+ * which it advances; 0 at the end; < 0 on a malformed image */
+int gsa_record_next(const void *image, int64_t bytes, int64_t *offset, int64_t *contig, gsa_alignment *out);
+
 /* Stand-alone batch of global alignments through K3's DP kernel (ksw2_alignment semantics):
  * pair i aligns ref[ref_off[i] .. ref_off[i+1]) with qry[qry_off[i] .. qry_off[i+1]); rows are written
  * to out1/out2 at out_off[i] = ref_off[i] + qry_off[i], lengths to out_len.  Host pointers. */

@@ -213,3 +213,31 @@ def test_query_fasta_reader_edge_cases(tmp_path):
     big = b">a\n" + b"ACGT" * 50_000 + b"\n" + b"".join(b">s%d\n%s\n" % (i, b"GATTACA" * (i + 1)) for i in range(40))
     out, _ = run(big)
     assert out[0] == "ok=1 n=41" and out[1].startswith("[a] 200000 ACGTACGT") and out[41] == "[s39] 280 " + "GATTACA" * 40
+
+
+def test_record_walk_host_only():
+    """gsa_record_next is host code: walks a hand-built outbox image (two records) and rejects a truncated one"""
+    import ctypes as C
+    from gsalign_b200 import capi
+    lib = capi.load_library()
+
+    def pad(b):
+        return b + b"\0" * (-len(b) % 16)
+    blocks = np.zeros(2, dtype=capi.BLOCK_DTYPE); blocks["score"] = [7, 9]; blocks["n_frags"] = [1, 2]
+    frags = np.zeros(3, dtype=capi.FRAG_DTYPE); frags["qPos"] = [5, 6, 7]
+    a1, a2 = b"AC-GT", b"ACTGT"
+    rec0 = np.array([3, 2, 3, 5], dtype=np.int64).tobytes() + pad(blocks.tobytes()) + pad(frags.tobytes()) + pad(a1) + pad(a2)
+    rec1 = np.array([8, 0, 0, 0], dtype=np.int64).tobytes()
+    img = rec0 + rec1
+    buf = C.create_string_buffer(img, len(img))
+    off, contig, al = C.c_int64(0), C.c_int64(), capi.Alignment()
+    assert lib.gsa_record_next(buf, C.c_int64(len(img)), C.byref(off), C.byref(contig), C.byref(al)) == 1
+    assert contig.value == 3 and al.n_blocks == 2 and al.n_frags == 3 and al.aln_bytes == 5
+    assert C.string_at(al.aln1, 5) == a1 and C.string_at(al.aln2, 5) == a2
+    got = np.frombuffer(C.string_at(al.frags, 3 * capi.FRAG_DTYPE.itemsize), dtype=capi.FRAG_DTYPE)
+    assert list(got["qPos"]) == [5, 6, 7]
+    assert lib.gsa_record_next(buf, C.c_int64(len(img)), C.byref(off), C.byref(contig), C.byref(al)) == 1
+    assert contig.value == 8 and al.n_blocks == 0
+    assert lib.gsa_record_next(buf, C.c_int64(len(img)), C.byref(off), C.byref(contig), C.byref(al)) == 0
+    off = C.c_int64(0)
+    assert lib.gsa_record_next(buf, C.c_int64(len(rec0) - 16), C.byref(off), C.byref(contig), C.byref(al)) < 0

@@ -130,3 +130,53 @@ def test_index_builder_bytes_adversarial(workdir, block):
                 f.write(bytes(s[i:i + 61]) + eol)
             f.write(b"\n")
     _index_equal(d, "adv.fa", block)
+
+
+# ---- BASELINE.json configs through the drop-in, byte for byte against the unmodified reference ---------------------------
+def _workload_files(workdir, name, n, k, snv, indel, seed):
+    """the bench.py generator + bin/gsa_index, the GPU index builder (its files equal the reference's, above)"""
+    from gsalign_b200 import synth
+    d = os.path.join(workdir, name)
+    if not os.path.exists(os.path.join(d, "ref.sa")):
+        os.makedirs(d, exist_ok=True)
+        ref, qry = synth.make_pair(n, k, snv, indel, seed)
+        synth.write_fasta(os.path.join(d, "ref.fa"), ref); synth.write_fasta(os.path.join(d, "qry.fa"), qry)
+        run(OUR_INDEX, d, ["ref.fa", "ref"])
+    return d
+
+
+@pytest.mark.parametrize("name,n,k,snv,indel,seed,flags", [
+    ("C2", 100_000_000, 4, 0.01, 0.0, 2, []),                                         # config 2 at full size
+    ("C3s", 20_000_000, 4, 0.02, 0.002, 3, []),                                       # config 3's rates, time-boxed size
+    ("C4s", 24_000_000, 24, 0.01, 0.001, 4, []),                                      # config 4's rates and contig count
+    ("C5s", 10_000_000, 4, 0.10, 0.0, 5, ["-sen", "-slen", "10", "-idy", "70"]),      # config 5's rates and flags
+], ids=["C2", "C3s", "C4s", "C5s"])
+def test_baseline_configs_cli_bytes(workdir, name, n, k, snv, indel, seed, flags):
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/GSAlign not built")
+    d = _workload_files(workdir, name, n, k, snv, indel, seed)
+    nt = str(os.cpu_count() or 8)
+    run(REF, d, ["-t", nt, "-i", "ref", "-q", "qry.fa", "-o", "theirs"] + flags)
+    run(OURS, d, ["-t", nt, "-i", "ref", "-q", "qry.fa", "-o", "ours"] + flags)
+    for ext in ("maf", "vcf"):
+        a, b = os.path.join(d, "theirs." + ext), os.path.join(d, "ours." + ext)
+        assert os.path.getsize(a) > 1000
+        assert filecmp.cmp(a, b, shallow=False), f"{name}: .{ext} differs"
+        print(f"{name} .{ext}: {os.path.getsize(a)} bytes, md5 {md5(a)} (both)")
+        os.remove(a); os.remove(b)
+
+
+def test_nccl_gather_cli_same_bytes(workdir):
+    """-gpus 2 (or more): records travel through the per-GPU outboxes and the single NCCL gather to GPU 0; the files must equal
+    the 1-GPU run's and the host-copy variant's.  Needs 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = _workload_files(workdir, "C4s", 24_000_000, 24, 0.01, 0.001, 4)
+    n = min(8, torch.cuda.device_count())
+    run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "n1"])
+    run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "nn", "-gpus", str(n)])
+    run(OURS, d, ["-i", "ref", "-q", "qry.fa", "-o", "nh", "-gpus", str(n)], env={"GSA_GATHER": "host"})
+    for ext in ("maf", "vcf"):
+        for other in ("nn", "nh"):
+            assert filecmp.cmp(os.path.join(d, f"n1.{ext}"), os.path.join(d, f"{other}.{ext}"), shallow=False), (other, ext)

@@ -10,7 +10,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=$ROOT/gpurun_out/c4_parity.txt
 mkdir -p "$D" "$ROOT/gpurun_out"
 exec > >(tee "$OUT") 2>&1
-t() { /usr/bin/time -f "%e s wall, %M KB maxrss" "$@"; }
+t() { local s=$(date +%s%N); "$@"; local rc=$?; echo "$(( ($(date +%s%N) - s) / 1000000 )) ms wall"; return $rc; }
 echo "== box: $(nproc) cores, $(free -g | awk '/Mem:/{print $2}') GB RAM, $(nvidia-smi --query-gpu=name --format=csv,noheader | head -1) x $(nvidia-smi -L | wc -l)"
 if [ ! -f "$D/ok" ]; then
   echo "== generate C4 (gsalign_b200/synth.py write_pair_streams, seed 4)"
@@ -36,6 +36,6 @@ if [ "${C4_SKIP_REF:-0}" != "1" ]; then
   ( cd "$D" && md5sum theirs.maf theirs.vcf && ls -l theirs.maf theirs.vcf )
   a=$(cd "$D" && md5sum < theirs.maf); b=$(awk '/ours.maf/{print $1}' "$D/ours.md5" | head -1)
   c=$(cd "$D" && md5sum < theirs.vcf); e=$(awk '/ours.vcf/{print $1}' "$D/ours.md5" | head -1)
-  if [ "${a%% *}" = "$b" ] && [ "${c%% *}" = "$e" ]; then echo "C4: .maf and .vcf byte-identical (md5)"; else echo "C4: MISMATCH"; fi
+  if [ -s "$D/theirs.vcf" ] && [ -n "$b" ] && [ "${a%% *}" = "$b" ] && [ "${c%% *}" = "$e" ]; then echo "C4: .maf and .vcf byte-identical (md5)"; else echo "C4: MISMATCH"; fi
   rm -f "$D/theirs.maf"
 fi
