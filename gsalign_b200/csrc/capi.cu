@@ -64,6 +64,11 @@ int gsa_create(int device, gsa_ctx **out)
 	for (int i = 0; i < 12; i++) cudaEventCreate(&ctx->ev[i]);
 	if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
+	ctx->side[0] = ctx->stream2;
+	for (int i = 0; i < GSA_NSIDE; i++) {
+		if (i > 0 && cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
+		if (cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
+	}
 	if (gsa_ensure_host(ctx, ctx->h_small, 1 << 20) != GSA_OK) { delete ctx; return GSA_ERR_NOMEM; }
 	if (gsa_dpx_init_device(ctx) != GSA_OK) { fprintf(stderr, "gsalign_b200: %s\n", ctx->err.c_str()); delete ctx; return GSA_ERR_CUDA; }
 	*out = ctx;
@@ -104,7 +109,7 @@ void gsa_destroy(gsa_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *bufs[] = {&ctx->d_occ, &ctx->d_txt, &ctx->d_sa, &ctx->d_ktab, &ctx->d_kbits, &ctx->d_cend, &ctx->d_seq, &ctx->d_qpk, &ctx->d_qinv,
-	                  &ctx->d_counter, &ctx->d_sq, &ctx->d_sr, &ctx->d_sl, &ctx->d_cub, &ctx->d_cq, &ctx->d_cr, &ctx->d_cl, &ctx->d_cb,
+	                  &ctx->d_counter, &ctx->d_chain, &ctx->d_sq, &ctx->d_sr, &ctx->d_sl, &ctx->d_cub, &ctx->d_cq, &ctx->d_cr, &ctx->d_cl, &ctx->d_cb,
 	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	for (DevBuf &b : ctx->d_tmp) if (b.p) cudaFree(b.p);
@@ -120,6 +125,10 @@ void gsa_destroy(gsa_ctx *ctx)
 	for (int i = 0; i < 12; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
 	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+	for (int i = 0; i < GSA_NSIDE; i++) {
+		if (ctx->ev_side[i]) cudaEventDestroy(ctx->ev_side[i]);
+		if (i > 0 && ctx->side[i]) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); }
+	}
 	if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
 	if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;

@@ -9,23 +9,30 @@
 //   CheckAlnBlockSpanMultipleRefChrs   src/ProcessCandidateAlignment.cpp:81-99
 //   IdentifyNormalPairs                src/ProcessCandidateAlignment.cpp:241-265
 // following the exact restatement of SURVEY.md appendix B.  Everything is expressed as radix sorts
-// (diagonal,qpos) / (group,qpos), prefix scans, stream compactions and elementwise kernels over ALL groups
-// at once, so the one giant main-diagonal group of a collinear contig costs the same as many small ones:
+// (diagonal,qpos) / (group,qpos) and single-pass chained scans whose input and output are functors (scan.cuh: flag or
+// count per seed -> prefix -> scatter / segment id / hash insert in ONE launch) over ALL groups at once, so the one giant
+// main-diagonal group of a collinear contig costs the same as many small ones.  Element counts stay in device memory;
+// the host waits twice per contig (piece tables for its block logic, fragment count):
 //   * the greedy outlier windows (data-dependent resets) become "next window start" pointers computed
 //     by binary search per seed and resolved by pointer jumping;
 //   * the per-window PosDiff histograms become one global (window,bin) hash table with atomic counts;
 //   * overlap trimming, gap / contig-span break points and normal-pair insertion are adjacent-pair maps.
 // Only O(#blocks) headers go to the host (block_logic.cpp) for the reference's float/std::sort logic.
 #include "fm.cuh"
+#include "scan.cuh"
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <cub/device/device_select.cuh>
-#include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
 
 // ------------------------------------------------------------------------------------------------
-// scratch management
+// scratch, device counters, chain launches
 // ------------------------------------------------------------------------------------------------
+// Every element count of the phase lives in device memory (dc[]): the kernels of one contig are queued back to back and
+// sized by a host-side upper bound (the seed count), so the host only waits twice -- for the piece tables its block logic
+// needs, and for the fragment count at the end.
+enum { DC_N0 = 0, DC_NGROUPS, DC_N2, DC_NG2, DC_NC, DC_NLU, DC_N3, DC_N4, DC_NB0, DC_NB1, DC_N5, DC_N6A, DC_N6, DC_KILLS, DC_NCAND,
+       DC_NP0, DC_NP1, DC_NP2, DC_NPL0, DC_NFR, DC_NPTOT, DC_COUNT };
+#define K2_CHAINS 24
+
 struct Ws {
 	gsa_ctx *ctx; int next = 0; int rc = GSA_OK;
 	explicit Ws(gsa_ctx *c) : ctx(c) {}
@@ -39,48 +46,18 @@ struct Ws {
 	}
 };
 
-template <typename T>
-static int scan_inclusive(gsa_ctx *ctx, const T *in, T *out, int64_t n)
-{
-	if (n <= 0) return GSA_OK;
-	size_t bytes = 0;
-	cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream);
-	GSA_TRY(gsa_ensure(ctx, ctx->d_cub, bytes));
-	CUDA_TRY(ctx, cub::DeviceScan::InclusiveSum(ctx->d_cub.p, bytes, in, out, (int)n, ctx->stream));
-	ctx->tm.launches += 1;
-	return GSA_OK;
-}
+struct Chains { // the chain states of one gsa_cluster call: [tickets | totals | status slices], zeroed by one memset
+	unsigned int *ticket; unsigned long long *total, *status; int64_t tiles; int used = 0;
+	ChainState next() { ChainState c; c.ticket = ticket + used; c.total = total + used; c.status = status + (size_t)used * tiles; used++; return c; }
+};
 
-template <typename T>
-static int scan_exclusive(gsa_ctx *ctx, const T *in, T *out, int64_t n)
+template <typename F>
+static int run_chain(gsa_ctx *ctx, Chains &ch, const F &f, const int32_t *d_n, int64_t bound)
 {
-	if (n <= 0) return GSA_OK;
-	size_t bytes = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream);
-	GSA_TRY(gsa_ensure(ctx, ctx->d_cub, bytes));
-	CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, bytes, in, out, (int)n, ctx->stream));
-	ctx->tm.launches += 1;
-	return GSA_OK;
-}
-
-// indices i in [0,n) with flags[i] != 0 -> out (ascending); the count is left at d_count (device)
-static int select_indices(gsa_ctx *ctx, const uint8_t *flags, int32_t *out, int32_t *d_count, int64_t n)
-{
-	if (n <= 0) { CUDA_TRY(ctx, cudaMemsetAsync(d_count, 0, 4, ctx->stream)); return GSA_OK; }
-	thrust::counting_iterator<int32_t> it(0);
-	size_t bytes = 0;
-	cub::DeviceSelect::Flagged(nullptr, bytes, it, flags, out, d_count, (int)n, ctx->stream);
-	GSA_TRY(gsa_ensure(ctx, ctx->d_cub, bytes));
-	CUDA_TRY(ctx, cub::DeviceSelect::Flagged(ctx->d_cub.p, bytes, it, flags, out, d_count, (int)n, ctx->stream));
-	ctx->tm.launches += 2;
-	return GSA_OK;
-}
-
-static int read_count(gsa_ctx *ctx, const int32_t *d_count, int64_t *out)
-{
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small.p, d_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-	*out = *(int32_t *)ctx->h_small.p;
+	if (ch.used >= K2_CHAINS) return gsa_fail(ctx, GSA_ERR_NOMEM, "cluster: out of chain states");
+	if (bound + 1 > (ch.tiles - 1) * CH_TILE) return gsa_fail(ctx, GSA_ERR_ARG, "cluster: chain bound above the allocated tiles");
+	k_chain<F><<<(unsigned)chain_tiles(bound), CH_THREADS, 0, ctx->stream>>>(f, d_n, ch.next());
+	KERNEL_CHECK(ctx);
 	return GSA_OK;
 }
 
@@ -89,114 +66,130 @@ static int read_count(gsa_ctx *ctx, const int32_t *d_count, int64_t *out)
 		if ((n) > 0) { kernel<<<gsa_grid((n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__); KERNEL_CHECK(ctx); } \
 	} while (0)
 
-// ------------------------------------------------------------------------------------------------
-// kernels: grouping
-// ------------------------------------------------------------------------------------------------
-__global__ void k_group_flags(const int32_t *q, const int64_t *r, int32_t *flag, int64_t n, int max_indel)
+struct NoFinish { __device__ void finish(unsigned long long) const {} };
+
+__global__ void k_k2_init(int32_t *dc, int32_t n0)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	flag[i] = i == 0 || ((r[i] - q[i]) - (r[i - 1] - q[i - 1])) > max_indel; // SeedGrouping, src/GSAlign.cpp:133
+	if (threadIdx.x < DC_COUNT) dc[threadIdx.x] = threadIdx.x == DC_N0 ? n0 : 0;
 }
 
-__global__ void k_group_score(const int32_t *gid1, const int32_t *len, unsigned long long *score, int64_t n)
-{ // FindSeedGroupScore, src/GSAlign.cpp:298-303
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	bool in = i < n;
-	int g = in ? gid1[i] - 1 : -1, v = in ? len[i] : 0;
-	// warp-aggregate when the whole warp sits in one group (the common case: one giant diagonal group)
-	int g0 = __shfl_sync(0xffffffffu, g, 0);
-	if (__all_sync(0xffffffffu, g == g0)) {
-		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-		if ((threadIdx.x & 31) == 0 && g0 >= 0) atomicAdd(score + g0, (unsigned long long)(long long)v);
-	} else if (in) atomicAdd(score + g, (unsigned long long)(long long)v);
-}
-
-__global__ void k_group_keep(const int32_t *gid1, const unsigned long long *score, uint8_t *keep, int64_t n, int min_score)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	keep[i] = (long long)score[gid1[i] - 1] >= (long long)min_score; // FindSeedGroupScore < MinAlnBlockScore -> skip, src/GSAlign.cpp:387
-}
-
-// sort key of the per-group order CompByQueryPos (src/ProcessCandidateAlignment.cpp:9-13): (group, qPos); ties on
-// qPos keep their (PosDiff,qPos) input order under the stable radix sort, which for equal qPos is rPos order
-__global__ void k_group_keys(const int32_t *idx, const int32_t *gid1, const int32_t *q, uint64_t *key, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int32_t s = idx[i];
-	key[i] = ((uint64_t)(uint32_t)(gid1[s] - 1) << 32) | (uint32_t)q[s];
-}
-
-__global__ void k_gather_seeds(const int32_t *idx, const int32_t *q, const int64_t *r, const int32_t *l, const int32_t *g,
-                               int32_t *oq, int64_t *orr, int32_t *ol, int32_t *og, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int32_t s = idx[i];
-	oq[i] = q[s]; orr[i] = r[s]; ol[i] = l[s]; og[i] = g[s];
-}
-
-__global__ void k_seg_flags(const int32_t *g, uint8_t *flag, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	flag[i] = i == 0 || g[i] != g[i - 1];
-}
-
-__global__ void k_fill_i32(int32_t *a, int32_t v, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) a[i] = v;
-}
-
-// dense segment id per element from the ascending list of segment starts
-__global__ void k_seg_ids(const int32_t *starts, const int32_t *d_nseg, int32_t *dg, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int lo = 0, hi = *d_nseg; // last start <= i
-	while (lo < hi) { int m = (lo + hi) >> 1; if (starts[m] <= (int32_t)i) lo = m + 1; else hi = m; }
-	dg[i] = lo - 1;
-}
+// peers of the calling lane among the lanes with the same key; every lane of the warp must call (inactive lanes pass a key
+// no active lane uses)
+__device__ __forceinline__ unsigned peers_of(int key) { return __match_any_sync(0xffffffffu, key); }
+#define DEAD_KEY (-1 - (int)(threadIdx.x & 31))
 
 // ------------------------------------------------------------------------------------------------
-// kernels: SeedGroupAnalysis
+// 1. diagonal groups (SeedGrouping, src/GSAlign.cpp:126-143) and their scores (FindSeedGroupScore, :298-303)
+// ------------------------------------------------------------------------------------------------
+struct FGroup {
+	const int32_t *q; const int64_t *r; const int32_t *l; int32_t *gid1; unsigned long long *gscore; int32_t *dc; int max_indel;
+	struct Item { int32_t len; uint8_t flag; };
+	__device__ Item load(int64_t i) const
+	{
+		Item it; it.len = l[i];
+		it.flag = i == 0 || ((r[i] - q[i]) - (r[i - 1] - q[i - 1])) > max_indel; // src/GSAlign.cpp:133
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return it.flag; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		int g = valid ? (int)excl + it.flag : 0; // 1-based group id
+		if (valid) gid1[i] = g;
+		unsigned peers = peers_of(valid ? g : DEAD_KEY);
+		bool leader;
+		long long tot = gsa_peer_sum(peers, (long long)(valid ? it.len : 0), leader);
+		if (leader && valid) atomicAdd(gscore + (g - 1), (unsigned long long)tot);
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_NGROUPS] = (int32_t)total; }
+};
+
+// groups below MinAlnBlockScore are skipped (src/GSAlign.cpp:387); the survivors get the sort key of the per-group order
+// CompByQueryPos (src/ProcessCandidateAlignment.cpp:9-13): (group, qPos); ties on qPos keep their (PosDiff,qPos) input
+// order under the stable radix sort, which for equal qPos is rPos order
+struct FKeep {
+	const int32_t *q, *gid1; const unsigned long long *gscore; uint64_t *key; int32_t *val; int32_t *dc; int min_score, qbits;
+	struct Item { int32_t q, g; uint8_t keep; };
+	__device__ Item load(int64_t i) const
+	{
+		Item it; it.q = q[i]; it.g = gid1[i] - 1;
+		it.keep = (long long)gscore[it.g] >= (long long)min_score;
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return it.keep; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (valid && it.keep) { key[excl] = ((uint64_t)(uint32_t)it.g << qbits) | (uint32_t)it.q; val[excl] = (int32_t)i; }
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_N2] = (int32_t)total; }
+};
+
+// gather in the sorted order + dense group ids + group start table
+struct FSeg {
+	const int32_t *val, *gid1, *q; const int64_t *r; const int32_t *l;
+	int32_t *oq; int64_t *orr; int32_t *ol, *dg, *gstart, *dc;
+	struct Item { int32_t q, l; int64_t r; uint8_t flag; };
+	__device__ Item load(int64_t i) const
+	{
+		int32_t s = val[i];
+		Item it; it.q = q[s]; it.r = r[s]; it.l = l[s];
+		it.flag = i == 0 || gid1[s] != gid1[val[i - 1]];
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return it.flag; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (!valid) return;
+		oq[i] = it.q; orr[i] = it.r; ol[i] = it.l; dg[i] = (int32_t)excl + it.flag - 1;
+		if (it.flag) gstart[excl] = (int32_t)i;
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_NG2] = (int32_t)total; gstart[total] = dc[DC_N2]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// 2. SeedGroupAnalysis
 // ------------------------------------------------------------------------------------------------
 struct GroupView {
 	const int32_t *q; const int64_t *r; const int32_t *l; const int32_t *dg; const int32_t *gstart; // gstart[ng] = n
-	int64_t n;
+	const int32_t *dn;                                                                              // element count (device)
 };
 
 __device__ __forceinline__ int64_t pd_of(const GroupView &v, int64_t i) { return v.r[i] - v.q[i]; }
 
-__global__ void k_uniq(GroupView v, int32_t *uq)
-{ // UniqueArr, src/GSAlign.cpp:316-325
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= v.n) return;
-	int gs = v.gstart[v.dg[i]], ge = v.gstart[v.dg[i] + 1];
-	bool same_prev = i > gs && v.q[i - 1] == v.q[i], same_next = i + 1 < ge && v.q[i + 1] == v.q[i];
-	uq[i] = !(same_prev || same_next);
-}
+// UniqueArr (src/GSAlign.cpp:316-325) and the positions where a window may close: unique, and PosDiff differs from the
+// previous element (:328-331); U = inclusive count of unique seeds, C = list of the candidates
+struct FUniq {
+	GroupView v; int32_t *uq, *U; uint8_t *cand; int32_t *C, *dc;
+	struct Item { uint8_t uq, cand; };
+	__device__ Item load(int64_t i) const
+	{
+		const int64_t n = *v.dn;
+		int gs = v.gstart[v.dg[i]], ge = v.gstart[v.dg[i] + 1];
+		bool same_prev = i > gs && v.q[i - 1] == v.q[i], same_next = i + 1 < ge && i + 1 < n && v.q[i + 1] == v.q[i];
+		Item it; it.uq = !(same_prev || same_next);
+		it.cand = it.uq && i > gs && pd_of(v, i) != pd_of(v, i - 1);
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return CH_PACK2(it.uq, it.cand); }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (!valid) return;
+		uq[i] = it.uq; U[i] = (int32_t)CH_LO(excl) + it.uq; cand[i] = it.cand;
+		if (it.cand) C[CH_HI(excl)] = (int32_t)i;
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_NC] = (int32_t)CH_HI(total); }
+};
 
-__global__ void k_cand(GroupView v, const int32_t *uq, uint8_t *cand)
-{ // positions where a window may close: unique, and PosDiff differs from the previous element (src/GSAlign.cpp:328-331)
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= v.n) return;
-	int gs = v.gstart[v.dg[i]];
-	cand[i] = uq[i] && i > gs && pd_of(v, i) != pd_of(v, i - 1);
-}
-
-// next window start after a window that starts at i (src/GSAlign.cpp:326-337):
-// the first candidate j > i with (#unique in the window so far) >= 30 and q[j] - q[i] > 3000
-__global__ void k_next(GroupView v, const int32_t *uq, const int32_t *U, const uint8_t *cand, const int32_t *C, const int32_t *d_nC, int32_t *nxt)
+// next window start after a window that starts at i (src/GSAlign.cpp:326-337): the first candidate j > i with
+// (#unique in the window so far) >= 30 and q[j] - q[i] > 3000; reach[] starts at the group starts
+__global__ void k_next(GroupView v, const int32_t *uq, const int32_t *U, const uint8_t *cand, const int32_t *C, const int32_t *d_nC, int32_t *nxt, int32_t *reach)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i > v.n) return;
-	if (i == v.n) { nxt[i] = (int32_t)v.n; return; }
+	const int64_t n = *v.dn;
+	if (i > n) return;
+	if (i == n) { nxt[i] = (int32_t)n; reach[i] = 0; return; }
 	int gs = v.gstart[v.dg[i]], ge = v.gstart[v.dg[i] + 1];
-	if (i != gs && !cand[i]) { nxt[i] = (int32_t)v.n; return; }
+	reach[i] = i == gs;
+	if (i != gs && !cand[i]) { nxt[i] = (int32_t)n; return; }
 	int baseU = i == gs ? U[i] - uq[i] : U[i]; // the first window counts its own first element, later ones restart at 0
 	int lo = (int)i + 1, hi = ge;
 	while (lo < hi) { int m = (lo + hi) >> 1; if (U[m] - baseU >= 30) hi = m; else lo = m + 1; }
@@ -205,7 +198,7 @@ __global__ void k_next(GroupView v, const int32_t *uq, const int32_t *U, const u
 	int qi = v.q[i];
 	while (lo < hi) { int m = (lo + hi) >> 1; if (v.q[m] - qi > 3000) hi = m; else lo = m + 1; }
 	int j0 = max(jA, lo);
-	int res = (int)v.n;
+	int res = (int)n;
 	if (j0 < ge) {
 		int nC = *d_nC; lo = 0; hi = nC;
 		while (lo < hi) { int m = (lo + hi) >> 1; if (C[m] < j0) lo = m + 1; else hi = m; }
@@ -214,17 +207,11 @@ __global__ void k_next(GroupView v, const int32_t *uq, const int32_t *U, const u
 	nxt[i] = res;
 }
 
-__global__ void k_reach_init(GroupView v, int32_t *reach)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i > v.n) return;
-	reach[i] = i < v.n && (int64_t)v.gstart[v.dg[i]] == i;
-}
-
 // pointer jumping: reach is monotone and updated in place, the jump table is ping-ponged
-__global__ void k_jump(int32_t *reach, const int32_t *nin, int32_t *nout, int64_t n)
+__global__ void k_jump(int32_t *reach, const int32_t *nin, int32_t *nout, const int32_t *dn)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t n = *dn;
 	if (i > n) return;
 	int32_t j = nin[i];
 	if (reach[i] && j < n) reach[j] = 1;
@@ -238,31 +225,39 @@ __device__ __forceinline__ uint32_t hash64(uint64_t k)
 	return (uint32_t)k;
 }
 
-// per-window PosDiff>>4 histogram (PDFmap, src/GSAlign.cpp:264-270) as a global (window,bin) hash table
-__global__ void k_hist_insert(GroupView v, const int32_t *uq, const int32_t *wid1, unsigned long long *keys, int32_t *cnt, int32_t *slot_of, uint32_t hmask)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const bool act = i < v.n && uq[i];
-	// inactive lanes get distinct keys no (window,bin) can take (window ids are < 2^31)
-	unsigned long long key = 0xFFFFFFFF00000000ull | (threadIdx.x & 31);
-	if (act) key = ((unsigned long long)(uint32_t)(wid1[i] - 1) << 32) | (uint32_t)(int32_t)(pd_of(v, i) >> 4);
-	// neighbouring seeds mostly share the bin: one probe + one add per distinct key of the warp
-	unsigned peers = __match_any_sync(0xffffffffu, key);
-	bool leader;
-	int total = gsa_peer_sum(peers, 1, leader);
-	uint32_t s = 0;
-	if (leader && act) {
-		s = hash64(key) & hmask;
-		for (;;) {
-			unsigned long long old = atomicCAS(keys + s, HASH_EMPTY, key);
-			if (old == HASH_EMPTY || old == key) break;
-			s = (s + 1) & hmask;
+// window ids (inclusive count of window starts) and, in the same pass, the per-window PosDiff>>4 histogram (PDFmap,
+// src/GSAlign.cpp:264-270) as a global (window,bin) hash table
+struct FWin : NoFinish {
+	GroupView v; const int32_t *uq, *reach; int32_t *wid1; unsigned long long *keys; int32_t *cnt, *slot_of; uint32_t hmask;
+	struct Item { uint8_t r; };
+	__device__ Item load(int64_t i) const { Item it; it.r = reach[i] != 0; return it; }
+	__device__ unsigned long long value(const Item &it) const { return it.r; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		int w1 = valid ? (int)excl + it.r : 0;
+		if (valid) wid1[i] = w1;
+		const bool act = valid && uq[i];
+		// inactive lanes get distinct keys no (window,bin) can take (window ids are < 2^31)
+		unsigned long long key = 0xFFFFFFFF00000000ull | (threadIdx.x & 31);
+		if (act) key = ((unsigned long long)(uint32_t)(w1 - 1) << 32) | (uint32_t)(int32_t)(pd_of(v, i) >> 4);
+		// neighbouring seeds mostly share the bin: one probe + one add per distinct key of the warp
+		unsigned peers = __match_any_sync(0xffffffffu, key);
+		bool leader;
+		int total = gsa_peer_sum(peers, 1, leader);
+		uint32_t s = 0;
+		if (leader && act) {
+			s = hash64(key) & hmask;
+			for (;;) {
+				unsigned long long old = atomicCAS(keys + s, HASH_EMPTY, key);
+				if (old == HASH_EMPTY || old == key) break;
+				s = (s + 1) & hmask;
+			}
+			atomicAdd(cnt + s, total);
 		}
-		atomicAdd(cnt + s, total);
+		s = __shfl_sync(0xffffffffu, s, __ffs(peers) - 1);
+		if (act) slot_of[i] = (int32_t)s;
 	}
-	s = __shfl_sync(0xffffffffu, s, __ffs(peers) - 1);
-	if (act) slot_of[i] = (int32_t)s;
-}
+};
 
 // mode per window = the smallest bin with the maximal count (RefinePDFmap, src/GSAlign.cpp:250-251)
 __global__ void k_win_best(const unsigned long long *keys, const int32_t *cnt, unsigned long long *best, int64_t hsize)
@@ -284,7 +279,7 @@ __global__ void k_win_sum(GroupView v, const int32_t *uq, const int32_t *wid1, c
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	int w = -1 - (int)(threadIdx.x & 31);
 	int64_t pd = 0;
-	if (i < v.n && uq[i]) {
+	if (i < *v.dn && uq[i]) {
 		int wi = wid1[i] - 1;
 		pd = pd_of(v, i);
 		int32_t bin = (int32_t)(pd >> 4), mode = mode_of(best[wi]);
@@ -299,39 +294,45 @@ __global__ void k_win_sum(GroupView v, const int32_t *uq, const int32_t *wid1, c
 	if (leader && w >= 0) { atomicAdd(sum + w, tot); atomicAdd(cntk + w, c); }
 }
 
-__global__ void k_outlier_kill(GroupView v, const int32_t *uq, const int32_t *wid1, const unsigned long long *best, const unsigned long long *sum,
-                               const int32_t *cntk, const int32_t *cnt, const int32_t *slot_of, uint8_t *alive, int64_t genome, int max_indel)
-{ // src/GSAlign.cpp:282-294 with Check_PD_Frequency (:145-153), Min_PD_Freq = 3
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= v.n) return;
-	uint8_t a = 1;
-	if (uq[i]) {
-		int w = wid1[i] - 1;
-		int64_t pd = pd_of(v, i);
-		int32_t bin = (int32_t)(pd >> 4), mode = mode_of(best[w]);
-		long long d = (long long)bin - mode;
-		if (d < 0) d = -d;
-		int own = d < 3 ? cnt[slot_of[i]] : 0;
-		int64_t avg = cntk[w] > 0 ? (int64_t)sum[w] / cntk[w] : genome;
-		int64_t diff = avg - pd;
-		if (diff < 0) diff = -diff;
-		if (diff > max_indel && own < 3) a = 0;
+// outlier kill (src/GSAlign.cpp:282-294 with Check_PD_Frequency :145-153, Min_PD_Freq = 3) and the list of live unique seeds
+struct FOutlier {
+	GroupView v; const int32_t *uq, *wid1; const unsigned long long *best, *sum; const int32_t *cntk, *cnt, *slot_of;
+	uint8_t *alive; int32_t *LU, *dc; int64_t genome; int max_indel;
+	struct Item { uint8_t a, lu; };
+	__device__ Item load(int64_t i) const
+	{
+		Item it; it.a = 1; it.lu = 0;
+		if (uq[i]) {
+			int w = wid1[i] - 1;
+			int64_t pd = pd_of(v, i);
+			int32_t bin = (int32_t)(pd >> 4), mode = mode_of(best[w]);
+			long long d = (long long)bin - mode;
+			if (d < 0) d = -d;
+			int own = d < 3 ? cnt[slot_of[i]] : 0;
+			int64_t avg = cntk[w] > 0 ? (int64_t)sum[w] / cntk[w] : genome;
+			int64_t diff = avg - pd;
+			if (diff < 0) diff = -diff;
+			if (diff > max_indel && own < 3) it.a = 0;
+			it.lu = it.a;
+		}
+		return it;
 	}
-	alive[i] = a;
-}
-
-__global__ void k_live_unique(const int32_t *uq, const uint8_t *alive, uint8_t *lu, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) lu[i] = uq[i] && alive[i];
-}
+	__device__ unsigned long long value(const Item &it) const { return it.lu; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (!valid) return;
+		alive[i] = it.a;
+		if (it.lu) LU[excl] = (int32_t)i;
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_NLU] = (int32_t)total; }
+};
 
 // multi-hit runs (same qPos): keep the hit nearest to the mean PosDiff of <= 5 + 5 neighbouring live unique seeds
 // (src/GSAlign.cpp:341-350 with FindNeighboringPosDiffAvg :178-206 and RemoveRedundantSeeds :208-225)
 __global__ void k_runs(GroupView v, const int32_t *LU, const int32_t *d_nLU, uint8_t *alive, int64_t genome, int max_indel)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= v.n) return;
+	if (i >= *v.dn) return;
 	int gs = v.gstart[v.dg[i]], ge = v.gstart[v.dg[i] + 1];
 	int qi = v.q[i];
 	if (i > gs && v.q[i - 1] == qi) return;         // not a run start
@@ -355,97 +356,136 @@ __global__ void k_runs(GroupView v, const int32_t *LU, const int32_t *d_nLU, uin
 	for (int k = (int)i; k < j; k++) if (k != keep) alive[k] = 0;
 }
 
-// noise: interior seed whose PosDiff is > 5 away from both live neighbours of its group (src/GSAlign.cpp:355-362)
-__global__ void k_noise(const int32_t *q, const int64_t *r, const int32_t *g, uint8_t *alive, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint8_t a = 1;
-	if (i > 0 && i + 1 < n && g[i - 1] == g[i] && g[i + 1] == g[i]) {
-		int64_t p = r[i] - q[i], a1 = p - (r[i - 1] - q[i - 1]), a2 = p - (r[i + 1] - q[i + 1]);
-		if (a1 < 0) a1 = -a1;
-		if (a2 < 0) a2 = -a2;
-		if (a1 > 5 && a2 > 5) a = 0;
+// generic compaction of (q, r, l, tag) by a byte flag
+struct FCompact {
+	const uint8_t *alive; const int32_t *q; const int64_t *r; const int32_t *l, *g; int32_t *oq; int64_t *orr; int32_t *ol, *og, *dc; int slot;
+	struct Item { uint8_t a; };
+	__device__ Item load(int64_t i) const { Item it; it.a = alive[i]; return it; }
+	__device__ unsigned long long value(const Item &it) const { return it.a; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (valid && it.a) { oq[excl] = q[i]; orr[excl] = r[i]; ol[excl] = l[i]; og[excl] = g[i]; }
 	}
-	alive[i] = a;
-}
+	__device__ void finish(unsigned long long total) const { dc[slot] = (int32_t)total; }
+};
 
-// block cuts inside a group (src/GSAlign.cpp:364-374)
-__global__ void k_cut(const int32_t *q, const int64_t *r, const int32_t *l, const int32_t *g, uint8_t *flag, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	bool cut = i == 0 || g[i] != g[i - 1];
-	if (!cut) {
-		int64_t d = (r[i - 1] - q[i - 1]) - (r[i] - q[i]);
-		if (d < 0) d = -d;
-		cut = q[i] - q[i - 1] - l[i - 1] > GSA_MAX_SEED_GAP || d > 100;
-	}
-	flag[i] = cut;
-}
-
-// out[i] = l[i] for i < n, out[n] = 0 (launch n + 1 threads) so that an exclusive scan over n + 1 yields S[n] = total
-__global__ void k_len64(const int32_t *l, int64_t *out, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] = l[i];
-	else if (i == n) out[i] = 0;
-}
-
-__global__ void k_widen(const uint8_t *in, int32_t *out, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] = in[i];
-}
-
-// AddAlnBlock acceptance (src/GSAlign.cpp:29-49); S = exclusive prefix sum of len, S[n] = total
-__global__ void k_block_eval(const int32_t *bstart, int64_t nb, int64_t n, const int32_t *q, const int32_t *l, const int64_t *S,
-                             int32_t *score, uint8_t *accept, int min_score, int min_len)
-{
-	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= nb) return;
-	int64_t beg = bstart[b], end = b + 1 < nb ? bstart[b + 1] : n;
-	int32_t sc = (int32_t)(S[end] - S[beg]);
-	int32_t region = (q[end - 1] + l[end - 1]) - q[beg];
-	score[b] = sc;
-	accept[b] = !(sc < min_score || region < min_len || (sc < 1000 && sc < region * 0.05));
-}
-
-__global__ void k_seed_accept(const int32_t *bid, const uint8_t *accept, uint8_t *keep, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) keep[i] = accept[bid[i]];
-}
-
-__global__ void k_gather_block_seeds(const int32_t *idx, const int32_t *q, const int64_t *r, const int32_t *l, const int32_t *bid,
-                                     const int32_t *newid1, int32_t *oq, int64_t *orr, int32_t *ol, int32_t *ob, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int32_t s = idx[i];
-	oq[i] = q[s]; orr[i] = r[s]; ol[i] = l[s]; ob[i] = newid1[bid[s]] - 1;
-}
-
-// ------------------------------------------------------------------------------------------------
-// kernels: RemoveOverlaps, gap / span break points, pieces
-// ------------------------------------------------------------------------------------------------
-__global__ void k_overlap_pass(const int32_t *q, const int64_t *r, int32_t *l, const int32_t *b, uint8_t *alive, int32_t *kills, int64_t n)
-{ // one pass of RemoveOverlaps (src/ProcessCandidateAlignment.cpp:197-227): element i only reads q/r of i+1
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint8_t a = 1;
-	if (i + 1 < n && b[i + 1] == b[i]) {
-		if (r[i + 1] <= r[i]) a = 0;
-		else {
-			int32_t len = l[i], ov = (int32_t)(r[i] + len - r[i + 1]);
-			if (ov > 0) { len -= ov; if (len <= 0) a = 0; }
-			if (a && (ov = q[i] + len - q[i + 1]) > 0) { len -= ov; if (len <= 0) a = 0; }
-			l[i] = len;
+// noise: interior seed whose PosDiff is > 5 away from both live neighbours of its group (src/GSAlign.cpp:355-362); compacts
+struct FNoise {
+	const int32_t *q; const int64_t *r; const int32_t *l, *g; const int32_t *dn; int32_t *oq; int64_t *orr; int32_t *ol, *og, *dc;
+	struct Item { int32_t q, l, g; int64_t r; uint8_t a; };
+	__device__ Item load(int64_t i) const
+	{
+		const int64_t n = *dn;
+		Item it; it.q = q[i]; it.r = r[i]; it.l = l[i]; it.g = g[i]; it.a = 1;
+		if (i > 0 && i + 1 < n && g[i - 1] == it.g && g[i + 1] == it.g) {
+			int64_t p = it.r - it.q, a1 = p - (r[i - 1] - q[i - 1]), a2 = p - (r[i + 1] - q[i + 1]);
+			if (a1 < 0) a1 = -a1;
+			if (a2 < 0) a2 = -a2;
+			if (a1 > 5 && a2 > 5) it.a = 0;
 		}
+		return it;
 	}
-	alive[i] = a;
-	if (!a) atomicAdd(kills, 1); // rare
-}
+	__device__ unsigned long long value(const Item &it) const { return it.a; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (valid && it.a) { oq[excl] = it.q; orr[excl] = it.r; ol[excl] = it.l; og[excl] = it.g; }
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_N4] = (int32_t)total; }
+};
+
+// block cuts inside a group (src/GSAlign.cpp:364-374): block id per seed, block start table, block scores (sum of lengths)
+struct FCut {
+	const int32_t *q; const int64_t *r; const int32_t *l, *g; int32_t *bid, *bstart, *bscore, *dc;
+	struct Item { int32_t len; uint8_t cut; };
+	__device__ Item load(int64_t i) const
+	{
+		Item it; it.len = l[i];
+		bool cut = i == 0 || g[i] != g[i - 1];
+		if (!cut) {
+			int64_t d = (r[i - 1] - q[i - 1]) - (r[i] - q[i]);
+			if (d < 0) d = -d;
+			cut = q[i] - q[i - 1] - l[i - 1] > GSA_MAX_SEED_GAP || d > 100;
+		}
+		it.cut = cut;
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return it.cut; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		int b = valid ? (int)excl + it.cut - 1 : 0;
+		if (valid) { bid[i] = b; if (it.cut) bstart[excl] = (int32_t)i; }
+		unsigned peers = peers_of(valid ? b : DEAD_KEY);
+		bool leader;
+		int tot = gsa_peer_sum(peers, valid ? it.len : 0, leader);
+		if (leader && valid) atomicAdd(bscore + b, tot);
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_NB0] = (int32_t)total; bstart[total] = dc[DC_N4]; }
+};
+
+// AddAlnBlock acceptance (src/GSAlign.cpp:29-49): new (dense) ids of the accepted blocks and their scores
+struct FBlockEval {
+	const int32_t *bstart, *q, *l, *bscore; uint8_t *accept; int32_t *newid1, *kept_score, *dc; int min_score, min_len;
+	struct Item { int32_t sc; uint8_t a; };
+	__device__ Item load(int64_t b) const
+	{
+		int64_t beg = bstart[b], end = bstart[b + 1];
+		Item it; it.sc = bscore[b];
+		int32_t region = (q[end - 1] + l[end - 1]) - q[beg];
+		it.a = !(it.sc < min_score || region < min_len || (it.sc < 1000 && it.sc < region * 0.05));
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return it.a; }
+	__device__ void emit(int64_t b, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (!valid) return;
+		accept[b] = it.a; newid1[b] = (int32_t)excl + it.a;
+		if (it.a) kept_score[excl] = it.sc;
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_NB1] = (int32_t)total; }
+};
+
+struct FSeedAccept {
+	const int32_t *bid; const uint8_t *accept; const int32_t *newid1, *q; const int64_t *r; const int32_t *l; int32_t *oq; int64_t *orr; int32_t *ol, *ob, *dc;
+	struct Item { int32_t b; uint8_t a; };
+	__device__ Item load(int64_t i) const { Item it; it.b = bid[i]; it.a = accept[it.b]; return it; }
+	__device__ unsigned long long value(const Item &it) const { return it.a; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (valid && it.a) { oq[excl] = q[i]; orr[excl] = r[i]; ol[excl] = l[i]; ob[excl] = newid1[it.b] - 1; }
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_N5] = (int32_t)total; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// 3. RemoveOverlaps, gap / span break points, pieces
+// ------------------------------------------------------------------------------------------------
+// one pass of RemoveOverlaps (src/ProcessCandidateAlignment.cpp:197-227): element i only reads the untouched q/r of i+1, so a
+// pass is elementwise; the survivors are compacted into the other buffer
+struct FOverlap {
+	const int32_t *q; const int64_t *r; const int32_t *l, *b; const int32_t *dn; int32_t *oq; int64_t *orr; int32_t *ol, *ob, *dc; int slot_n;
+	struct Item { int32_t q, len, b; int64_t r; uint8_t a; };
+	__device__ Item load(int64_t i) const
+	{
+		const int64_t n = *dn;
+		Item it; it.q = q[i]; it.r = r[i]; it.len = l[i]; it.b = b[i]; it.a = 1;
+		if (i + 1 < n && b[i + 1] == it.b) {
+			if (r[i + 1] <= it.r) it.a = 0;
+			else {
+				int32_t len = it.len, ov = (int32_t)(it.r + len - r[i + 1]);
+				if (ov > 0) { len -= ov; if (len <= 0) it.a = 0; }
+				if (it.a && (ov = it.q + len - q[i + 1]) > 0) { len -= ov; if (len <= 0) it.a = 0; }
+				it.len = len;
+			}
+		}
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return it.a; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (valid && it.a) { oq[excl] = it.q; orr[excl] = it.r; ol[excl] = it.len; ob[excl] = it.b; }
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_KILLS] = *dn - (int32_t)total; dc[slot_n] = (int32_t)total; }
+};
 
 __device__ __forceinline__ int64_t contig_end_of(const ContigEnd *ce, int nce, int64_t rpos)
 {
@@ -454,27 +494,40 @@ __device__ __forceinline__ int64_t contig_end_of(const ContigEnd *ce, int nce, i
 	return ce[lo < nce ? lo : nce - 1].end;
 }
 
-// bit0: certain gap break, bit1: contig-span break, bit2: gap needs the similarity test
-__global__ void k_gap_flags(const int32_t *q, const int64_t *r, const int32_t *l, const int32_t *b, const ContigEnd *ce, int nce, uint8_t *flag, uint8_t *need, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint8_t f = 0;
-	if (i > 0 && b[i] == b[i - 1]) {
-		int32_t qg = q[i] - q[i - 1] - l[i - 1], rg = (int32_t)(r[i] - r[i - 1] - l[i - 1]);
-		if (qg > 300 || rg > 300) f |= (qg > GSA_MAX_SEED_GAP || rg > GSA_MAX_SEED_GAP) ? 1 : 4;
-		if (contig_end_of(ce, nce, r[i]) != contig_end_of(ce, nce, r[i - 1])) f |= 2;
+// break-point flags per seed -- bit0: certain gap break, bit1: contig-span break, bit2: gap needs the similarity test -- and
+// the list of the gaps to test
+struct FGapFlags {
+	const int32_t *q; const int64_t *r; const int32_t *l, *b; const ContigEnd *ce; int nce; uint8_t *flag; int32_t *cand, *dc;
+	struct Item { uint8_t f; };
+	__device__ Item load(int64_t i) const
+	{
+		Item it; it.f = 0;
+		if (i > 0 && b[i] == b[i - 1]) {
+			int32_t qg = q[i] - q[i - 1] - l[i - 1], rg = (int32_t)(r[i] - r[i - 1] - l[i - 1]);
+			if (qg > 300 || rg > 300) it.f |= (qg > GSA_MAX_SEED_GAP || rg > GSA_MAX_SEED_GAP) ? 1 : 4;
+			if (contig_end_of(ce, nce, r[i]) != contig_end_of(ce, nce, r[i - 1])) it.f |= 2;
+		}
+		return it;
 	}
-	flag[i] = f; need[i] = (f >> 2) & 1;
-}
+	__device__ unsigned long long value(const Item &it) const { return (it.f >> 2) & 1; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (!valid) return;
+		flag[i] = it.f;
+		if (it.f & 4) cand[excl] = (int32_t)i;
+	}
+	__device__ void finish(unsigned long long total) const { dc[DC_NCAND] = (int32_t)total; }
+};
 
 // CalGapSimilarity (src/KmerAnalysis.cpp:78-121) for the gap in front of seed cand[blockIdx.x]; one warp per gap.
 // hist: ids of CreateKmerVecFromReadSeq are < 2048 (rolling ((id & 0xFF) << 2) + nt with nt in 0..4)
-__global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, const int32_t *q, const int64_t *r, const int32_t *l,
+__global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, const int32_t *d_ncand, const int32_t *q, const int64_t *r, const int32_t *l,
                                                        const unsigned char *seq, DevIndex ix, uint8_t *flag)
 {
 	__shared__ unsigned short h1[2048], h2[2048];
-	int i = cand[blockIdx.x], lane = threadIdx.x;
+	const int lane = threadIdx.x, ncand = *d_ncand;
+	for (int c = blockIdx.x; c < ncand; c += gridDim.x) { // a fixed grid of warps walks the list: its length only exists on the device
+	int i = cand[c];
 	int q1 = q[i - 1] + l[i - 1], q2 = q[i];
 	int64_t r1 = r[i - 1] + l[i - 1], r2 = r[i];
 	int q_len = q2 - q1, r_len = (int)(r2 - r1);
@@ -523,26 +576,46 @@ __global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, cons
 		similar = common > (q_len + r_len) * 0.1;
 	}
 	if (lane == 0 && !similar) flag[i] |= 1;
+	__syncwarp();
+	}
 }
 
-__global__ void k_piece_flags(const int32_t *b, const uint8_t *flag, uint8_t mask, uint8_t *out, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] = i == 0 || b[i] != b[i - 1] || (flag[i] & mask);
-}
 
-__global__ void k_piece_table(const int32_t *starts, int64_t np, int64_t n, const int32_t *q, const int64_t *r, const int32_t *l, const int64_t *S, Piece *out)
+// pieces: maximal runs of seeds between break points (block boundaries and the flags selected by mask); start table + sums
+struct FPiece {
+	const int32_t *b, *l; const uint8_t *flag; uint8_t mask; const int32_t *dn; int32_t *pstart, *psum, *dc; int slot;
+	struct Item { int32_t len; uint8_t f; };
+	__device__ Item load(int64_t i) const
+	{
+		Item it; it.len = l[i];
+		it.f = i == 0 || b[i] != b[i - 1] || (mask && (flag[i] & mask));
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const { return it.f; }
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		int p = valid ? (int)excl + it.f - 1 : 0;
+		if (valid && it.f) pstart[excl] = (int32_t)i;
+		unsigned peers = peers_of(valid ? p : DEAD_KEY);
+		bool leader;
+		int tot = gsa_peer_sum(peers, valid ? it.len : 0, leader);
+		if (leader && valid) atomicAdd(psum + p, tot);
+	}
+	__device__ void finish(unsigned long long total) const { dc[slot] = (int32_t)total; pstart[total] = *dn; }
+};
+
+__global__ void k_piece_table(const int32_t *starts, const int32_t *psum, const int32_t *d_np, const int32_t *q, const int64_t *r, const int32_t *l, Piece *out)
 {
 	int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= np) return;
-	int64_t beg = starts[p], end = p + 1 < np ? starts[p + 1] : n;
-	Piece x; x.beg = beg; x.end = end; x.sumlen = S[end] - S[beg]; x.rf = r[beg]; x.rl = r[end - 1];
+	if (p >= *d_np) return;
+	int64_t beg = starts[p], end = starts[p + 1];
+	Piece x; x.beg = beg; x.end = end; x.sumlen = psum[p]; x.rf = r[beg]; x.rl = r[end - 1];
 	x.qf = q[beg]; x.ql = q[end - 1]; x.lenl = l[end - 1]; x.pad = 0;
 	out[p] = x;
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernels: IdentifyNormalPairs -> fragment list
+// 4. IdentifyNormalPairs -> fragment list (src/ProcessCandidateAlignment.cpp:241-265)
 // ------------------------------------------------------------------------------------------------
 struct NpBlock { int64_t src_beg, dst_beg; int32_t n, pad; };
 
@@ -554,39 +627,34 @@ __device__ __forceinline__ void np_locate(const NpBlock *nb, int nblk, int64_t t
 	k = lo - 1; s = nb[k].src_beg + (t - nb[k].dst_beg);
 }
 
-__global__ void k_np_count(const NpBlock *nb, int nblk, int64_t total, const int32_t *q, const int64_t *r, const int32_t *l, int32_t *cnt)
-{
-	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= total) return;
-	int k; int64_t s; np_locate(nb, nblk, t, k, s);
-	int c = 1;
-	if (t + 1 < nb[k].dst_beg + nb[k].n) { // not the last seed of its block
-		int32_t qg = q[s + 1] - (q[s] + l[s]); int64_t rg = r[s + 1] - (r[s] + l[s]);
-		if (qg > 0 || (int32_t)rg > 0) c = 2;
+struct FNormalPairs {
+	const NpBlock *nb; int nblk; const int32_t *q; const int64_t *r; const int32_t *l; gsa_frag *frag; int32_t *fblk; int64_t *blk_frag_beg; int32_t *dc;
+	struct Item { int32_t k, q, l, qg, rg; int64_t r; uint8_t first; };
+	__device__ Item load(int64_t t) const
+	{
+		Item it; int64_t s;
+		np_locate(nb, nblk, t, it.k, s);
+		it.q = q[s]; it.r = r[s]; it.l = l[s]; it.qg = it.rg = 0; it.first = t == nb[it.k].dst_beg;
+		if (t + 1 < nb[it.k].dst_beg + nb[it.k].n) { // not the last seed of its block
+			it.qg = q[s + 1] - (it.q + it.l); it.rg = (int32_t)(r[s + 1] - (it.r + it.l));
+		}
+		return it;
 	}
-	cnt[t] = c;
-}
-
-__global__ void k_np_write(const NpBlock *nb, int nblk, int64_t total, const int32_t *q, const int64_t *r, const int32_t *l, const int32_t *off,
-                           gsa_frag *frag, int32_t *fblk, int64_t *blk_frag_beg)
-{
-	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= total) return;
-	int k; int64_t s; np_locate(nb, nblk, t, k, s);
-	int64_t o = off[t];
-	if (t == nb[k].dst_beg) blk_frag_beg[k] = o;
-	gsa_frag f; f.rPos = r[s]; f.qPos = q[s]; f.qLen = l[s]; f.rLen = l[s]; f.bSeed = 1; f.aln_off = 0; f.aln_len = l[s]; f.reserved = 0;
-	frag[o] = f; fblk[o] = k;
-	if (t + 1 < nb[k].dst_beg + nb[k].n) {
-		int32_t qg = q[s + 1] - (q[s] + l[s]); int32_t rg = (int32_t)(r[s + 1] - (r[s] + l[s]));
-		if (qg < 0) qg = 0;
-		if (rg < 0) rg = 0;
-		if (qg > 0 || rg > 0) {
-			gsa_frag g; g.rPos = r[s] + l[s]; g.qPos = q[s] + l[s]; g.qLen = qg; g.rLen = rg; g.bSeed = 0; g.aln_off = 0; g.aln_len = 0; g.reserved = 0;
-			frag[o + 1] = g; fblk[o + 1] = k;
+	__device__ unsigned long long value(const Item &it) const { return (it.qg > 0 || it.rg > 0) ? 2 : 1; }
+	__device__ void emit(int64_t t, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (!valid) return;
+		const int64_t o = (int64_t)excl;
+		if (it.first) blk_frag_beg[it.k] = o;
+		gsa_frag f; f.rPos = it.r; f.qPos = it.q; f.qLen = it.l; f.rLen = it.l; f.bSeed = 1; f.aln_off = 0; f.aln_len = it.l; f.reserved = 0;
+		frag[o] = f; fblk[o] = it.k;
+		if (it.qg > 0 || it.rg > 0) {
+			gsa_frag g; g.rPos = it.r + it.l; g.qPos = it.q + it.l; g.qLen = max(it.qg, 0); g.rLen = max(it.rg, 0); g.bSeed = 0; g.aln_off = 0; g.aln_len = 0; g.reserved = 0;
+			frag[o + 1] = g; fblk[o + 1] = it.k;
 		}
 	}
-}
+	__device__ void finish(unsigned long long total) const { dc[DC_NFR] = (int32_t)total; }
+};
 
 // ------------------------------------------------------------------------------------------------
 // host driver
@@ -598,20 +666,32 @@ static BlockHdr hdr_from_piece(const Piece &p, int32_t score)
 	return b;
 }
 
-static int fetch_pieces(gsa_ctx *ctx, Ws &ws, const int32_t *cb, const uint8_t *gflag, uint8_t mask, int64_t n, const int32_t *q, const int64_t *r, const int32_t *l,
-                        const int64_t *S, uint8_t *pflag, int32_t *pstart, int32_t *d_cnt, std::vector<Piece> &out)
+#define PIECE_FIRST 4096   // piece-table entries copied to the host before their count is known
+
+struct PieceTable { Piece *d = nullptr; int slot = 0; };
+
+// queues the piece table of (q, r, l, b) under `mask`: one chain + one table kernel; nothing comes to the host yet
+static int queue_pieces(gsa_ctx *ctx, Ws &ws, Chains &ch, int32_t *dc, const int32_t *dn, int64_t bound, const int32_t *q, const int64_t *r, const int32_t *l,
+                        const int32_t *b, const uint8_t *gflag, uint8_t mask, int slot, PieceTable &pt)
 {
-	LAUNCH(k_piece_flags, n, cb, gflag, mask, pflag, n);
-	GSA_TRY(select_indices(ctx, pflag, pstart, d_cnt, n));
-	int64_t np = 0;
-	GSA_TRY(read_count(ctx, d_cnt, &np));
+	int32_t *pstart = ws.get<int32_t>(bound + 2), *psum = ws.get<int32_t>(bound + 2);
+	pt.d = ws.get<Piece>(bound + 1); pt.slot = slot;
+	if (ws.rc) return ws.rc;
+	CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, (size_t)(bound + 2) * 4, ctx->stream));
+	FPiece f; f.b = b; f.l = l; f.flag = gflag; f.mask = mask; f.dn = dn; f.pstart = pstart; f.psum = psum; f.dc = dc; f.slot = slot;
+	GSA_TRY(run_chain(ctx, ch, f, dn, bound));
+	LAUNCH(k_piece_table, bound, pstart, psum, dc + slot, q, r, l, pt.d);
+	return GSA_OK;
+}
+
+// after a synchronisation that brought dc[] to the host: the table itself (the first PIECE_FIRST entries were prefetched)
+static int fetch_piece_table(gsa_ctx *ctx, const PieceTable &pt, int64_t np, const Piece *prefetched, std::vector<Piece> &out)
+{
 	out.resize((size_t)np);
 	if (np == 0) return GSA_OK;
-	Piece *d_p = ws.get<Piece>(np);
-	if (!d_p) return ws.rc;
-	LAUNCH(k_piece_table, np, pstart, np, n, q, r, l, S, d_p);
+	if (np <= PIECE_FIRST) { memcpy(out.data(), prefetched, (size_t)np * sizeof(Piece)); return GSA_OK; }
 	GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, (size_t)np * sizeof(Piece)));
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_p, (size_t)np * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage.p, pt.d, (size_t)np * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	memcpy(out.data(), ctx->h_stage.p, (size_t)np * sizeof(Piece));
 	return GSA_OK;
@@ -623,250 +703,210 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 	const gsa_params &P = ctx->prm;
 	for (auto &v : ctx->blocks_stage) v.clear();
 	ctx->final_blocks.clear(); ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->n_s0 = 0;
-	int64_t n = ctx->n_seeds;
+	const int64_t n = ctx->n_seeds;
 	if (n >= 0x7FFFFFF0ll) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_cluster: more than 2^31 seeds in one contig");
 	if (n == 0) return GSA_OK;
 	const int32_t *sq = (const int32_t *)ctx->d_sq.p; const int64_t *sr = (const int64_t *)ctx->d_sr.p; const int32_t *sl = (const int32_t *)ctx->d_sl.p;
-	int32_t *d_cnt = (int32_t *)ctx->d_counter.p + 8; // a few device counters
-
-	// ---- 1. diagonal groups over the (PosDiff,qPos)-sorted seeds; drop groups below MinAlnBlockScore -------------------
-	int32_t *gflag = ws.get<int32_t>(n), *gid1 = ws.get<int32_t>(n);
-	uint8_t *keep = ws.get<uint8_t>(n);
-	int32_t *kidx = ws.get<int32_t>(n);
-	if (ws.rc) return ws.rc;
-	LAUNCH(k_group_flags, n, sq, sr, gflag, n, P.max_indel);
-	GSA_TRY(scan_inclusive(ctx, gflag, gid1, n));
-	int64_t ngroups = 0;
-	GSA_TRY(read_count(ctx, gid1 + (n - 1), &ngroups));
-	unsigned long long *gscore = ws.get<unsigned long long>(ngroups);
-	if (ws.rc) return ws.rc;
-	CUDA_TRY(ctx, cudaMemsetAsync(gscore, 0, (size_t)ngroups * 8, ctx->stream));
-	LAUNCH(k_group_score, n, gid1, sl, gscore, n);
-	LAUNCH(k_group_keep, n, gid1, gscore, keep, n, P.min_block_score);
-	GSA_TRY(select_indices(ctx, keep, kidx, d_cnt, n));
-	int64_t n2 = 0;
-	GSA_TRY(read_count(ctx, d_cnt, &n2));
-	if (n2 == 0) return GSA_OK;
-
-	// ---- 2. per-group order (qPos, rPos): stable radix sort on (group, qPos) ---------------------------------------------
-	uint64_t *key_in = ws.get<uint64_t>(n2), *key_out = ws.get<uint64_t>(n2);
-	int32_t *val_out = ws.get<int32_t>(n2);
-	int32_t *q2 = ws.get<int32_t>(n2 + 1), *l2 = ws.get<int32_t>(n2 + 1), *g2 = ws.get<int32_t>(n2 + 1);
-	int64_t *r2 = ws.get<int64_t>(n2 + 1);
-	if (ws.rc) return ws.rc;
-	LAUNCH(k_group_keys, n2, kidx, gid1, sq, key_in, n2);
+	GSA_TRY(gsa_ensure(ctx, ctx->d_counter, 4096));
+	int32_t *dc = (int32_t *)ctx->d_counter.p + 512; // byte 2048 onwards: the K2 counters
+	Chains ch;
+	ch.tiles = chain_tiles(n + 2);
 	{
-		int gbits = 1; while ((1ll << gbits) < ngroups + 1) gbits++;
+		const size_t words = (size_t)K2_CHAINS * 2 + (size_t)K2_CHAINS * ch.tiles; // tickets (u32, padded to u64) + totals + status
+		GSA_TRY(gsa_ensure(ctx, ctx->d_chain, words * 8));
+		CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_chain.p, 0, words * 8, ctx->stream));
+		ch.ticket = (unsigned int *)ctx->d_chain.p;
+		ch.total = (unsigned long long *)ctx->d_chain.p + K2_CHAINS;
+		ch.status = ch.total + K2_CHAINS;
+	}
+	k_k2_init<<<1, 64, 0, ctx->stream>>>(dc, (int32_t)n);
+	KERNEL_CHECK(ctx);
+
+	// ---- 1. diagonal groups over the (PosDiff,qPos)-sorted seeds; drop groups below MinAlnBlockScore; per-group order --------
+	int32_t *gid1 = ws.get<int32_t>(n + 2);
+	unsigned long long *gscore = ws.get<unsigned long long>(n + 2);
+	uint64_t *key_in = ws.get<uint64_t>(n + 2), *key_out = ws.get<uint64_t>(n + 2);
+	int32_t *val_in = ws.get<int32_t>(n + 2), *val_out = ws.get<int32_t>(n + 2);
+	if (ws.rc) return ws.rc;
+	CUDA_TRY(ctx, cudaMemsetAsync(gscore, 0, (size_t)(n + 2) * 8, ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(key_in, 0xFF, (size_t)(n + 2) * 8, ctx->stream)); // dropped seeds sort behind every kept one
+	{ FGroup f; f.q = sq; f.r = sr; f.l = sl; f.gid1 = gid1; f.gscore = gscore; f.dc = dc; f.max_indel = P.max_indel; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N0, n)); }
+	int qbits = 1, gbits = 1;
+	while ((1ull << qbits) < (uint64_t)ctx->qlen) qbits++;
+	while ((1ll << gbits) < n + 1) gbits++;
+	{ FKeep f; f.q = sq; f.gid1 = gid1; f.gscore = gscore; f.key = key_in; f.val = val_in; f.dc = dc; f.min_score = P.min_block_score; f.qbits = qbits; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N0, n)); }
+	{
 		size_t bytes = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, kidx, val_out, (int)n2, 0, 32 + gbits, ctx->stream);
+		cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, val_in, val_out, n, 0, qbits + gbits, ctx->stream);
 		GSA_TRY(gsa_ensure(ctx, ctx->d_cub, bytes));
-		CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, bytes, key_in, key_out, kidx, val_out, (int)n2, 0, 32 + gbits, ctx->stream));
-		ctx->tm.launches += 4;
+		CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, bytes, key_in, key_out, val_in, val_out, n, 0, qbits + gbits, ctx->stream));
+		ctx->tm.launches += 2 + (qbits + gbits + 7) / 8;
 	}
-	LAUNCH(k_gather_seeds, n2, val_out, sq, sr, sl, gid1, q2, r2, l2, g2, n2);
-
-	// dense group ids + group start table
-	uint8_t *f8 = ws.get<uint8_t>(n2 + 1);
-	int32_t *gstart = ws.get<int32_t>(n2 + 2), *dg = ws.get<int32_t>(n2 + 1);
+	int32_t *q2 = ws.get<int32_t>(n + 2), *l2 = ws.get<int32_t>(n + 2), *dg = ws.get<int32_t>(n + 2), *gstart = ws.get<int32_t>(n + 3);
+	int64_t *r2 = ws.get<int64_t>(n + 2);
 	if (ws.rc) return ws.rc;
-	LAUNCH(k_seg_flags, n2, g2, f8, n2);
-	GSA_TRY(select_indices(ctx, f8, gstart, d_cnt + 1, n2));
-	int64_t ng2 = 0;
-	GSA_TRY(read_count(ctx, d_cnt + 1, &ng2));
-	LAUNCH(k_fill_i32, 1, gstart + ng2, (int32_t)n2, 1);
-	LAUNCH(k_seg_ids, n2, gstart, d_cnt + 1, dg, n2);
-	GroupView gv; gv.q = q2; gv.r = r2; gv.l = l2; gv.dg = dg; gv.gstart = gstart; gv.n = n2;
+	{ FSeg f; f.val = val_out; f.gid1 = gid1; f.q = sq; f.r = sr; f.l = sl; f.oq = q2; f.orr = r2; f.ol = l2; f.dg = dg; f.gstart = gstart; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N2, n)); }
+	GroupView gv; gv.q = q2; gv.r = r2; gv.l = l2; gv.dg = dg; gv.gstart = gstart; gv.dn = dc + DC_N2;
 
-	// ---- 3. outlier windows ----------------------------------------------------------------------------------------------
-	int32_t *uq = ws.get<int32_t>(n2 + 1), *U = ws.get<int32_t>(n2 + 1);
-	uint8_t *cand = ws.get<uint8_t>(n2 + 1);
-	int32_t *C = ws.get<int32_t>(n2 + 1);
-	int32_t *nxtA = ws.get<int32_t>(n2 + 1), *nxtB = ws.get<int32_t>(n2 + 1), *reach = ws.get<int32_t>(n2 + 1), *wid1 = ws.get<int32_t>(n2 + 1);
+	// ---- 2. outlier windows --------------------------------------------------------------------------------------------------------
+	int32_t *uq = ws.get<int32_t>(n + 2), *U = ws.get<int32_t>(n + 2), *C = ws.get<int32_t>(n + 2);
+	uint8_t *cand = ws.get<uint8_t>(n + 2);
+	int32_t *nxtA = ws.get<int32_t>(n + 2), *nxtB = ws.get<int32_t>(n + 2), *reach = ws.get<int32_t>(n + 2), *wid1 = ws.get<int32_t>(n + 2);
 	if (ws.rc) return ws.rc;
-	LAUNCH(k_uniq, n2, gv, uq);
-	GSA_TRY(scan_inclusive(ctx, uq, U, n2));
-	LAUNCH(k_cand, n2, gv, uq, cand);
-	GSA_TRY(select_indices(ctx, cand, C, d_cnt + 2, n2));
-	LAUNCH(k_next, n2 + 1, gv, uq, U, cand, C, d_cnt + 2, nxtA);
-	LAUNCH(k_reach_init, n2 + 1, gv, reach);
+	{ FUniq f; f.v = gv; f.uq = uq; f.U = U; f.cand = cand; f.C = C; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N2, n)); }
+	LAUNCH(k_next, n + 1, gv, uq, U, cand, C, dc + DC_NC, nxtA, reach);
 	{
-		int rounds = 1; while ((1ll << rounds) < n2 / 30 + 2) rounds++;
-		for (int k = 0; k <= rounds; k++) { LAUNCH(k_jump, n2 + 1, reach, nxtA, nxtB, n2); std::swap(nxtA, nxtB); }
+		int rounds = 1; while ((1ll << rounds) < n / 30 + 2) rounds++;
+		for (int k = 0; k <= rounds; k++) { LAUNCH(k_jump, n + 1, reach, nxtA, nxtB, dc + DC_N2); std::swap(nxtA, nxtB); }
 	}
-	GSA_TRY(scan_inclusive(ctx, reach, wid1, n2));
-
 	// per-window histogram of PosDiff>>4 over unique seeds -> mode, average, outlier kill
-	int64_t hsize = 1024; while (hsize < 2 * n2) hsize <<= 1;
+	int64_t hsize = 1024; while (hsize < 2 * n) hsize <<= 1;
 	unsigned long long *hkeys = ws.get<unsigned long long>(hsize);
-	int32_t *hcnt = ws.get<int32_t>(hsize), *slot_of = ws.get<int32_t>(n2);
-	unsigned long long *wbest = ws.get<unsigned long long>(n2), *wsum = ws.get<unsigned long long>(n2);
-	int32_t *wcnt = ws.get<int32_t>(n2);
-	uint8_t *alive = ws.get<uint8_t>(n2 + 1);
+	int32_t *hcnt = ws.get<int32_t>(hsize), *slot_of = ws.get<int32_t>(n + 2);
+	unsigned long long *wbest = ws.get<unsigned long long>(n + 2), *wsum = ws.get<unsigned long long>(n + 2);
+	int32_t *wcnt = ws.get<int32_t>(n + 2), *LU = ws.get<int32_t>(n + 2);
+	uint8_t *alive = ws.get<uint8_t>(n + 2);
 	if (ws.rc) return ws.rc;
 	CUDA_TRY(ctx, cudaMemsetAsync(hkeys, 0xFF, (size_t)hsize * 8, ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(hcnt, 0, (size_t)hsize * 4, ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(wbest, 0, (size_t)n2 * 8, ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(wsum, 0, (size_t)n2 * 8, ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(wcnt, 0, (size_t)n2 * 4, ctx->stream));
-	LAUNCH(k_hist_insert, n2, gv, uq, wid1, hkeys, hcnt, slot_of, (uint32_t)(hsize - 1));
+	CUDA_TRY(ctx, cudaMemsetAsync(wbest, 0, (size_t)(n + 2) * 8, ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(wsum, 0, (size_t)(n + 2) * 8, ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(wcnt, 0, (size_t)(n + 2) * 4, ctx->stream));
+	{ FWin f; f.v = gv; f.uq = uq; f.reach = reach; f.wid1 = wid1; f.keys = hkeys; f.cnt = hcnt; f.slot_of = slot_of; f.hmask = (uint32_t)(hsize - 1); GSA_TRY(run_chain(ctx, ch, f, dc + DC_N2, n)); }
 	LAUNCH(k_win_best, hsize, hkeys, hcnt, wbest, hsize);
-	LAUNCH(k_win_sum, n2, gv, uq, wid1, wbest, wsum, wcnt);
-	LAUNCH(k_outlier_kill, n2, gv, uq, wid1, wbest, wsum, wcnt, hcnt, slot_of, alive, ctx->N, P.max_indel);
+	LAUNCH(k_win_sum, n, gv, uq, wid1, wbest, wsum, wcnt);
+	{ FOutlier f; f.v = gv; f.uq = uq; f.wid1 = wid1; f.best = wbest; f.sum = wsum; f.cntk = wcnt; f.cnt = hcnt; f.slot_of = slot_of; f.alive = alive; f.LU = LU; f.dc = dc;
+	  f.genome = ctx->N; f.max_indel = P.max_indel; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N2, n)); }
+	// multi-hit runs
+	LAUNCH(k_runs, n, gv, LU, dc + DC_NLU, alive, ctx->N, P.max_indel);
 
-	// ---- 4. multi-hit runs ------------------------------------------------------------------------------------------------
-	int32_t *LU = ws.get<int32_t>(n2 + 1);
+	// ---- 3. compact, noise filter + compact, cut groups into blocks, AddAlnBlock acceptance -----------------------------------------
+	int32_t *q3 = ws.get<int32_t>(n + 2), *l3 = ws.get<int32_t>(n + 2), *g3 = ws.get<int32_t>(n + 2);
+	int64_t *r3 = ws.get<int64_t>(n + 2);
 	if (ws.rc) return ws.rc;
-	LAUNCH(k_live_unique, n2, uq, alive, f8, n2);
-	GSA_TRY(select_indices(ctx, f8, LU, d_cnt + 3, n2));
-	LAUNCH(k_runs, n2, gv, LU, d_cnt + 3, alive, ctx->N, P.max_indel);
-
-	// ---- 5. compact, noise filter, compact ------------------------------------------------------------------------------------
-	int32_t *idx3 = ws.get<int32_t>(n2 + 1);
-	if (ws.rc) return ws.rc;
-	GSA_TRY(select_indices(ctx, alive, idx3, d_cnt + 4, n2));
-	int64_t n3 = 0;
-	GSA_TRY(read_count(ctx, d_cnt + 4, &n3));
-	if (n3 == 0) return GSA_OK;
-	int32_t *q3 = ws.get<int32_t>(n3 + 1), *l3 = ws.get<int32_t>(n3 + 1), *g3 = ws.get<int32_t>(n3 + 1);
-	int64_t *r3 = ws.get<int64_t>(n3 + 1);
-	uint8_t *alive3 = ws.get<uint8_t>(n3 + 1);
-	int32_t *idx4 = ws.get<int32_t>(n3 + 1);
-	if (ws.rc) return ws.rc;
-	LAUNCH(k_gather_seeds, n3, idx3, q2, r2, l2, dg, q3, r3, l3, g3, n3);
-	LAUNCH(k_noise, n3, q3, r3, g3, alive3, n3);
-	GSA_TRY(select_indices(ctx, alive3, idx4, d_cnt + 5, n3));
-	int64_t n4 = 0;
-	GSA_TRY(read_count(ctx, d_cnt + 5, &n4));
-	if (n4 == 0) return GSA_OK;
-	// reuse the n2-sized arrays for the n4 generation (n4 <= n3 <= n2)
-	int32_t *q4 = q2, *l4 = l2, *g4 = g2; int64_t *r4 = r2;
-	LAUNCH(k_gather_seeds, n4, idx4, q3, r3, l3, g3, q4, r4, l4, g4, n4);
-
-	// ---- 6. cut groups into blocks, AddAlnBlock acceptance ------------------------------------------------------------------------
-	int32_t *bid = uq, *bstart = C; // reuse n2-sized scratch
-	int64_t *len64 = ws.get<int64_t>(n4 + 2), *S = ws.get<int64_t>(n4 + 2);
-	if (ws.rc) return ws.rc;
-	LAUNCH(k_cut, n4, q4, r4, l4, g4, f8, n4);
-	GSA_TRY(select_indices(ctx, f8, bstart, d_cnt + 6, n4));
-	int64_t nb0 = 0;
-	GSA_TRY(read_count(ctx, d_cnt + 6, &nb0));
-	LAUNCH(k_seg_ids, n4, bstart, d_cnt + 6, bid, n4);
-	LAUNCH(k_len64, n4 + 1, l4, len64, n4);
-	GSA_TRY(scan_exclusive(ctx, len64, S, n4 + 1));
-	int32_t *bscore = ws.get<int32_t>(nb0 + 1), *acc32 = ws.get<int32_t>(nb0 + 1), *newid1 = ws.get<int32_t>(nb0 + 1);
-	uint8_t *accept = ws.get<uint8_t>(nb0 + 1);
-	if (ws.rc) return ws.rc;
-	LAUNCH(k_block_eval, nb0, bstart, nb0, n4, q4, l4, S, bscore, accept, P.min_block_score, P.min_aln_len);
-	LAUNCH(k_widen, nb0, accept, acc32, nb0);
-	GSA_TRY(scan_inclusive(ctx, acc32, newid1, nb0));
-	LAUNCH(k_seed_accept, n4, bid, accept, f8, n4);
-	int32_t *idx5 = idx3;
-	GSA_TRY(select_indices(ctx, f8, idx5, d_cnt + 7, n4));
-	int64_t n5 = 0;
-	GSA_TRY(read_count(ctx, d_cnt + 7, &n5));
-	if (n5 == 0) return GSA_OK;
+	{ FCompact f; f.alive = alive; f.q = q2; f.r = r2; f.l = l2; f.g = dg; f.oq = q3; f.orr = r3; f.ol = l3; f.og = g3; f.dc = dc; f.slot = DC_N3; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N2, n)); }
+	// the n2 generation is dead from here on: its arrays carry the n4 generation
+	int32_t *q4 = q2, *l4 = l2, *g4 = uq; int64_t *r4 = r2;
+	{ FNoise f; f.q = q3; f.r = r3; f.l = l3; f.g = g3; f.dn = dc + DC_N3; f.oq = q4; f.orr = r4; f.ol = l4; f.og = g4; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N3, n)); }
+	int32_t *bid = U, *bstart = C, *bscore = wcnt, *newid1 = nxtA, *kept_score = nxtB; uint8_t *accept = cand;
+	CUDA_TRY(ctx, cudaMemsetAsync(bscore, 0, (size_t)(n + 2) * 4, ctx->stream));
+	{ FCut f; f.q = q4; f.r = r4; f.l = l4; f.g = g4; f.bid = bid; f.bstart = bstart; f.bscore = bscore; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N4, n)); }
+	{ FBlockEval f; f.bstart = bstart; f.q = q4; f.l = l4; f.bscore = bscore; f.accept = accept; f.newid1 = newid1; f.kept_score = kept_score; f.dc = dc;
+	  f.min_score = P.min_block_score; f.min_len = P.min_aln_len; GSA_TRY(run_chain(ctx, ch, f, dc + DC_NB0, n)); }
 	// the working set of the remaining phases lives in the context (K3 and the dump hooks read it)
-	GSA_TRY(gsa_ensure(ctx, ctx->d_cq, (size_t)(n5 + 1) * 4)); GSA_TRY(gsa_ensure(ctx, ctx->d_cr, (size_t)(n5 + 1) * 8));
-	GSA_TRY(gsa_ensure(ctx, ctx->d_cl, (size_t)(n5 + 1) * 4)); GSA_TRY(gsa_ensure(ctx, ctx->d_cb, (size_t)(n5 + 1) * 4));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_cq, (size_t)(n + 2) * 4)); GSA_TRY(gsa_ensure(ctx, ctx->d_cr, (size_t)(n + 2) * 8));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_cl, (size_t)(n + 2) * 4)); GSA_TRY(gsa_ensure(ctx, ctx->d_cb, (size_t)(n + 2) * 4));
 	int32_t *cq = (int32_t *)ctx->d_cq.p, *cl = (int32_t *)ctx->d_cl.p, *cb = (int32_t *)ctx->d_cb.p; int64_t *cr = (int64_t *)ctx->d_cr.p;
-	LAUNCH(k_gather_block_seeds, n5, idx5, q4, r4, l4, bid, newid1, cq, cr, cl, cb, n5);
+	{ FSeedAccept f; f.bid = bid; f.accept = accept; f.newid1 = newid1; f.q = q4; f.r = r4; f.l = l4; f.oq = cq; f.orr = cr; f.ol = cl; f.ob = cb; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N4, n)); }
 
-	// level-0 piece table = the candidate blocks in the reference's -t 1 push order (group order, then qPos order)
-	uint8_t *gapf = ws.get<uint8_t>(n5 + 1), *need = ws.get<uint8_t>(n5 + 1), *pflag = ws.get<uint8_t>(n5 + 1);
-	int32_t *pstart = ws.get<int32_t>(n5 + 2);
-	int64_t *S5 = ws.get<int64_t>(n5 + 2);
-	if (ws.rc) return ws.rc;
-	LAUNCH(k_len64, n5 + 1, cl, len64, n5);
-	GSA_TRY(scan_exclusive(ctx, len64, S5, n5 + 1));
-	CUDA_TRY(ctx, cudaMemsetAsync(gapf, 0, (size_t)n5, ctx->stream));
+	int32_t *hc = (int32_t *)ctx->h_small.p;                       // dc[] on the host after a synchronisation
+	Piece *h_first = (Piece *)((char *)ctx->h_small.p + 4096);       // 3 x PIECE_FIRST prefetched piece-table entries
+	static_assert(4096 + 3 * PIECE_FIRST * sizeof(Piece) <= (1u << 20), "h_small too small for the prefetched piece tables");
 	std::vector<Piece> pc0, pc1, pc2;
-	GSA_TRY(fetch_pieces(ctx, ws, cb, gapf, 0, n5, cq, cr, cl, S5, pflag, pstart, d_cnt + 8, pc0));
 	std::vector<BlockHdr> vec;
-	vec.reserve(pc0.size());
-	for (const Piece &p : pc0) vec.push_back(hdr_from_piece(p, (int32_t)p.sumlen)); // score = sum of seed lengths (AddAlnBlock :36)
-	if (ctx->keep_dumps) {
-		ctx->blocks_stage[0] = vec; ctx->n_s0 = n5;
-		GSA_TRY(gsa_ensure(ctx, ctx->d_s0q, (size_t)n5 * 4)); GSA_TRY(gsa_ensure(ctx, ctx->d_s0r, (size_t)n5 * 8)); GSA_TRY(gsa_ensure(ctx, ctx->d_s0l, (size_t)n5 * 4));
+	std::vector<int32_t> scores;
+	if (ctx->keep_dumps) { // stage 0 = the candidate blocks in the reference's -t 1 push order (group order, then qPos order), before RemoveOverlaps
+		PieceTable pl0;
+		GSA_TRY(queue_pieces(ctx, ws, ch, dc, dc + DC_N5, n, cq, cr, cl, cb, nullptr, 0, DC_NPL0, pl0));
+		CUDA_TRY(ctx, cudaMemcpyAsync(hc, dc, DC_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(h_first, pl0.d, (size_t)std::min<int64_t>(PIECE_FIRST, n + 1) * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		const int64_t n5 = hc[DC_N5];
+		GSA_TRY(fetch_piece_table(ctx, pl0, hc[DC_NPL0], h_first, pc0));
+		for (const Piece &p : pc0) ctx->blocks_stage[0].push_back(hdr_from_piece(p, (int32_t)p.sumlen)); // score = sum of seed lengths (AddAlnBlock :36)
+		ctx->n_s0 = n5;
+		GSA_TRY(gsa_ensure(ctx, ctx->d_s0q, (size_t)(n5 + 1) * 4)); GSA_TRY(gsa_ensure(ctx, ctx->d_s0r, (size_t)(n5 + 1) * 8)); GSA_TRY(gsa_ensure(ctx, ctx->d_s0l, (size_t)(n5 + 1) * 4));
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_s0q.p, cq, (size_t)n5 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_s0r.p, cr, (size_t)n5 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_s0l.p, cl, (size_t)n5 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
 	}
 
-	// ---- 7. RemoveOverlaps: elementwise passes + compaction until nothing dies ------------------------------------------------------
-	int64_t n6 = n5;
-	{
-		int32_t *tq = q3, *tl = l3, *tb = g3; int64_t *tr = r3; // n3-sized scratch (n5 <= n3)
-		uint8_t *al = alive;
-		for (int pass = 0; pass < 1000; pass++) {
-			CUDA_TRY(ctx, cudaMemsetAsync(d_cnt + 9, 0, 4, ctx->stream));
-			LAUNCH(k_overlap_pass, n6, cq, cr, cl, cb, al, d_cnt + 9, n6);
-			int64_t kills = 0;
-			GSA_TRY(read_count(ctx, d_cnt + 9, &kills));
-			if (kills == 0) break;
-			GSA_TRY(select_indices(ctx, al, idx5, d_cnt + 10, n6));
-			int64_t m = n6 - kills;
-			LAUNCH(k_gather_seeds, m, idx5, cq, cr, cl, cb, tq, tr, tl, tb, m);
-			CUDA_TRY(ctx, cudaMemcpyAsync(cq, tq, (size_t)m * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-			CUDA_TRY(ctx, cudaMemcpyAsync(cr, tr, (size_t)m * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-			CUDA_TRY(ctx, cudaMemcpyAsync(cl, tl, (size_t)m * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-			CUDA_TRY(ctx, cudaMemcpyAsync(cb, tb, (size_t)m * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-			n6 = m;
-		}
-	}
-	ctx->n_cseeds = n6;
-	LAUNCH(k_len64, n6 + 1, cl, len64, n6);
-	GSA_TRY(scan_exclusive(ctx, len64, S5, n6 + 1));
-	CUDA_TRY(ctx, cudaMemsetAsync(gapf, 0, (size_t)n6, ctx->stream));
-	// blocks keep their push order and their pre-overlap score; only the ranges move
-	GSA_TRY(fetch_pieces(ctx, ws, cb, gapf, 0, n6, cq, cr, cl, S5, pflag, pstart, d_cnt + 8, pc0));
-	if (pc0.size() != vec.size()) return gsa_fail(ctx, GSA_ERR_CUDA, "gsa_cluster: block count changed in RemoveOverlaps (%zu -> %zu)", vec.size(), pc0.size());
-	for (size_t i = 0; i < vec.size(); i++) { int32_t sc = vec[i].score; vec[i] = hdr_from_piece(pc0[i], sc); }
-	if (ctx->keep_dumps) ctx->blocks_stage[1] = vec;
-
-	// ---- 8. gap and contig-span break points -> piece tables -> host split logic ---------------------------------------------------------
-	LAUNCH(k_gap_flags, n6, cq, cr, cl, cb, (const ContigEnd *)ctx->d_cend.p, (int)ctx->cend.size(), gapf, need, n6);
-	GSA_TRY(select_indices(ctx, need, idx5, d_cnt + 11, n6));
-	int64_t ncand = 0;
-	GSA_TRY(read_count(ctx, d_cnt + 11, &ncand));
-	if (ncand > 0) {
-		k_gap_similarity<<<(unsigned)ncand, 32, 0, ctx->stream>>>(idx5, cq, cr, cl, (const unsigned char *)ctx->d_seq.p, ctx->ix, gapf);
+	// ---- 4. RemoveOverlaps: two passes queued blindly (survivors ping-pong between the context arrays and scratch); the rare
+	// contig that still loses seeds in the second pass continues pass pair by pass pair below -----------------------------------------
+	int32_t *tq = q3, *tl = l3, *tb = g3; int64_t *tr = r3;
+	uint8_t *gapf = alive;
+	int32_t *gcand = reach;
+	PieceTable pt0, pt1, pt2;
+	for (int round = 0;; round++) {
+		{ FOverlap f; f.q = cq; f.r = cr; f.l = cl; f.b = cb; f.dn = dc + (round == 0 ? DC_N5 : DC_N6); f.oq = tq; f.orr = tr; f.ol = tl; f.ob = tb; f.dc = dc; f.slot_n = DC_N6A;
+		  if (round > 0) { // every earlier chain has run (the host waited): all chain states are free again
+			  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_chain.p, 0, ((size_t)K2_CHAINS * 2 + (size_t)K2_CHAINS * ch.tiles) * 8, ctx->stream));
+			  ch.used = 0;
+		  }
+		  GSA_TRY(run_chain(ctx, ch, f, f.dn, n)); }
+		{ FOverlap f; f.q = tq; f.r = tr; f.l = tl; f.b = tb; f.dn = dc + DC_N6A; f.oq = cq; f.orr = cr; f.ol = cl; f.ob = cb; f.dc = dc; f.slot_n = DC_N6; GSA_TRY(run_chain(ctx, ch, f, f.dn, n)); }
+		// ---- 5. gap and contig-span break points, piece tables ----------------------------------------------------------------------
+		Ws ws2 = ws; // the piece scratch of a repeated round reuses the same slots
+		{ FGapFlags f; f.q = cq; f.r = cr; f.l = cl; f.b = cb; f.ce = (const ContigEnd *)ctx->d_cend.p; f.nce = (int)ctx->cend.size(); f.flag = gapf; f.cand = gcand; f.dc = dc;
+		  GSA_TRY(run_chain(ctx, ch, f, dc + DC_N6, n)); }
+		k_gap_similarity<<<1184, 32, 0, ctx->stream>>>(gcand, dc + DC_NCAND, cq, cr, cl, (const unsigned char *)ctx->d_seq.p, ctx->ix, gapf);
 		KERNEL_CHECK(ctx);
+		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 0, DC_NP0, pt0)); // blocks keep their push order; only the ranges moved
+		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 1, DC_NP1, pt1));
+		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 3, DC_NP2, pt2));
+		const int64_t first = std::min<int64_t>(PIECE_FIRST, n + 1);
+		CUDA_TRY(ctx, cudaMemcpyAsync(hc, dc, DC_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(h_first, pt0.d, (size_t)first * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(h_first + PIECE_FIRST, pt1.d, (size_t)first * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(h_first + 2 * PIECE_FIRST, pt2.d, (size_t)first * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
+		if (round == 0) {
+			GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, (size_t)first * 4));
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage.p, kept_score, (size_t)first * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // ---- first wait of the phase
+		if (round == 0) {
+			const int64_t nb1 = hc[DC_NB1];
+			scores.resize((size_t)nb1);
+			if (nb1 <= first) memcpy(scores.data(), ctx->h_stage.p, (size_t)nb1 * 4);
+			else CUDA_TRY(ctx, cudaMemcpy(scores.data(), kept_score, (size_t)nb1 * 4, cudaMemcpyDeviceToHost));
+		}
+		if (hc[DC_KILLS] == 0 || round > 500) break;
 	}
-	GSA_TRY(fetch_pieces(ctx, ws, cb, gapf, 1, n6, cq, cr, cl, S5, pflag, pstart, d_cnt + 8, pc1));
-	GSA_TRY(fetch_pieces(ctx, ws, cb, gapf, 3, n6, cq, cr, cl, S5, pflag, pstart, d_cnt + 8, pc2));
+	const int64_t n6 = hc[DC_N6];
+	ctx->n_cseeds = n6;
+	if (hc[DC_N5] == 0 || n6 == 0) return GSA_OK;
+	GSA_TRY(fetch_piece_table(ctx, pt0, hc[DC_NP0], h_first, pc0));
+	if (pc0.size() != scores.size()) return gsa_fail(ctx, GSA_ERR_CUDA, "gsa_cluster: block count changed in RemoveOverlaps (%zu -> %zu)", scores.size(), pc0.size());
+	vec.reserve(pc0.size());
+	for (size_t i = 0; i < pc0.size(); i++) vec.push_back(hdr_from_piece(pc0[i], scores[i])); // blocks keep their pre-overlap score
+	if (ctx->keep_dumps) ctx->blocks_stage[1] = vec;
+	GSA_TRY(fetch_piece_table(ctx, pt1, hc[DC_NP1], h_first + PIECE_FIRST, pc1));
+	GSA_TRY(fetch_piece_table(ctx, pt2, hc[DC_NP2], h_first + 2 * PIECE_FIRST, pc2));
 	gsa_host_split(ctx, vec, pc1, pc2);
 	if (ctx->keep_dumps) ctx->blocks_stage[2] = vec;
 
-	// ---- 9. block-level dedup on the host (float ratios + std::sort ties, O(#blocks)) ------------------------------------------------------
+	// ---- 6. block-level dedup on the host (float ratios + std::sort ties, O(#blocks)) ------------------------------------------------------
 	gsa_host_dedup(ctx, vec);
 
-	// ---- 10. IdentifyNormalPairs for the surviving blocks -> fragment list --------------------------------------------------------------------
+	// ---- 7. IdentifyNormalPairs for the surviving blocks -> fragment list --------------------------------------------------------------------
 	int nblk = (int)vec.size();
 	ctx->final_blocks = vec;
 	if (nblk == 0) return GSA_OK;
 	std::vector<NpBlock> npb((size_t)nblk);
 	int64_t total = 0;
 	for (int k = 0; k < nblk; k++) { npb[k].src_beg = vec[k].beg; npb[k].dst_beg = total; npb[k].n = (int32_t)(vec[k].end - vec[k].beg); npb[k].pad = 0; total += npb[k].n; }
+	if (total >= 0x3FFFFFF0ll) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_cluster: more than 2^30 seeds in the kept blocks of one contig");
 	NpBlock *d_npb = ws.get<NpBlock>(nblk);
-	int32_t *npcnt = ws.get<int32_t>(total + 1), *npoff = ws.get<int32_t>(total + 1);
 	int64_t *d_fbeg = ws.get<int64_t>(nblk + 1);
 	if (ws.rc) return ws.rc;
-	CUDA_TRY(ctx, cudaMemcpyAsync(d_npb, npb.data(), (size_t)nblk * sizeof(NpBlock), cudaMemcpyHostToDevice, ctx->stream));
-	LAUNCH(k_np_count, total, d_npb, nblk, total, cq, cr, cl, npcnt);
-	CUDA_TRY(ctx, cudaMemsetAsync(npcnt + total, 0, 4, ctx->stream));
-	GSA_TRY(scan_exclusive(ctx, npcnt, npoff, total + 1));
-	int64_t nfr = 0;
-	GSA_TRY(read_count(ctx, npoff + total, &nfr));
-	GSA_TRY(gsa_ensure(ctx, ctx->d_frag, (size_t)(nfr + 1) * sizeof(gsa_frag)));
-	GSA_TRY(gsa_ensure(ctx, ctx->d_fblk, (size_t)(nfr + 1) * 4));
-	LAUNCH(k_np_write, total, d_npb, nblk, total, cq, cr, cl, npoff, (gsa_frag *)ctx->d_frag.p, (int32_t *)ctx->d_fblk.p, d_fbeg);
-	GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, (size_t)nblk * 8)); // O(#blocks): a fixed-size buffer overflows on highly fragmented contigs
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_fbeg, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-	const int64_t *fb = (const int64_t *)ctx->h_stage.p;
+	GSA_TRY(gsa_ensure(ctx, ctx->d_frag, (size_t)(2 * total + 2) * sizeof(gsa_frag)));
+	GSA_TRY(gsa_ensure(ctx, ctx->d_fblk, (size_t)(2 * total + 2) * 4));
+	GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, (size_t)nblk * (sizeof(NpBlock) + 8) + 64));
+	memcpy(ctx->h_stage.p, npb.data(), (size_t)nblk * sizeof(NpBlock));
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_npb, ctx->h_stage.p, (size_t)nblk * sizeof(NpBlock), cudaMemcpyHostToDevice, ctx->stream));
+	k_k2_init<<<1, 64, 0, ctx->stream>>>(dc, (int32_t)total); // dc[DC_N0] = element count of the last chain
+	KERNEL_CHECK(ctx);
+	{ FNormalPairs f; f.nb = d_npb; f.nblk = nblk; f.q = cq; f.r = cr; f.l = cl; f.frag = (gsa_frag *)ctx->d_frag.p; f.fblk = (int32_t *)ctx->d_fblk.p; f.blk_frag_beg = d_fbeg; f.dc = dc;
+	  GSA_TRY(run_chain(ctx, ch, f, dc + DC_N0, total)); }
+	int64_t *h_fb = (int64_t *)((char *)ctx->h_stage.p + (size_t)nblk * sizeof(NpBlock) + 8);
+	h_fb = (int64_t *)(((uintptr_t)h_fb + 7) & ~(uintptr_t)7);
+	CUDA_TRY(ctx, cudaMemcpyAsync(hc, dc, DC_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(h_fb, d_fbeg, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // ---- second wait of the phase
+	const int64_t nfr = hc[DC_NFR];
 	for (int k = 0; k < nblk; k++) {
-		ctx->final_blocks[k].frag_beg = fb[k];
-		ctx->final_blocks[k].n_frags = (int32_t)((k + 1 < nblk ? fb[k + 1] : nfr) - fb[k]);
+		ctx->final_blocks[k].frag_beg = h_fb[k];
+		ctx->final_blocks[k].n_frags = (int32_t)((k + 1 < nblk ? h_fb[k + 1] : nfr) - h_fb[k]);
 	}
 	ctx->n_frags = nfr;
 	return GSA_OK;

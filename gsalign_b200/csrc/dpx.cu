@@ -26,6 +26,7 @@
 #include "fm.cuh"
 
 #define DPX_FULL 0xffffffffu
+#define DPX_PACK_SMEM (96 * 1024)   // dynamic shared memory ceiling of k_dpx_pack (the largest class needs ~66 KB)
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
@@ -205,6 +206,151 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 	}
 }
 
+// ---- k_dpx_pack: several small problems per warp -------------------------------------------------------------------------
+// LG lanes per problem (1 .. 32), two query rows per lane, strips of R = 2*LG rows; a CTA of 128 threads holds 128/LG
+// problems, each with its own shared-memory slot (PackLayout, dpx.cuh).  The recurrence, the sentinel columns and the
+// per-step work are those of k_dpx; what differs:
+//   * the shuffle that hands H / E' down one row works inside the problem's LG lanes (width = LG), the first lane of a
+//     problem reads the boundary row of the strip above from its slot, the last lane writes its own there;
+//   * control flow stays warp-uniform: strips and 8-step groups run to the maximum over the warp's problems (they are
+//     sorted by size, so neighbours are alike); a problem that is done computes cells nobody reads and skips its stores;
+//   * the decision bits never leave shared memory;
+//   * after a CTA-wide barrier thread t walks the traceback of problem t (ksw_backtrack), so the CTA's walks run side by
+//     side instead of one lane per warp, writing the rows right-aligned into the (dead) boundary-row area; the problem's
+//     lanes then copy them out.
+template <int LG, bool HASN>
+__global__ void __launch_bounds__(128)
+k_dpx_pack(const DpProblem *prob, int nprob, DevIndex ix, int Mx, int Nx, char *aln1, char *aln2, int32_t *out_len, int64_t *out_start,
+           gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+{
+	extern __shared__ uint32_t dsm_all[];
+	constexpr int R = 2 * LG, NPB = 128 / LG, SH = (LG == 1 ? 1 : LG == 2 ? 2 : LG == 4 ? 3 : LG == 8 ? 4 : LG == 16 ? 5 : 6); // R = 1 << SH
+	const PackLayout L = pack_layout(LG, Mx, Nx);
+	const int tid = threadIdx.x, gl = tid & (LG - 1), grp = tid / LG;
+	const int pi = blockIdx.x * NPB + grp;
+	uint32_t *slot = dsm_all + (size_t)grp * L.words;
+	int m = 0, n = 0;
+	DpProblem P;
+	P.ref_chars = nullptr; P.qry_chars = nullptr; P.rpos = 0; P.out_off = 0; P.frag = 0;
+	if (pi < nprob) { P = prob[pi]; m = P.m; n = P.n; }
+	uint32_t *bhe = slot + L.off_bhe + R;                                              // bhe[j] = {H(i0-1,j), E'(i0-1,j)}, j >= -R
+	uint16_t *a16 = (uint16_t *)(slot + L.off_a16) + R;                                // a16[k] = selector halves for columns k, k-1
+	uint32_t *F0 = slot + L.off_f0, *F1 = slot + L.off_f1;
+	unsigned char *qch = (unsigned char *)(slot + L.off_q), *rch = (unsigned char *)(slot + L.off_r);
+
+	// ---- stage both fragments, the reference selector array and the row above strip 0 --------------------------------------
+	for (int i = gl; i < n; i += LG) qch[i] = (unsigned char)P.qry_chars[i];
+	for (int j = gl; j < m; j += LG) rch[j] = P.ref_chars ? (unsigned char)P.ref_chars[j] : (unsigned char)gsa_text_char(ix, P.rpos + j);
+	if (gl == 0) { slot[L.off_hdr + 2] = (uint32_t)m; slot[L.off_hdr + 3] = (uint32_t)n; }
+	__syncwarp();
+	for (int k = -R + gl; k < L.cols - R; k += LG) {
+		int c0 = 4, c1 = 4; // 0..3 = ACGT, 4 = sentinel outside the fragment, 5 = any other letter
+		if (k >= 0 && k < m) { c0 = gsa_nt4(rch[k]); if (c0 == 4) c0 = 5; }
+		if (k >= 1 && k <= m) { c1 = gsa_nt4(rch[k - 1]); if (c1 == 4) c1 = 5; }
+		a16[k] = (uint16_t)(c0 | 0x80 | (c1 << 8) | 0x8000);
+		bhe[k] = pack16(-(3 + k), DP_NEG);
+	}
+	__syncwarp();
+
+	const uint32_t M1 = 0xFFFFFFFFu, M3 = 0xFFFDFFFDu, TA = 0x02020204u, TB = 0x02020202u;
+	const int ns_own = (n + R - 1) >> SH;
+	const int ns_w = __reduce_max_sync(DPX_FULL, ns_own);
+	for (int s = 0; s < ns_w; s++) {
+		const int i0 = s << SH, r0 = i0 + 2 * gl, r1 = r0 + 1;
+		const int Gs_own = s < ns_own ? (m + min(R, n - i0) - 1 + 7) >> 3 : 0;
+		const int Gs_w = __reduce_max_sync(DPX_FULL, Gs_own);
+		uint32_t Hl = pack16(-(3 + r0), -(3 + r1));                 // H(i,-1)
+		uint32_t El = pack16(DP_NEG, DP_NEG), Fl = El;
+		uint32_t Dg = pack16(r0 == 0 ? 0 : -(2 + r0), -(2 + r1));   // H(i-1,-1)
+		const int q0 = r0 < n ? gsa_nt4(qch[r0]) : 0, q1 = r1 < n ? gsa_nt4(qch[r1]) : 0;
+		const uint32_t qw = (uint32_t)q0 | ((uint32_t)q1 << 8);
+		const uint32_t T0 = q0 < 4 ? 0x02020202u + (2u << (8 * q0)) : 0x03030303u, T1 = q1 < 4 ? 0x02020202u + (2u << (8 * q1)) : 0x03030303u;
+		const uint32_t TN = 0x03030302u;
+		const uint16_t *ap = a16 - 2 * gl;
+		uint32_t *f0p = F0 + (size_t)s * L.Gx * LG + gl, *f1p = F1 + (size_t)s * L.Gx * LG + gl;
+		__syncwarp(); // the last lane's boundary row of the previous strip is complete
+		for (int g = 0; g < Gs_w; g++) {
+			const int d0 = g << 3;
+			uint32_t f0 = 0, f1 = 0;
+#define DPX_PSTEP(k)                                                                                              \
+			{                                                                                                             \
+				const int d = d0 + (k);                                                                                   \
+				uint32_t rv;                                                                                              \
+				if (LG > 1) { rv = __shfl_up_sync(DPX_FULL, __byte_perm(Hl, El, 0x7632), 1, LG); if (gl == 0) rv = bhe[d]; } \
+				else rv = bhe[d];                                                                                         \
+				uint32_t up = __byte_perm(rv, Hl, 0x5410), eu = __byte_perm(rv, El, 0x5432);                              \
+				uint32_t s3;                                                                                              \
+				if (HASN) { uint32_t sel = ap[d]; s3 = __byte_perm(prmt(T0, TN, sel), prmt(T1, TN, sel), 0x7610); }       \
+				else s3 = prmt(TA, TB, qw ^ (uint32_t)ap[d]);                                                             \
+				uint32_t E = vmax_flag<(4u << (4 * (k)))>(up, __vadd2(eu, M1), f0, f1);                                   \
+				uint32_t F = vmax_flag<(8u << (4 * (k)))>(Hl, __vadd2(Fl, M1), f0, f1);                                   \
+				uint32_t h = vmax_flag<(1u << (4 * (k)))>(__vadd2(Dg, s3), E, f0, f1);                                    \
+				h = vmax_flag<(2u << (4 * (k)))>(h, F, f0, f1);                                                           \
+				Dg = up; Hl = __vadd2(h, M3); El = E; Fl = F;                                                             \
+				if (gl == LG - 1) bhe[d - (R - 1)] = __byte_perm(Hl, El, 0x7632);                                         \
+			}
+			DPX_PSTEP(0) DPX_PSTEP(1) DPX_PSTEP(2) DPX_PSTEP(3) DPX_PSTEP(4) DPX_PSTEP(5) DPX_PSTEP(6) DPX_PSTEP(7)
+#undef DPX_PSTEP
+			if (g < Gs_own) { f0p[(size_t)g * LG] = f0; f1p[(size_t)g * LG] = f1; }
+		}
+	}
+	__syncthreads();
+
+	// ---- traceback (ksw_backtrack, reference src/ksw2_alignment.cpp:25-68): thread t walks problem t of the CTA ---------------
+	if (tid < NPB && blockIdx.x * NPB + tid < nprob) {
+		uint32_t *ws = dsm_all + (size_t)tid * L.words;
+		const int wm = (int)ws[L.off_hdr + 2], wn = (int)ws[L.off_hdr + 3];
+		const uint32_t *W0 = ws + L.off_f0, *W1 = ws + L.off_f1;
+		const unsigned char *wq = (const unsigned char *)(ws + L.off_q), *wr = (const unsigned char *)(ws + L.off_r);
+		char *t1 = (char *)(ws + L.off_bhe), *t2 = t1 + ((Mx + Nx + 3) & ~3);
+		int i = wn - 1, j = wm - 1, state = 0, cont = 0, pos = wm + wn, same = 0;
+		while (i >= 0 && j >= 0) {
+			const int s = i >> SH, ii = i & (R - 1), d = j + ii;
+			const uint32_t w = ((ii & 1) ? W1 : W0)[((size_t)s * L.Gx + (d >> 3)) * LG + (ii >> 1)];
+			const int t = (w >> ((d & 7) << 2)) & 15;
+			if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
+			char c1, c2;
+			if (state == 0) { c1 = (char)wr[j]; c2 = (char)wq[i]; i--; j--; }
+			else if (state == 1) { c1 = '-'; c2 = (char)wq[i]; cont = (t >> 2) & 1; i--; }
+			else { c1 = (char)wr[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
+			same += gsa_nt4((unsigned char)c1) == gsa_nt4((unsigned char)c2); // nt4 classes: '-' equals a non-ACGT letter (H7)
+			pos--; t1[pos] = c1; t2[pos] = c2;
+		}
+		for (; i >= 0; i--) { pos--; t1[pos] = '-'; t2[pos] = (char)wq[i]; same += gsa_nt4(wq[i]) == 4; }
+		for (; j >= 0; j--) { pos--; t1[pos] = (char)wr[j]; t2[pos] = '-'; same += gsa_nt4(wr[j]) == 4; }
+		ws[L.off_hdr] = (uint32_t)pos; ws[L.off_hdr + 1] = (uint32_t)same;
+	}
+	__syncthreads();
+	if (pi >= nprob) return;
+
+	// ---- copy-out by the problem's own lanes -----------------------------------------------------------------------------------
+	const int pos = (int)slot[L.off_hdr], len = m + n - pos;
+	const char *t1 = (const char *)(slot + L.off_bhe), *t2 = t1 + ((Mx + Nx + 3) & ~3);
+	char *o1 = aln1 + P.out_off, *o2 = aln2 + P.out_off;
+	for (int k = pos + gl; k < m + n; k += LG) { o1[k] = t1[k]; o2[k] = t2[k]; }
+	if (gl == 0) {
+		if (out_len) { out_len[P.frag] = len; out_start[P.frag] = P.out_off + pos; }
+		if (frag) {
+			frag[P.frag].aln_off = P.out_off + pos; frag[P.frag].aln_len = len;
+			int b = fblk[P.frag];
+			atomicAdd(bsum + 2 * b, (unsigned)len); atomicAdd(bsum + 2 * b + 1, slot[L.off_hdr + 1]);
+		}
+	}
+}
+
+template <int LG, bool HASN>
+static int launch_pack(gsa_ctx *ctx, cudaStream_t stream, int max_m, int max_n, const DpProblem *prob, int nprob, char *a1, char *a2,
+                       int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
+{
+	constexpr int NPB = 128 / LG;
+	const PackLayout L = pack_layout(LG, max_m, max_n);
+	const size_t smem = (size_t)L.words * 4 * NPB;
+	if (smem > DPX_PACK_SMEM) return gsa_fail(ctx, GSA_ERR_LIMIT, "k_dpx_pack: %zu bytes of shared memory for %d x %d", smem, max_m, max_n);
+	k_dpx_pack<LG, HASN><<<(nprob + NPB - 1) / NPB, 128, smem, stream>>>(prob, nprob, ctx->ix, max_m, max_n, a1, a2, out_len, out_start, frag, fblk, bsum);
+	KERNEL_CHECK(ctx);
+	return GSA_OK;
+}
+
 template <int W, int NP, bool STAGE, bool HASN>
 static int launch_dpx(gsa_ctx *ctx, cudaStream_t stream, uint32_t slot, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
                       int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
@@ -226,6 +372,11 @@ int gsa_dpx_init_device(gsa_ctx *ctx)
 	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<4, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<8, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx<16, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define PACK_ATTR(LG) \
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx_pack<LG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPX_PACK_SMEM)); \
+	CUDA_TRY(ctx, cudaFuncSetAttribute(k_dpx_pack<LG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPX_PACK_SMEM));
+	PACK_ATTR(1) PACK_ATTR(2) PACK_ATTR(4) PACK_ATTR(8) PACK_ATTR(16) PACK_ATTR(32)
+#undef PACK_ATTR
 	return GSA_OK; // the S classes stay below the 48 KB default (m <= 1000, n <= 256)
 }
 
@@ -233,6 +384,16 @@ template <bool HASN>
 static int dpx_launch_size(gsa_ctx *ctx, cudaStream_t stream, int size, int max_m, int max_n, const DpProblem *prob, int nprob, uint8_t *flags, char *a1, char *a2,
                            int32_t *out_len, int64_t *out_start, gsa_frag *frag, const int32_t *fblk, unsigned int *bsum)
 {
+	if (size >= DPX_CLS_P1) {
+		switch (dpx_pack_lanes(size)) {
+		case 1: return launch_pack<1, HASN>(ctx, stream, max_m, max_n, prob, nprob, a1, a2, out_len, out_start, frag, fblk, bsum);
+		case 2: return launch_pack<2, HASN>(ctx, stream, max_m, max_n, prob, nprob, a1, a2, out_len, out_start, frag, fblk, bsum);
+		case 4: return launch_pack<4, HASN>(ctx, stream, max_m, max_n, prob, nprob, a1, a2, out_len, out_start, frag, fblk, bsum);
+		case 8: return launch_pack<8, HASN>(ctx, stream, max_m, max_n, prob, nprob, a1, a2, out_len, out_start, frag, fblk, bsum);
+		case 16: return launch_pack<16, HASN>(ctx, stream, max_m, max_n, prob, nprob, a1, a2, out_len, out_start, frag, fblk, bsum);
+		default: return launch_pack<32, HASN>(ctx, stream, max_m, max_n, prob, nprob, a1, a2, out_len, out_start, frag, fblk, bsum);
+		}
+	}
 	if (size == DPX_CLS_S1 || size == DPX_CLS_S2) {
 		const uint32_t slot = dpx_layout(max_m, max_n, true).total;
 		if (slot <= 3584) return launch_dpx<1, 2, true, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);

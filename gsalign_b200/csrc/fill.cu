@@ -21,6 +21,14 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
+#include <stdlib.h>
+
+// GSA_NO_PACK=1 sends every DP problem through the one-warp-per-problem kernels (A/B measurements)
+static int dpx_use_pack()
+{
+	static const int v = getenv("GSA_NO_PACK") ? 0 : 1;
+	return v;
+}
 
 // fragment type codes
 enum { FT_SEED = 0, FT_DEL = 1, FT_INS = 2, FT_COPY = 3, FT_DP = 4 };
@@ -29,7 +37,7 @@ enum { FT_SEED = 0, FT_DEL = 1, FT_INS = 2, FT_COPY = 3, FT_DP = 4 };
 // One thread per fragment: type, mismatch count for equal-length fragments (CheckFragPairMismatch,
 // src/ProcessCandidateAlignment.cpp:49-61), upper bound of its row length, DP cell count.
 __global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char *seq, const uint32_t *qinv, DevIndex ix, uint8_t *type, int32_t *mism,
-                                int64_t *row_len, int64_t *flag_len, uint8_t *is_dp, uint8_t *dp_cls)
+                                int64_t *row_len, int64_t *flag_len, uint8_t *is_dp, uint8_t *dp_cls, int use_pack)
 {
 	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= nfr) return;
@@ -52,8 +60,8 @@ __global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char
 				rl = (int64_t)f.qLen + f.rLen;
 				bool other = false; // any non-ACGT query base in the fragment (the 2-bit reference text holds none)
 				for (uint32_t p = (uint32_t)f.qPos, e = p + (uint32_t)f.qLen; p < e && !other; p += 32) other = (gsa_bit_window(qinv, p) >> (32 - min(32u, e - p))) != 0;
-				cls = (uint8_t)dpx_class(f.rLen, f.qLen, other);
-				fl = dpx_flag_bytes(f.rLen, f.qLen);
+				cls = (uint8_t)dpx_class(f.rLen, f.qLen, other, use_pack != 0);
+				fl = dpx_flag_bytes(f.rLen, f.qLen, cls);
 			}
 		}
 	}
@@ -126,14 +134,30 @@ struct DpStats { unsigned int count[DP_NBINS]; int max_m[DPX_NCLS], max_n[DPX_NC
 __global__ void k_dp_keys(const DpProblem *prob, int n, uint32_t *key, uint32_t *idx, DpStats *st)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int m = prob[i].m, q = prob[i].n, cls = prob[i].cls, big = max(m, q), bin;
-	if (big > DP_MAX_DIM || cls < 0 || cls >= DPX_NCLS) bin = DP_BIN_TOOLONG;
-	else { bin = cls; atomicMax(&st->max_m[cls], m); atomicMax(&st->max_n[cls], q); }
-	atomicAdd(&st->count[bin], 1u);
-	atomicAdd(&st->cells, (unsigned long long)m * (unsigned long long)q);
-	key[i] = ((uint32_t)bin << 12) | (uint32_t)(4095 - min(4095, (m + q) >> 2));
-	idx[i] = (uint32_t)i;
+	int bin = -1 - (int)(threadIdx.x & 31), m = 0, q = 0;
+	if (i < n) {
+		m = prob[i].m; q = prob[i].n;
+		int cls = prob[i].cls, big = max(m, q);
+		bin = (big > DP_MAX_DIM || cls < 0 || cls >= DPX_NCLS) ? DP_BIN_TOOLONG : cls;
+		// inside a bin: largest first; the pack classes run warp-uniform loops over the problems that share a warp, so they are
+		// ordered by rows, then columns
+		const bool pack = bin < DP_BIN_TOOLONG && (bin % DPX_NSIZE) >= DPX_CLS_P1;
+		uint32_t sz = pack ? (uint32_t)((min(q, 127) << 4) | min(15, m >> 4)) : (uint32_t)min(2047, (m + q) >> 3);
+		key[i] = ((uint32_t)bin << 11) | (2047u - sz);
+		idx[i] = (uint32_t)i;
+	}
+	// per-bin statistics: one atomic per distinct bin of the warp (the counters are few and every thread hits them)
+	unsigned peers = __match_any_sync(0xffffffffu, bin);
+	bool leader;
+	unsigned long long cells = gsa_peer_sum(peers, (unsigned long long)m * (unsigned long long)q, leader);
+	int cnt = gsa_peer_sum(peers, 1, leader);
+	int mm = m, mq = q;
+	for (unsigned rest = peers; rest; rest &= rest - 1) { int src = __ffs(rest) - 1; mm = max(mm, __shfl_sync(peers, m, src)); mq = max(mq, __shfl_sync(peers, q, src)); }
+	if (leader && bin >= 0) {
+		atomicAdd(&st->count[bin], (unsigned)cnt);
+		atomicAdd(&st->cells, cells);
+		if (bin < DP_BIN_TOOLONG) { atomicMax(&st->max_m[bin], mm); atomicMax(&st->max_n[bin], mq); }
+	}
 }
 
 __global__ void k_dp_permute(const DpProblem *in, const uint32_t *idx, DpProblem *out, int n)
@@ -167,20 +191,25 @@ static int run_dp_binned(gsa_ctx *ctx, Ws3 &ws, const DpProblem *d_prob, DpProbl
 	ctx->tm.dp_cells = (int64_t)st->cells;
 	if (st->count[DP_BIN_TOOLONG]) return gsa_fail(ctx, GSA_ERR_LIMIT, "DP fragment longer than %d", DP_MAX_DIM);
 	if (e0) CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-	// the big problems (classes G8 / G16, largest first) run on a side stream so that their long critical paths overlap
-	// the many small ones
+	// one launch per non-empty class; the classes are independent, so they are spread over the context's side streams and
+	// run next to each other (the few big problems of G8 / G16 have long critical paths, the small classes fill the SMs)
 	size_t off[DP_NBINS + 1]; off[0] = 0;
 	for (int b = 0; b < DP_NBINS; b++) off[b + 1] = off[b] + st->count[b];
-	const bool side = (st->count[DPX_CLS_G8] + st->count[DPX_CLS_G16] + st->count[DPX_NSIZE + DPX_CLS_G8] + st->count[DPX_NSIZE + DPX_CLS_G16]) > 0;
-	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0)); }
-	const int order[DPX_NSIZE] = {DPX_CLS_G16, DPX_CLS_G8, DPX_CLS_G4, DPX_CLS_S2, DPX_CLS_S1};
+	const int order[] = {DPX_CLS_G16, DPX_CLS_G8, DPX_CLS_G4, DPX_CLS_S2, DPX_CLS_S1, DPX_CLS_P16, DPX_CLS_P8, DPX_CLS_P4, DPX_CLS_P2, DPX_CLS_P1};
+	int nlaunch = 0;
+	for (int c = 0; c < DPX_NCLS; c++) nlaunch += st->count[c] > 0;
+	const bool side = nlaunch > 1;
+	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); for (int i = 0; i < GSA_NSIDE; i++) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0)); }
+	int turn = 0;
 	for (int size : order)
 		for (int hasn = 0; hasn < 2; hasn++) {
 			const int cls = size + hasn * DPX_NSIZE;
-			cudaStream_t st_cls = size >= DPX_CLS_G8 ? ctx->stream2 : ctx->stream;
+			if (st->count[cls] == 0) continue;
+			cudaStream_t st_cls = !side ? ctx->stream : (turn % (GSA_NSIDE + 1) == GSA_NSIDE ? ctx->stream : ctx->side[turn % (GSA_NSIDE + 1)]);
+			turn++;
 			GSA_TRY(gsa_dpx_launch(ctx, st_cls, cls, std::max(1, st->max_m[cls]), std::max(1, st->max_n[cls]), d_sorted + off[cls], (int)st->count[cls], flags, a1, a2, out_len, out_start, frag, fblk, bsum));
 		}
-	if (side) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2)); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
+	if (side) for (int i = 0; i < GSA_NSIDE; i++) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_side[i], ctx->side[i])); CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side[i], 0)); }
 	if (e1) CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
 	return GSA_OK;
 }
@@ -214,7 +243,7 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 	unsigned int *bsum = (unsigned int *)ctx->d_bsum.p;
 	int32_t *d_ndp = (int32_t *)ctx->d_counter.p + 32;
 	CUDA_TRY(ctx, cudaMemsetAsync(bsum, 0, (size_t)nblk * 8, ctx->stream));
-	k_frag_classify<<<gsa_grid(nfr, 128), 128, 0, ctx->stream>>>(frag, nfr, seq, (const uint32_t *)ctx->d_qinv.p, ctx->ix, type, mism, row_len, flag_len, is_dp, dp_cls);
+	k_frag_classify<<<gsa_grid(nfr, 128), 128, 0, ctx->stream>>>(frag, nfr, seq, (const uint32_t *)ctx->d_qinv.p, ctx->ix, type, mism, row_len, flag_len, is_dp, dp_cls, dpx_use_pack());
 	KERNEL_CHECK(ctx);
 	CUDA_TRY(ctx, cudaMemsetAsync(row_len + nfr, 0, 8, ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(flag_len + nfr, 0, 8, ctx->stream));
@@ -324,8 +353,8 @@ int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int6
 		bool other = false; // any letter outside ACGT/acgt: the HASN variant of the kernels
 		for (int64_t k = ref_off[i]; k < ref_off[i + 1] && !other; k++) { char c = ref[k] & 0xDF; other = !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
 		for (int64_t k = qry_off[i]; k < qry_off[i + 1] && !other; k++) { char c = qry[k] & 0xDF; other = !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
-		p.frag = i; p.cls = dpx_class(p.m, p.n, other);
-		fbytes += dpx_flag_bytes(p.m, p.n);
+		p.frag = i; p.cls = dpx_class(p.m, p.n, other, dpx_use_pack() != 0);
+		fbytes += dpx_flag_bytes(p.m, p.n, p.cls);
 	}
 	uint8_t *flags = ws.get<uint8_t>(fbytes + 256);
 	if (ws.rc) return ws.rc;

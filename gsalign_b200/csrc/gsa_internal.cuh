@@ -11,6 +11,7 @@
 #define GSA_SEED_CHUNK 10000   // SeedExplorationChunk, reference src/GSAlign.cpp:5 (observable: MEMs are cut at chunk ends)
 #define GSA_MAX_SEED_FREQ 100  // MaxSeedFreq, reference src/bwt_search.cpp:3
 #define GSA_MAX_SEED_GAP 5000  // MaxSeedGap, reference src/structure.h:23
+#define GSA_NSIDE 4
 #define GSA_KTAB_MAX_K 14
 #define GSA_KBITS_MAX_K 16     // presence bitmap depth: 4^16 bits = 512 MB      // k-mer prefix table depth (never above MinSeedLength, see seed.cu)
 
@@ -80,6 +81,8 @@ struct gsa_ctx {
 	cudaStream_t stream = nullptr;
 	cudaStream_t stream2 = nullptr; // side stream (forked from / joined to `stream` with ev_fork / ev_join)
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	cudaStream_t side[GSA_NSIDE] = {};   // side[0] = stream2: the DP classes of one contig run next to each other (fill.cu)
+	cudaEvent_t ev_side[GSA_NSIDE] = {};
 	cudaEvent_t ev[12] = {};        // 0/1 h2d, 2/3 seed, 4/5 cluster, 6/7 fill, 8/9 k_seed, 10/11 the DP launches
 	bool own_stream = true; bool dp_timed = false;
 	std::string err;
@@ -109,6 +112,7 @@ struct gsa_ctx {
 	DevBuf d_sq, d_sr, d_sl;       // seeds: qPos (i32), rPos (i64), len (i32), sorted by (PosDiff,qPos) after gsa_seed
 	DevBuf d_tmp[64];              // scratch arrays for K2/K3 (sized on demand)
 	DevBuf d_cub;                  // cub temp storage
+	DevBuf d_chain;                // chained-scan states of K2 (scan.cuh)
 	HostBuf h_small;               // pinned scratch for counters / piece tables
 	HostBuf h_stage;               // pinned staging for dumps
 

@@ -184,7 +184,9 @@ def test_dpx_classes_vs_oracle(oracle):
     from gsalign_b200 import capi
     rng = random.Random(11)
     refs, qrys = [], []
-    dims = [(1, 1), (1, 70), (70, 1), (5, 64), (64, 5), (63, 63), (64, 64), (65, 65), (66, 127), (127, 66), (128, 128), (129, 130),
+    dims = [(2, 1), (1, 2), (10, 2), (2, 10), (40, 2), (41, 2), (48, 4), (49, 4), (5, 4), (3, 3), (64, 8), (65, 8), (9, 8), (96, 16), (97, 16), (15, 16),
+            (20, 17), (128, 32), (129, 32), (30, 33), (160, 64), (100, 65), (160, 128), (161, 128), (33, 127), (159, 129),   # pack class edges
+            (1, 1), (1, 70), (70, 1), (5, 64), (64, 5), (63, 63), (64, 64), (65, 65), (66, 127), (127, 66), (128, 128), (129, 130),
             (200, 190), (257, 255), (300, 320), (500, 64), (64, 500), (3, 900), (900, 3), (640, 641), (1000, 1010), (1500, 1400),
             (2100, 2000), (4000, 7), (7, 4000), (3100, 3000)]
     for m, n in dims:
@@ -193,9 +195,14 @@ def test_dpx_classes_vs_oracle(oracle):
         if min(m, n) > 8 and abs(m - n) < 0.2 * m:
             refs.append(a); qrys.append(_mutate(rng, a, 0.05, 0.02))                                # related, indels
             refs.append(a.lower()); qrys.append(_mutate(rng, a, 0.3, 0.05))                         # divergent, lower-case ref
-    for t in range(300):                                                                             # many small ones
-        m = rng.randint(1, 140); a = bytes(rng.choice(list(b"ACGT")) for _ in range(m))
+    for t in range(1500):                                                                            # many small ones (several per warp)
+        m = rng.randint(1, 140) if t % 3 else rng.randint(1, 24); a = bytes(rng.choice(list(b"ACGT")) for _ in range(m))
         refs.append(a); qrys.append(_mutate(rng, a, rng.choice([0.02, 0.1, 0.5]), rng.choice([0.0, 0.02, 0.1])))
+    for t in range(300):                                                                             # one side tiny: the fragments around an indel
+        m, n = rng.randint(1, 30), rng.randint(1, 3)
+        if t & 1:
+            m, n = n, m
+        refs.append(bytes(rng.choice(list(b"ACGT")) for _ in range(m))); qrys.append(bytes(rng.choice(list(b"ACGT")) for _ in range(n)))
     al = capi.Aligner(0)
     res, ms = al.dp_batch(refs, qrys)
     for a, b, (x, y) in zip(refs, qrys, res):
@@ -214,7 +221,8 @@ def test_dpx_other_letters_all_classes(oracle):
     from gsalign_b200 import capi
     rng = random.Random(23)
     refs, qrys = [], []
-    for m, n in [(1, 1), (9, 64), (64, 65), (130, 120), (200, 250), (700, 200), (300, 320), (520, 500), (1100, 1000), (2600, 2500), (5, 3000), (3000, 5)]:
+    for m, n in [(2, 2), (12, 3), (3, 12), (30, 7), (50, 14), (90, 30), (120, 60), (150, 120), (40, 100),
+                 (1, 1), (9, 64), (64, 65), (130, 120), (200, 250), (700, 200), (300, 320), (520, 500), (1100, 1000), (2600, 2500), (5, 3000), (3000, 5)]:
         a = bytearray(rng.choice(b"ACGT") for _ in range(m))
         b = bytearray(_mutate(rng, bytes(a), 0.05, 0.02)) if min(m, n) > 8 and abs(m - n) < 0.3 * m else bytearray(rng.choice(b"ACGT") for _ in range(n))
         for s, frac in ((a, 0.02), (b, 0.06)):                    # sprinkle other letters, and one run of N in the query
