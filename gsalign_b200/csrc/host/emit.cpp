@@ -1,7 +1,11 @@
 // emit.cpp -- MAF / ALN / VCF emitters of bin/GSAlign, byte-compatible with the reference
 // (src/tools.cpp:3-44,142-286 and src/SeqVariant.cpp:6-143; format hazards H3-H8, H15 of SURVEY.md).
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
 #include <functional>
 #include <thread>
@@ -23,6 +27,93 @@ static void parallel_chunks(int n, int threads, const std::function<void(int)> &
 	for (int k = 1; k < n; k++) th.emplace_back(fn, k);
 	fn(0);
 	for (auto &t : th) t.join();
+}
+
+// ---- output files written through a mapping ---------------------------------------------------------------------------
+// The alignment file of a human-size pair is 2 bytes per aligned base (6 GB at 3 Gbp); one thread pushing it through
+// write() is the floor of the whole run.  The file is grown with ftruncate and the new range mapped instead, so that the
+// emitter threads assemble the rows straight into the page cache, all of them at once.
+struct MappedOut {
+	int fd = -1; size_t end = 0;               // logical end of the file
+	char *map = nullptr; size_t map_off = 0, map_len = 0;
+	bool open_file(const char *path, bool truncate)
+	{
+		fd = open(path, O_RDWR | O_CREAT | (truncate ? O_TRUNC : 0), 0644);
+		if (fd < 0) return false;
+		struct stat sb;
+		end = fstat(fd, &sb) == 0 ? (size_t)sb.st_size : 0;
+		return true;
+	}
+	// appends n bytes to the file and returns where to write them (valid until the next reserve / close)
+	char *reserve(size_t n)
+	{
+		release();
+		if (n == 0) return nullptr;
+		const size_t page = 4096, lo = end & ~(page - 1);
+		if (ftruncate(fd, (off_t)(end + n)) != 0) return nullptr;
+		void *m = mmap(nullptr, end + n - lo, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)lo);
+		if (m == MAP_FAILED) return nullptr;
+		map = (char *)m; map_off = lo; map_len = end + n - lo;
+		char *p = map + (end - lo);
+		end += n;
+		return p;
+	}
+	void release() { if (map) { munmap(map, map_len); map = nullptr; } }
+	void close_file() { release(); if (fd >= 0) { close(fd); fd = -1; } }
+};
+
+// copies [src, src + n) to dst on up to `threads` threads
+static void parallel_copy(char *dst, const char *src, size_t n, int threads)
+{
+	const size_t piece = (size_t)8 << 20;
+	int nch = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / piece));
+	parallel_chunks(nch, threads, [&](int k) { size_t a = n * (size_t)k / (size_t)nch, b = n * (size_t)(k + 1) / (size_t)nch; memcpy(dst + a, src + a, b - a); });
+}
+
+// ---- std::sort, bit for bit, on several threads ---------------------------------------------------------------------------
+// The order of records with equal keys in the reference's output is whatever libstdc++'s introsort makes of the input order
+// (hazard H5), so the sort must BE that introsort.  Its structure leaves room for threads all the same: after a partition
+// the right part is sorted by a recursive call that never touches the left part, and the loop carries on with the left one.
+// Running the recursive call on another thread changes no comparison and no move: same partition pivots
+// (std::__unguarded_partition_pivot), same depth limit and heap-sort fallback (std::__partial_sort), same final insertion
+// sort, all libstdc++'s own.
+template <typename It, typename Cmp>
+static void introsort_loop_threads(It first, It last, long depth_limit, Cmp comp, int spawn_levels)
+{
+	std::vector<std::thread> kids;
+	while (last - first > 16) { // _S_threshold
+		if (depth_limit == 0) { std::__partial_sort(first, last, last, comp); break; }
+		--depth_limit;
+		It cut = std::__unguarded_partition_pivot(first, last, comp);
+		if (spawn_levels > 0 && last - cut > (1 << 15)) {
+			--spawn_levels;
+			const long d = depth_limit; const int sl = spawn_levels;
+			kids.emplace_back([cut, last, d, comp, sl] { introsort_loop_threads(cut, last, d, comp, sl); });
+		} else introsort_loop_threads(cut, last, depth_limit, comp, 0);
+		last = cut;
+	}
+	for (auto &t : kids) t.join();
+}
+
+template <typename It, typename Compare>
+static void sort_like_std(It first, It last, Compare comp, int threads)
+{
+	if (first == last) return;
+	auto c = __gnu_cxx::__ops::__iter_comp_iter(comp);
+	int levels = 0;
+	while ((1 << levels) < threads) levels++;
+	introsort_loop_threads(first, last, (long)std::__lg(last - first) * 2, c, threads > 1 ? levels + 2 : 0);
+	std::__final_insertion_sort(first, last, c);
+}
+
+// test hook (tests/test_emit_cpu.py): sorts (key, index) pairs like output_variants does
+void gsa_test_sort_keys(uint64_t *keys, uint32_t *idx, size_t n, int threads)
+{
+	struct K { uint64_t key; uint32_t idx; };
+	std::vector<K> v(n);
+	for (size_t i = 0; i < n; i++) { v[i].key = keys[i]; v[i].idx = idx[i]; }
+	sort_like_std(v.begin(), v.end(), [](const K &a, const K &b) { return a.key < b.key; }, threads);
+	for (size_t i = 0; i < n; i++) { keys[i] = v[i].key; idx[i] = v[i].idx; }
 }
 
 static const char *VERSION_STR = "1.0.22"; // VersionStr, src/main.cpp:9 (printed in the VCF header)
@@ -114,13 +205,6 @@ static void build_rows(const QueryChr &qc, const ContigResult &r, const gsa_bloc
 	for (int k = 0; k < nch; k++) { gaps1 += g1[(size_t)k]; gaps2 += g2[(size_t)k]; }
 }
 
-// what fprintf("%s") would print of a row: everything up to the first NUL (ReverseMap turns unknown letters into NUL, H3)
-static void write_row(FILE *out, const std::vector<char> &a, int aln_len)
-{
-	const void *z = memchr(a.data(), 0, (size_t)aln_len);
-	fwrite(a.data(), 1, z ? (size_t)((const char *)z - a.data()) : (size_t)aln_len, out);
-}
-
 // iExtension (src/tools.cpp:192-202): a block whose last seed runs past the end of its contig is trimmed in place
 static void trim_extension(const HostIndex &ix, const Coordinate &coor, ContigResult &r, gsa_block &b, std::vector<char> &a1, std::vector<char> &a2)
 {
@@ -141,45 +225,143 @@ static void padded_names(const HostIndex &ix, const QueryChr &qc, int ref_idx, s
 	else qname += std::string(rname.length() - qname.length(), ' ');
 }
 
-void output_maf(const Options &o, const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, ContigResult &r)
+// number of '-' characters in either row of a block: only gap fragments hold any
+static void count_block_gaps(const ContigResult &r, const gsa_block &b, int threads, int64_t &gaps1, int64_t &gaps2)
 {
-	FILE *out;
-	if (qidx == 0) { out = fopen(o.maf.c_str(), "w"); if (out) fprintf(out, "##maf version=1\n"); }
-	else out = fopen(o.maf.c_str(), "a");
-	if (!out) return;
+	const int64_t nf = b.n_frags;
+	int nch = (int)std::max<int64_t>(1, std::min<int64_t>(threads, nf / emit_chunk()));
+	std::vector<int64_t> g1((size_t)nch, 0), g2((size_t)nch, 0);
+	parallel_chunks(nch, threads, [&](int k) {
+		int64_t c1 = 0, c2 = 0;
+		for (int64_t t = b.frag_beg + nf * k / nch; t < b.frag_beg + nf * (k + 1) / nch; t++) {
+			const gsa_frag &f = r.frags[(size_t)t];
+			if (f.bSeed) continue;
+			const char *s1 = r.aln1.data() + f.aln_off, *s2 = r.aln2.data() + f.aln_off;
+			for (int i = 0; i < f.aln_len; i++) { c1 += s1[i] == '-'; c2 += s2[i] == '-'; }
+		}
+		g1[(size_t)k] = c1; g2[(size_t)k] = c2;
+	});
+	gaps1 = gaps2 = 0;
+	for (int k = 0; k < nch; k++) { gaps1 += g1[(size_t)k]; gaps2 += g2[(size_t)k]; }
+}
+
+// The two rows of a block assembled straight into their place in the output (src/tools.cpp:169-184: inside seeds BOTH rows
+// are copied from the query), forward or -- for a block on the reverse strand -- already reverse-complemented
+// (SelfComplementarySeq + ReverseMap, src/tools.cpp:3-44): fragment t then lands mirrored at the other end of the row.
+// Fragments are independent once their offsets are known, so the threads take a share each.
+static void assemble_rows(const QueryChr &qc, const ContigResult &r, const gsa_block &b, char *d1, char *d2, bool reverse, int threads)
+{
+	const int64_t nf = b.n_frags;
+	const size_t alen = (size_t)b.aln_len;
+	int nch = (int)std::max<int64_t>(1, std::min<int64_t>(threads, nf / emit_chunk()));
+	std::vector<size_t> start((size_t)nch + 1, 0);
+	auto frag_len = [&](int64_t t) { const gsa_frag &f = r.frags[(size_t)t]; return (size_t)(f.bSeed ? f.qLen : f.aln_len); };
+	auto chunk_beg = [&](int k) { return b.frag_beg + nf * k / nch; };
+	parallel_chunks(nch, threads, [&](int k) { size_t n = 0; for (int64_t t = chunk_beg(k); t < chunk_beg(k + 1); t++) n += frag_len(t); start[(size_t)k + 1] = n; });
+	for (int k = 0; k < nch; k++) start[(size_t)k + 1] += start[(size_t)k];
+	parallel_chunks(nch, threads, [&](int k) {
+		size_t pos = start[(size_t)k];
+		for (int64_t t = chunk_beg(k); t < chunk_beg(k + 1); t++) {
+			const gsa_frag &f = r.frags[(size_t)t];
+			const size_t L = frag_len(t);
+			const char *s1 = f.bSeed ? qc.seq.data() + f.qPos : r.aln1.data() + f.aln_off;
+			const char *s2 = f.bSeed ? qc.seq.data() + f.qPos : r.aln2.data() + f.aln_off;
+			if (!reverse) { memcpy(d1 + pos, s1, L); memcpy(d2 + pos, s2, L); }
+			else {
+				char *e1 = d1 + (alen - pos - 1), *e2 = d2 + (alen - pos - 1);
+				for (size_t i = 0; i < L; i++) { e1[-(ptrdiff_t)i] = reverse_map(s1[i]); e2[-(ptrdiff_t)i] = reverse_map(s2[i]); }
+			}
+			pos += L;
+		}
+	});
+}
+
+// every letter of seq[beg, end) survives ReverseMap (anything else becomes NUL there and cuts the printed row short)
+static bool reverse_safe(const std::string &seq, size_t beg, size_t end, int threads)
+{
+	const size_t n = end - beg, piece = (size_t)4 << 20;
+	int nch = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / piece));
+	std::vector<int> bad((size_t)nch, 0);
+	parallel_chunks(nch, threads, [&](int k) {
+		int x = 0;
+		for (size_t i = beg + n * (size_t)k / (size_t)nch, e = beg + n * (size_t)(k + 1) / (size_t)nch; i < e; i++) x |= reverse_map(seq[i]) == '\0';
+		bad[(size_t)k] = x;
+	});
+	for (int x : bad) if (x) return false;
+	return true;
+}
+
+static void put_bytes(MappedOut &out, const char *p, size_t n) { char *d = out.reserve(n); if (d) memcpy(d, p, n); }
+
+void output_maf(const Options &o, const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, ContigResult &r)
+{ // OutputMAF, src/tools.cpp:149-220; the file is opened "w" by the first contig and "a" by the others (H15)
+	MappedOut out;
+	if (!out.open_file(o.maf.c_str(), qidx == 0)) return;
+	if (qidx == 0) put_bytes(out, "##maf version=1\n", 16);
 	const QueryChr &qc = q[(size_t)qidx];
 	std::vector<char> a1, a2;
 	std::string qname, rname;
+	char h1[1024], h2[1024];
 	for (gsa_block &b : r.blocks) {
 		if (!o.allow_dup && b.bDup) continue;
 		int64_t gaps1 = 0, gaps2 = 0;
-		build_rows(qc, r, b, a1, a2, o.threads, gaps1, gaps2);
+		count_block_gaps(r, b, o.threads, gaps1, gaps2);
 		Coordinate coor = gen_coordinate(ix, r.frags[(size_t)b.frag_beg].rPos);
 		int idx = coor.ChromosomeIdx;
 		padded_names(ix, qc, idx, qname, rname);
+		gsa_frag &lastf = r.frags[(size_t)(b.frag_beg + b.n_frags - 1)];
+		const int64_t lim = (coor.bDir ? ix.offset[idx] : ix.reverse_location(idx)) + ix.len[idx], fend = lastf.rPos + lastf.rLen;
+		const int ext = fend > lim ? (int)(fend - lim) : 0;     // iExtension, src/tools.cpp:192-202
+		const bool direct = (ext == 0 || (lastf.bSeed && ext < lastf.qLen)) && qname.size() < 400 && ix.names[(size_t)idx].size() < 400 &&
+		                    (coor.bDir || reverse_safe(qc.seq, (size_t)r.frags[(size_t)b.frag_beg].qPos, (size_t)(lastf.qPos + lastf.qLen), o.threads));
+		if (direct) { // rows go straight into the mapped file
+			if (ext > 0) { b.aln_len -= ext; b.score -= ext; lastf.rLen -= ext; lastf.qLen -= ext; }
+			const gsa_frag &first = r.frags[(size_t)b.frag_beg], &last = lastf;
+			int n1, n2;
+			if (coor.bDir) {
+				n1 = snprintf(h1, sizeof(h1), "a score=%d\ns ref.%s %d %d + %d ", b.bDup ? 1 : b.score, ix.names[(size_t)idx].c_str(), coor.gPos - 1, (int)(b.aln_len - gaps1), ix.len[(size_t)idx]);
+				n2 = snprintf(h2, sizeof(h2), "\ns qry.%s %d %d + %d ", qname.c_str(), first.qPos, (int)(b.aln_len - gaps2), (uint32_t)qc.seq.length());
+			} else {
+				int64_t rpos = last.rPos + last.rLen - 1;
+				n1 = snprintf(h1, sizeof(h1), "a score=%d\ns ref.%s %d %d + %d ", b.bDup ? 1 : b.score, ix.names[(size_t)idx].c_str(), gen_coordinate(ix, rpos).gPos - 1, (int)(b.aln_len - gaps1), ix.len[(size_t)idx]);
+				n2 = snprintf(h2, sizeof(h2), "\ns qry.%s %d %d - %d ", qname.c_str(), (uint32_t)qc.seq.length() - (last.qPos + last.qLen), (int)(b.aln_len - gaps2), (uint32_t)qc.seq.length());
+			}
+			const size_t alen = (size_t)b.aln_len;
+			char *p = out.reserve((size_t)n1 + alen + (size_t)n2 + alen + 2);
+			if (!p) break;
+			memcpy(p, h1, (size_t)n1); memcpy(p + n1 + alen, h2, (size_t)n2); memcpy(p + n1 + alen + n2 + alen, "\n\n", 2);
+			assemble_rows(qc, r, b, p + n1, p + n1 + alen + n2, !coor.bDir, o.threads);
+			continue;
+		}
+		// the general path: rows in memory, cut at the first NUL like fprintf("%s") does
+		build_rows(qc, r, b, a1, a2, o.threads, gaps1, gaps2);
 		trim_extension(ix, coor, r, b, a1, a2); // trims inside the last seed, which holds no gap characters
 		const gsa_frag &first = r.frags[(size_t)b.frag_beg], &last = r.frags[(size_t)(b.frag_beg + b.n_frags - 1)];
+		std::string txt;
+		auto row = [&](const std::vector<char> &a) { const void *z = memchr(a.data(), 0, (size_t)b.aln_len); txt.append(a.data(), z ? (size_t)((const char *)z - a.data()) : (size_t)b.aln_len); };
+		char num[2048];
 		if (coor.bDir) {
-			fprintf(out, "a score=%d\n", b.bDup ? 1 : b.score);
-			fprintf(out, "s ref.%s %d %d + %d ", ix.names[(size_t)idx].c_str(), coor.gPos - 1, (int)(b.aln_len - gaps1), ix.len[(size_t)idx]);
-			write_row(out, a1, b.aln_len);
-			fprintf(out, "\ns qry.%s %d %d + %d ", qname.c_str(), first.qPos, (int)(b.aln_len - gaps2), (uint32_t)qc.seq.length());
-			write_row(out, a2, b.aln_len);
-			fputs("\n\n", out);
+			snprintf(num, sizeof(num), "a score=%d\ns ref.%s %d %d + %d ", b.bDup ? 1 : b.score, ix.names[(size_t)idx].c_str(), coor.gPos - 1, (int)(b.aln_len - gaps1), ix.len[(size_t)idx]);
+			txt += num; row(a1);
+			txt += "\ns qry." + qname; snprintf(num, sizeof(num), " %d %d + %d ", first.qPos, (int)(b.aln_len - gaps2), (uint32_t)qc.seq.length());
+			txt += num; row(a2);
 		} else {
 			int64_t rpos = last.rPos + last.rLen - 1;
 			std::thread t2([&] { self_complementary((size_t)b.aln_len, a2.data()); });
 			self_complementary((size_t)b.aln_len, a1.data());
 			t2.join();
-			fprintf(out, "a score=%d\n", b.bDup ? 1 : b.score);
-			fprintf(out, "s ref.%s %d %d + %d ", ix.names[(size_t)idx].c_str(), gen_coordinate(ix, rpos).gPos - 1, (int)(b.aln_len - gaps1), ix.len[(size_t)idx]);
-			write_row(out, a1, b.aln_len);
-			fprintf(out, "\ns qry.%s %d %d - %d ", qname.c_str(), (uint32_t)qc.seq.length() - (last.qPos + last.qLen), (int)(b.aln_len - gaps2), (uint32_t)qc.seq.length());
-			write_row(out, a2, b.aln_len);
-			fputs("\n\n", out);
+			snprintf(num, sizeof(num), "a score=%d\ns ref.", b.bDup ? 1 : b.score);
+			txt += num; txt += ix.names[(size_t)idx];
+			snprintf(num, sizeof(num), " %d %d + %d ", gen_coordinate(ix, rpos).gPos - 1, (int)(b.aln_len - gaps1), ix.len[(size_t)idx]);
+			txt += num; row(a1);
+			txt += "\ns qry." + qname; snprintf(num, sizeof(num), " %d %d - %d ", (uint32_t)qc.seq.length() - (last.qPos + last.qLen), (int)(b.aln_len - gaps2), (uint32_t)qc.seq.length());
+			txt += num; row(a2);
 		}
+		txt += "\n\n";
+		char *p = out.reserve(txt.size());
+		if (p) parallel_copy(p, txt.data(), txt.size(), o.threads);
 	}
-	fclose(out);
+	out.close_file();
 }
 
 void output_aln(const Options &o, const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, ContigResult &r)
@@ -321,18 +503,22 @@ void output_variants(const Options &o, const HostIndex &ix, EmitState &st)
 	if (st.variants.size() >= 0xFFFFFFFFull) { fprintf(stderr, "too many variants for this build\n"); return; }
 	std::vector<VarKey> keys(st.variants.size());
 	for (size_t i = 0; i < keys.size(); i++) { keys[i].key = ((uint64_t)(uint32_t)st.variants[i].chr_idx << 32) | (uint32_t)st.variants[i].pos; keys[i].idx = (uint32_t)i; }
-	std::sort(keys.begin(), keys.end(), by_variant_pos);
+	sort_like_std(keys.begin(), keys.end(), by_variant_pos, st.threads); // std::sort's own moves, its recursive calls on threads
 	st.iSNV = st.iInsertion = st.iDeletion = 0;
-	FILE *out = fopen(o.vcf_name.c_str(), "w");
-	if (!out) return;
-	fprintf(out, "##fileformat=VCFv4.1\n");
-	fprintf(out, "##reference=%s\n", o.index_prefix ? o.index_prefix : o.ref_fa);
-	fprintf(out, "##source=GSAlign %s\n", VERSION_STR);
-	fprintf(out, "##INFO=<ID=TYPE,Number=1,Type=String,Description=\"The type of allele, either SUBSTITUTE, INSERT, or DELETE.\">\n");
-	for (size_t i = 0; i < ix.names.size(); i++) fprintf(out, "##contig=<ID=%s,length=%d>\n", ix.names[i].c_str(), ix.len[i]);
-	fprintf(out, "#CHROM	POS	ID	REF	ALT	QUAL	FILTER	INFO\n");
-	// records are formatted into per-thread buffers, a batch at a time, and written in order.  "%s" of an allele stops at a
-	// NUL, which an allele cannot hold (query letters are alphabetic, reference letters ACGT), so lengths can be used as they are.
+	MappedOut out;
+	if (!out.open_file(o.vcf_name.c_str(), true)) return;
+	{
+		std::string hdr = "##fileformat=VCFv4.1\n";
+		hdr += std::string("##reference=") + (o.index_prefix ? o.index_prefix : o.ref_fa) + "\n";
+		hdr += std::string("##source=GSAlign ") + VERSION_STR + "\n";
+		hdr += "##INFO=<ID=TYPE,Number=1,Type=String,Description=\"The type of allele, either SUBSTITUTE, INSERT, or DELETE.\">\n";
+		for (size_t i = 0; i < ix.names.size(); i++) hdr += "##contig=<ID=" + ix.names[i] + ",length=" + std::to_string(ix.len[i]) + ">\n";
+		hdr += "#CHROM	POS	ID	REF	ALT	QUAL	FILTER	INFO\n";
+		put_bytes(out, hdr.data(), hdr.size());
+	}
+	// records are formatted into per-thread buffers, a batch at a time, and copied to their place in the mapped file by the
+	// same threads.  "%s" of an allele stops at a NUL, which an allele cannot hold (query letters are alphabetic, reference
+	// letters ACGT), so lengths can be used as they are.
 	const size_t batch = (size_t)emit_chunk() * 16;
 	const int nth = std::max(1, st.threads);
 	std::vector<std::string> buf((size_t)nth);
@@ -353,7 +539,11 @@ void output_variants(const Options &o, const HostIndex &ix, EmitState &st)
 				s += "\t100\t*\tTYPE="; s += MutType[v.type]; s += '\n';
 			}
 		});
-		for (int k = 0; k < nch; k++) fwrite(buf[(size_t)k].data(), 1, buf[(size_t)k].size(), out);
+		std::vector<size_t> at((size_t)nch + 1, 0);
+		for (int k = 0; k < nch; k++) at[(size_t)k + 1] = at[(size_t)k] + buf[(size_t)k].size();
+		char *p = out.reserve(at[(size_t)nch]);
+		if (!p) break;
+		parallel_chunks(nch, nth, [&](int k) { memcpy(p + at[(size_t)k], buf[(size_t)k].data(), buf[(size_t)k].size()); });
 	}
-	fclose(out);
+	out.close_file();
 }

@@ -5,12 +5,36 @@
 // records.bin, per query contig in file order: int32 n_blocks; gsa_block[n_blocks]; int64 n_frags; gsa_frag[n_frags];
 // int64 aln_bytes; char aln1[aln_bytes]; char aln2[aln_bytes]
 #include <stdlib.h>
+#include <algorithm>
 #include "host.h"
 
 template <typename T> static bool rd(FILE *f, T *p, size_t n) { return n == 0 || fread(p, sizeof(T), n, f) == n; }
 
+void gsa_test_sort_keys(uint64_t *keys, uint32_t *idx, size_t n, int threads); // emit.cpp
+
+// emit_harness sort <n> <distinct keys> <threads> <seed>: the emitters' threaded sort against std::sort on the same
+// (key, index) records -- the order of equal keys must come out the same (hazard H5)
+static int sort_mode(char **argv)
+{
+	size_t n = (size_t)atoll(argv[2]); uint64_t distinct = (uint64_t)atoll(argv[3]); int threads = atoi(argv[4]);
+	uint64_t x = (uint64_t)atoll(argv[5]) * 0x9E3779B97F4A7C15ull + 1;
+	struct K { uint64_t key; uint32_t idx; };
+	std::vector<K> want(n);
+	std::vector<uint64_t> keys(n); std::vector<uint32_t> idx(n);
+	for (size_t i = 0; i < n; i++) {
+		x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+		keys[i] = want[i].key = x % distinct; idx[i] = want[i].idx = (uint32_t)i;
+	}
+	std::sort(want.begin(), want.end(), [](const K &a, const K &b) { return a.key < b.key; });
+	gsa_test_sort_keys(keys.data(), idx.data(), n, threads);
+	for (size_t i = 0; i < n; i++) if (keys[i] != want[i].key || idx[i] != want[i].idx) { printf("differs at %zu\n", i); return 1; }
+	printf("same\n");
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
+	if (argc == 6 && std::string(argv[1]) == "sort") return sort_mode(argv);
 	if (argc != 7) return 2;
 	Options o;
 	o.index_prefix = argv[1]; o.query = argv[2];

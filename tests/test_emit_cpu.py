@@ -76,3 +76,11 @@ def test_emitters_match_reference_cli(workdir, harness, fmt, threads, prm, flags
         with open(ours + e, "rb") as a, open(theirs + e, "rb") as b:
             assert a.read() == b.read(), e
     assert os.path.getsize(ours + ".vcf") > 1000 and os.path.getsize(ours + ext) > 100_000
+
+
+@pytest.mark.parametrize("n,distinct,threads", [(0, 1, 4), (17, 3, 4), (300_000, 7, 1), (300_000, 1000, 8), (1_000_000, 50_000, 16), (400_000, 1, 5)])
+def test_threaded_sort_moves_like_std_sort(harness, n, distinct, threads):
+    """output_variants sorts (chr, pos) keys whose ties keep whatever order libstdc++'s introsort leaves (hazard H5): the
+    threaded sort must produce std::sort's exact permutation, ties included."""
+    out = subprocess.run([harness, "sort", str(n), str(distinct), str(threads), "7"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "same", out.stdout
