@@ -40,11 +40,16 @@ class Frag(C.Structure):
 FRAG_DTYPE = np.dtype([("rPos", "<i8"), ("qPos", "<i4"), ("qLen", "<i4"), ("rLen", "<i4"), ("bSeed", "<i4"),
                        ("aln_off", "<i8"), ("aln_len", "<i4"), ("reserved", "<i4")])
 BLOCK_DTYPE = np.dtype([("score", "<i4"), ("aln_len", "<i4"), ("bDup", "<i4"), ("n_frags", "<i4"), ("frag_beg", "<i8")])
+VARIANT_DTYPE = np.dtype([("rPos", "<i8"), ("qPos", "<i4"), ("gPos", "<i4"), ("len", "<i4"), ("kind", "<i4")])   # gsa_variant
 
 
 class Alignment(C.Structure):
     _fields_ = [("n_blocks", C.c_int32), ("blocks", C.c_void_p), ("n_frags", C.c_int64), ("frags", C.c_void_p),
                 ("aln_bytes", C.c_int64), ("aln1", C.c_void_p), ("aln2", C.c_void_p)]
+
+
+class VariantList(C.Structure):
+    _fields_ = [("n_variants", C.c_int64), ("variants", C.c_void_p), ("block_first", C.c_void_p), ("block_count", C.c_void_p)]
 
 
 class Timing(C.Structure):
@@ -59,7 +64,7 @@ EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "g
            "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes", "gsa_index_selfcheck",
            "gsa_comm_unique_id", "gsa_comm_init_rank", "gsa_comm_init_all", "gsa_comm_destroy", "gsa_outbox_reset", "gsa_outbox_reserve",
            "gsa_outbox_append", "gsa_outbox_bytes", "gsa_gather_records", "gsa_gather_records_all", "gsa_gather_wait", "gsa_inbox_device",
-           "gsa_inbox_host", "gsa_record_next"]
+           "gsa_inbox_host", "gsa_record_next", "gsa_variants"]
 
 
 def load_library() -> C.CDLL:
@@ -208,6 +213,16 @@ class Aligner:
         al = Alignment()
         self._chk(self.lib.gsa_align_contig(self.ctx, a.ctypes.data_as(C.c_char_p), C.c_uint32(a.shape[0]), C.byref(al)))
         return self._alignment(al)
+
+    def variants(self, n_blocks: int):
+        """N3: the variant records of the last fill()/align_contig() (device scan of the rows): (records, block_first,
+        block_count), the last two aligned with the blocks of that result"""
+        vl = VariantList()
+        self._chk(self.lib.gsa_variants(self.ctx, C.byref(vl)))
+        rec = _as_array(vl.variants, vl.n_variants, VARIANT_DTYPE).copy() if vl.n_variants else np.zeros(0, dtype=VARIANT_DTYPE)
+        if n_blocks == 0 or not vl.block_first:
+            return rec, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        return rec, _as_array(vl.block_first, n_blocks, np.dtype("<i8")).copy(), _as_array(vl.block_count, n_blocks, np.dtype("<i8")).copy()
 
     def align_contig_raw(self, a: np.ndarray) -> Alignment:
         """No copies of the result (bench path): returns the struct pointing into the library's pinned buffers."""

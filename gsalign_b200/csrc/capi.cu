@@ -37,6 +37,56 @@ int gsa_ensure_host(gsa_ctx *ctx, HostBuf &b, size_t bytes)
 	return GSA_OK;
 }
 
+// ---- small transfers that stay off the copy engines ---------------------------------------------------------------------
+// A lane waits on a handful of counters per contig.  As cudaMemcpyAsync calls those 8-byte reads queue on the same copy
+// engine as the bulk transfers of the OTHER lanes (a 125 MB contig upload, 100 MB of records coming back) and wait
+// milliseconds behind them.  Pinned host memory is mapped into the device's address space, so a few warps store / load
+// the words over PCIe directly instead; bulk transfers keep using the copy engines.
+#define GSA_SMALL_BYTES ((size_t)256 << 10)
+__global__ void k_copy_words(uint32_t *dst, const uint32_t *src, size_t n)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+static int small_copy(gsa_ctx *ctx, void *dst, const void *src, size_t bytes, bool to_host)
+{
+	if (bytes == 0) return GSA_OK;
+	void *mapped = nullptr;
+	void *host = to_host ? dst : const_cast<void *>(src);
+	if (bytes <= GSA_SMALL_BYTES && (bytes & 3) == 0 && (((uintptr_t)dst | (uintptr_t)src) & 3) == 0 && cudaHostGetDevicePointer(&mapped, host, 0) == cudaSuccess && mapped) {
+		const size_t n = bytes >> 2;
+		const unsigned grid = (unsigned)std::min<size_t>(64, (n + 255) / 256);
+		if (to_host) k_copy_words<<<grid, 256, 0, ctx->stream>>>((uint32_t *)mapped, (const uint32_t *)src, n);
+		else k_copy_words<<<grid, 256, 0, ctx->stream>>>((uint32_t *)dst, (const uint32_t *)mapped, n);
+		KERNEL_CHECK(ctx);
+		return GSA_OK;
+	}
+	(void)cudaGetLastError();
+	CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, ctx->stream));
+	return GSA_OK;
+}
+int gsa_small_d2h(gsa_ctx *ctx, void *host_pinned, const void *dev, size_t bytes) { return small_copy(ctx, host_pinned, dev, bytes, true); }
+
+// the first min(*d_count, cap) elements of a device table whose length is only known on the device
+__global__ void k_copy_counted(uint32_t *dst, const uint32_t *src, const int32_t *count, int words_per_elem, int cap)
+{
+	const size_t n = (size_t)max(0, min(*count, cap)) * (size_t)words_per_elem;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int gsa_small_d2h_counted(gsa_ctx *ctx, void *host_pinned, const void *dev, size_t elem_bytes, const int32_t *d_count, int cap)
+{
+	void *mapped = nullptr;
+	if ((elem_bytes & 3) == 0 && cudaHostGetDevicePointer(&mapped, host_pinned, 0) == cudaSuccess && mapped) {
+		k_copy_counted<<<16, 256, 0, ctx->stream>>>((uint32_t *)mapped, (const uint32_t *)dev, d_count, (int)(elem_bytes >> 2), cap);
+		KERNEL_CHECK(ctx);
+		return GSA_OK;
+	}
+	(void)cudaGetLastError();
+	CUDA_TRY(ctx, cudaMemcpyAsync(host_pinned, dev, elem_bytes * (size_t)cap, cudaMemcpyDeviceToHost, ctx->stream));
+	return GSA_OK;
+}
+int gsa_small_h2d(gsa_ctx *ctx, void *dev, const void *host_pinned, size_t bytes) { return small_copy(ctx, dev, host_pinned, bytes, false); }
+
 extern "C" {
 
 void gsa_default_params(gsa_params *p)
@@ -61,6 +111,9 @@ int gsa_create(int device, gsa_ctx **out)
 	memset(&ctx->tm, 0, sizeof(ctx->tm));
 	memset(&ctx->ix, 0, sizeof(ctx->ix));
 	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
+	// K1 reads single random 32-byte sectors of a multi-GB index; the L2 otherwise fetches 64 bytes from DRAM per miss (the
+	// neighbour sector is dead weight for a rank block or a suffix-array group).  GSA_L2_FETCH=32|64|128 sets the hint.
+	if (const char *g = getenv("GSA_L2_FETCH")) { int v = atoi(g); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); }
 	for (int i = 0; i < 12; i++) cudaEventCreate(&ctx->ev[i]);
 	if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GSA_ERR_CUDA; }
@@ -110,7 +163,7 @@ void gsa_destroy(gsa_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *bufs[] = {&ctx->d_occ, &ctx->d_txt, &ctx->d_sa, &ctx->d_ktab, &ctx->d_kbits, &ctx->d_cend, &ctx->d_seq, &ctx->d_qpk, &ctx->d_qinv,
 	                  &ctx->d_counter, &ctx->d_chain, &ctx->d_sq, &ctx->d_sr, &ctx->d_sl, &ctx->d_cub, &ctx->d_cq, &ctx->d_cr, &ctx->d_cl, &ctx->d_cb,
-	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum};
+	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum, &ctx->d_var};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	for (DevBuf &b : ctx->d_tmp) if (b.p) cudaFree(b.p);
 	gsa_comm_destroy(ctx);
@@ -120,7 +173,7 @@ void gsa_destroy(gsa_ctx *ctx)
 	if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);
 	if (ctx->ev_outbox) cudaEventDestroy(ctx->ev_outbox);
 	if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
-	HostBuf *hb[] = {&ctx->h_small, &ctx->h_stage, &ctx->h_frag, &ctx->h_aln1, &ctx->h_aln2, &ctx->h_blocks, &ctx->h_inbox, &ctx->h_rec};
+	HostBuf *hb[] = {&ctx->h_small, &ctx->h_stage, &ctx->h_frag, &ctx->h_aln1, &ctx->h_aln2, &ctx->h_blocks, &ctx->h_inbox, &ctx->h_rec, &ctx->h_var, &ctx->h_vrange};
 	for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
 	for (int i = 0; i < 12; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -193,7 +246,7 @@ static int contig_reset(gsa_ctx *ctx, uint32_t len)
 	if (len >= 0x7FFFFF00u) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_contig_begin: contig longer than 2^31 (positions are int in the reference)");
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	ctx->qlen = len; ctx->have_contig = false; ctx->have_seeds = false; ctx->have_cluster = false;
-	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->aln_bytes = 0; ctx->dp_timed = false;
+	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->aln_bytes = 0; ctx->dp_timed = false; ctx->have_fill = false;
 	memset(&ctx->tm, 0, sizeof(ctx->tm));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_seq, (size_t)len + 64));
 	return GSA_OK;
@@ -270,7 +323,9 @@ int gsa_fill(gsa_ctx *ctx, gsa_alignment *out)
 	if (!ctx->have_cluster) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_fill: call gsa_cluster first");
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+	ctx->have_fill = false;
 	GSA_TRY(gsa_impl_fill(ctx, out));
+	ctx->have_fill = true;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
 	CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[7]));
 	cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
@@ -281,6 +336,14 @@ int gsa_fill(gsa_ctx *ctx, gsa_alignment *out)
 	if (ctx->qlen > 0) cudaEventElapsedTime(&ctx->tm.k_seed_ms, ctx->ev[8], ctx->ev[9]);
 	if (ctx->dp_timed) cudaEventElapsedTime(&ctx->tm.k_dp_ms, ctx->ev[10], ctx->ev[11]);
 	return GSA_OK;
+}
+
+int gsa_variants(gsa_ctx *ctx, gsa_variant_list *out)
+{
+	if (!ctx || !out) return GSA_ERR_ARG;
+	if (!ctx->have_fill) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_variants: call gsa_fill first");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	return gsa_impl_variants(ctx, out);
 }
 
 int gsa_set_host_results(gsa_ctx *ctx, int enable)

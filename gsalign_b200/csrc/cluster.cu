@@ -520,11 +520,16 @@ struct FGapFlags {
 };
 
 // CalGapSimilarity (src/KmerAnalysis.cpp:78-121) for the gap in front of seed cand[blockIdx.x]; one warp per gap.
-// hist: ids of CreateKmerVecFromReadSeq are < 2048 (rolling ((id & 0xFF) << 2) + nt with nt in 0..4)
+// hist: ids of CreateKmerVecFromReadSeq are < 2048 (rolling ((id & 0xFF) << 2) + nt with nt in 0..4).
+// An id only depends on the five bases it ends on (each step keeps 8 bits of the previous id and shifts them by 2), so the
+// lanes take the positions of a gap side by side and count into shared-memory histograms with atomics.  The reference's
+// quirks on the query side (only the byte 'N' restarts the window, the window head is stale after a restart, any other
+// non-ACGT letter enters the id as 4 and carries) only show when the gap holds a letter outside ACGT: those gaps -- rare --
+// are walked by one lane exactly like the reference does.
 __global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, const int32_t *d_ncand, const int32_t *q, const int64_t *r, const int32_t *l,
                                                        const unsigned char *seq, DevIndex ix, uint8_t *flag)
 {
-	__shared__ unsigned short h1[2048], h2[2048];
+	__shared__ unsigned int h1[2048], h2[2048];
 	const int lane = threadIdx.x, ncand = *d_ncand;
 	for (int c = blockIdx.x; c < ncand; c += gridDim.x) { // a fixed grid of warps walks the list: its length only exists on the device
 	int i = cand[c];
@@ -543,9 +548,21 @@ __global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, cons
 	}
 	if (!similar && q_len <= GSA_MAX_SEED_GAP && r_len <= GSA_MAX_SEED_GAP) {
 		for (int k = lane; k < 2048; k += 32) { h1[k] = 0; h2[k] = 0; }
+		const unsigned char *s = seq + q1;
+		bool other = false;
+		for (int k = lane; k < q_len; k += 32) other |= gsa_nt4(s[k]) == 4;
+		other = __any_sync(0xffffffffu, other);
 		__syncwarp();
-		if (lane == 0) { // query k-mers, quirks kept: only the byte 'N' restarts, stale head after a restart
-			const unsigned char *s = seq + q1;
+		// reference k-mers (no N in the text): the 5-mer starting at k is the top 10 bits of the 16-base window there
+		for (int k = lane; k + 5 <= r_len; k += 32) atomicAdd(&h2[gsa_pk_window(ix.txt, (uint64_t)(r1 + k)) >> 22], 1u);
+		if (!other) { // query k-mers, ACGT only: plain 5-mers
+			for (int k = lane; k + 5 <= q_len; k += 32) {
+				uint32_t wid = 0;
+#pragma unroll
+				for (int j = 0; j < 5; j++) wid = (wid << 2) + (uint32_t)gsa_nt4(s[k + j]);
+				atomicAdd(&h1[wid], 1u);
+			}
+		} else if (lane == 0) { // quirks kept: only the byte 'N' restarts, stale head after a restart
 			uint32_t wid = 0, count = 0, head = 0, tail = 0, len = (uint32_t)q_len;
 			while (count < 5 && tail < len) { if (s[tail++] != 'N') count++; else count = 0; }
 			if (count == 5) {
@@ -563,15 +580,10 @@ __global__ void __launch_bounds__(32) k_gap_similarity(const int32_t *cand, cons
 					}
 				}
 			}
-		} else if (lane == 1 && r_len >= 5) { // reference k-mers (no N in the text)
-			uint32_t wid = 0;
-			for (int k = 0; k < 5; k++) wid = (wid << 2) + (uint32_t)gsa_pk_base(ix.txt, (uint64_t)(r1 + k));
-			h2[wid]++;
-			for (int k = 5; k < r_len; k++) { wid = ((wid & 0xFF) << 2) + (uint32_t)gsa_pk_base(ix.txt, (uint64_t)(r1 + k)); h2[wid]++; }
 		}
 		__syncwarp();
 		int common = 0;
-		for (int k = lane; k < 2048; k += 32) common += min((int)h1[k], (int)h2[k]);
+		for (int k = lane; k < 2048; k += 32) common += (int)min(h1[k], h2[k]);
 		for (int o = 16; o > 0; o >>= 1) common += __shfl_xor_sync(0xffffffffu, common, o);
 		similar = common > (q_len + r_len) * 0.1;
 	}
@@ -808,8 +820,8 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 	if (ctx->keep_dumps) { // stage 0 = the candidate blocks in the reference's -t 1 push order (group order, then qPos order), before RemoveOverlaps
 		PieceTable pl0;
 		GSA_TRY(queue_pieces(ctx, ws, ch, dc, dc + DC_N5, n, cq, cr, cl, cb, nullptr, 0, DC_NPL0, pl0));
-		CUDA_TRY(ctx, cudaMemcpyAsync(hc, dc, DC_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaMemcpyAsync(h_first, pl0.d, (size_t)std::min<int64_t>(PIECE_FIRST, n + 1) * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
+		GSA_TRY(gsa_small_d2h(ctx, hc, dc, DC_COUNT * 4));
+		GSA_TRY(gsa_small_d2h_counted(ctx, h_first, pl0.d, sizeof(Piece), dc + DC_NPL0, (int)std::min<int64_t>(PIECE_FIRST, n + 1)));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		const int64_t n5 = hc[DC_N5];
 		GSA_TRY(fetch_piece_table(ctx, pl0, hc[DC_NPL0], h_first, pc0));
@@ -845,13 +857,13 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 1, DC_NP1, pt1));
 		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 3, DC_NP2, pt2));
 		const int64_t first = std::min<int64_t>(PIECE_FIRST, n + 1);
-		CUDA_TRY(ctx, cudaMemcpyAsync(hc, dc, DC_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaMemcpyAsync(h_first, pt0.d, (size_t)first * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaMemcpyAsync(h_first + PIECE_FIRST, pt1.d, (size_t)first * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaMemcpyAsync(h_first + 2 * PIECE_FIRST, pt2.d, (size_t)first * sizeof(Piece), cudaMemcpyDeviceToHost, ctx->stream));
+		GSA_TRY(gsa_small_d2h(ctx, hc, dc, DC_COUNT * 4));
+		GSA_TRY(gsa_small_d2h_counted(ctx, h_first, pt0.d, sizeof(Piece), dc + DC_NP0, (int)first));
+		GSA_TRY(gsa_small_d2h_counted(ctx, h_first + PIECE_FIRST, pt1.d, sizeof(Piece), dc + DC_NP1, (int)first));
+		GSA_TRY(gsa_small_d2h_counted(ctx, h_first + 2 * PIECE_FIRST, pt2.d, sizeof(Piece), dc + DC_NP2, (int)first));
 		if (round == 0) {
 			GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, (size_t)first * 4));
-			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage.p, kept_score, (size_t)first * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			GSA_TRY(gsa_small_d2h_counted(ctx, ctx->h_stage.p, kept_score, 4, dc + DC_NB1, (int)first));
 		}
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // ---- first wait of the phase
 		if (round == 0) {
@@ -893,15 +905,15 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 	GSA_TRY(gsa_ensure(ctx, ctx->d_fblk, (size_t)(2 * total + 2) * 4));
 	GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, (size_t)nblk * (sizeof(NpBlock) + 8) + 64));
 	memcpy(ctx->h_stage.p, npb.data(), (size_t)nblk * sizeof(NpBlock));
-	CUDA_TRY(ctx, cudaMemcpyAsync(d_npb, ctx->h_stage.p, (size_t)nblk * sizeof(NpBlock), cudaMemcpyHostToDevice, ctx->stream));
+	GSA_TRY(gsa_small_h2d(ctx, d_npb, ctx->h_stage.p, (size_t)nblk * sizeof(NpBlock)));
 	k_k2_init<<<1, 64, 0, ctx->stream>>>(dc, (int32_t)total); // dc[DC_N0] = element count of the last chain
 	KERNEL_CHECK(ctx);
 	{ FNormalPairs f; f.nb = d_npb; f.nblk = nblk; f.q = cq; f.r = cr; f.l = cl; f.frag = (gsa_frag *)ctx->d_frag.p; f.fblk = (int32_t *)ctx->d_fblk.p; f.blk_frag_beg = d_fbeg; f.dc = dc;
 	  GSA_TRY(run_chain(ctx, ch, f, dc + DC_N0, total)); }
 	int64_t *h_fb = (int64_t *)((char *)ctx->h_stage.p + (size_t)nblk * sizeof(NpBlock) + 8);
 	h_fb = (int64_t *)(((uintptr_t)h_fb + 7) & ~(uintptr_t)7);
-	CUDA_TRY(ctx, cudaMemcpyAsync(hc, dc, DC_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaMemcpyAsync(h_fb, d_fbeg, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	GSA_TRY(gsa_small_d2h(ctx, hc, dc, DC_COUNT * 4));
+	GSA_TRY(gsa_small_d2h(ctx, h_fb, d_fbeg, (size_t)nblk * 8));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // ---- second wait of the phase
 	const int64_t nfr = hc[DC_NFR];
 	for (int k = 0; k < nblk; k++) {

@@ -18,10 +18,12 @@
 // cell (E>diag, F>both, E extended, F extended) are the VIMNMX predicates, collected over 8 steps into one word per
 // row and written as coalesced 256-byte warp rows to the flag pool (HBM; L2-resident at these sizes).
 // Strips of one problem run one after the other on one warp (small problems, several problems per CTA) or on W warps as
-// a pipeline: strip s+1 trails strip s by 72 steps, synchronised by a per-strip progress counter in shared memory.
-// Traceback: warp 0 of the problem stages windows of the flag rows back in shared memory (coalesced) and lane 0 walks
-// them (ksw_backtrack), writing both rows right-aligned into the problem's slot of the row pools, so nothing has to be
-// reversed afterwards.
+// a pipeline: strip s+1 trails strip s by 72 steps, synchronised by a per-strip progress counter in shared memory
+// (store.release by the lane that wrote the boundary row, load.acquire by the lane that reads it).
+// Traceback (ksw_backtrack): warp 0 of the problem follows the path run by run -- the decision bits of the next 32 cells
+// of the current diagonal / vertical / horizontal line are read together, a ballot finds where the run ends -- and writes
+// both rows right-aligned into the problem's slot of the row pools, so nothing has to be reversed afterwards.
+#include <cuda/atomic>
 #include "dpx.cuh"
 #include "fm.cuh"
 
@@ -76,7 +78,7 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 	const DpxLayout L = dpx_layout(m, n, STAGE);
 	uint32_t *bhe = dsm + (L.off_bhe >> 2) + 64;                                   // bhe[j] = {H(i0-1,j), E'(i0-1,j)}
 	uint16_t *a16 = (uint16_t *)((char *)dsm + L.off_a16) + 64;                    // a16[k] = selector halves for columns k, k-1
-	volatile int *prog = (volatile int *)((char *)dsm + L.off_prog);
+	int *prog = (int *)((char *)dsm + L.off_prog);   // per strip: 8-step groups finished (release by lane 31, acquire by lane 0 of the next strip)
 	unsigned char *qch = (unsigned char *)dsm + L.off_qch, *rch = (unsigned char *)dsm + L.off_rch;
 	uint2 *fl = (uint2 *)(gflags + P.flag_off);
 	const int G = L.G, cols = 8 * G + 8;
@@ -114,9 +116,12 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 		if (W == 1 && s > 0) __syncwarp(); // lane 31's boundary row of the previous strip is complete
 		for (int g = 0; g < Gs; g++) {
 			if (W > 1 && s > 0) {
-				if (lane == 0) { int need = min(g + 9, G); while (prog[s - 1] < need) { } }
+				if (lane == 0) {
+					const int need = min(g + 9, G);
+					cuda::atomic_ref<int, cuda::thread_scope_block> done(prog[s - 1]);
+					while (done.load(cuda::memory_order_acquire) < need) { }
+				}
 				__syncwarp();
-				__threadfence_block();
 			}
 			const int d0 = g << 3;
 			uint32_t f0 = 0, f1 = 0;
@@ -139,53 +144,65 @@ k_dpx(const DpProblem *prob, int nprob, DevIndex ix, uint8_t *gflags, uint32_t s
 			DPX_STEP(0) DPX_STEP(1) DPX_STEP(2) DPX_STEP(3) DPX_STEP(4) DPX_STEP(5) DPX_STEP(6) DPX_STEP(7)
 #undef DPX_STEP
 			fs[(size_t)g * 32] = make_uint2(f0, f1);
-			if (W > 1 && lane == 31) { __threadfence_block(); prog[s] = g + 1; }
+			if (W > 1 && lane == 31) cuda::atomic_ref<int, cuda::thread_scope_block>(prog[s]).store(g + 1, cuda::memory_order_release);
 		}
-		if (W > 1 && lane == 31) { __threadfence_block(); prog[s] = G; } // a short last strip still releases its (absent) follower
+		if (W > 1 && lane == 31) cuda::atomic_ref<int, cuda::thread_scope_block>(prog[s]).store(G, cuda::memory_order_release); // a short last strip still releases its (absent) follower
 	}
 	if (W == 1) __syncwarp(); else __syncthreads();
 	if (warp != 0) return;
 
-	// ---- traceback (ksw_backtrack, reference src/ksw2_alignment.cpp:25-68) by warp 0 ------------------------------
-	// The flags were written to the pool (HBM / L2): the warp stages a window of up to DPX_TBW step groups of the current
-	// strip (one coalesced 256-byte row per group) in shared memory and lane 0 walks while the path stays inside it
-	// (d = j + i%64 only ever decreases inside a strip).  Rows come out back to front, so they are written from the end of
-	// the problem's slot downwards: nothing is reversed afterwards.
-	uint2 *win = (uint2 *)((char *)dsm + L.off_win);
+	// ---- traceback (ksw_backtrack, reference src/ksw2_alignment.cpp:25-68) by warp 0, 32 cells at a time ---------------------
+	// The walk is a chain of straight runs: diagonal steps while a cell's decision says "diagonal", vertical / horizontal
+	// steps while the gap's "extended" bit stays set.  Which cells a run covers depends only on the decision bits of the cells
+	// on the run's own line, so the warp reads the bits of the next 32 cells of the line together (one word per lane from
+	// the flag pool, L2-resident), finds the first cell that ends the run with a ballot, and the lanes before it write their
+	// column of both rows side by side.  Rows come out back to front and are written from the end of the problem's slot
+	// downwards: nothing is reversed afterwards.
 	char *o1 = aln1 + P.out_off, *o2 = aln2 + P.out_off;
 	char *t1 = STAGE ? (char *)dsm + L.off_st : o1, *t2 = STAGE ? t1 + ((m + n + 3) & ~3) : o2;
-	const int wgroups = min(G, DPX_TBW);
-	int i = n - 1, j = m - 1, state = 0, cont = 0, pos = m + n, same = 0;
+	const uint32_t *fw = (const uint32_t *)fl;
+	int i = n - 1, j = m - 1, state = 0, pos = m + n, same = 0;
 	__threadfence_block();
 	while (i >= 0 && j >= 0) {
-		const int s = i >> 6, g_hi = (j + (i & 63)) >> 3, g_lo = max(0, g_hi - (wgroups - 1));
-		const uint2 *src = fl + (size_t)s * G * 32 + lane;
-		for (int g = g_lo; g <= g_hi; g++) win[(g - g_lo) * 32 + lane] = __ldcg(src + (size_t)g * 32);
-		__syncwarp();
-		if (lane == 0) {
-			const uint32_t *w32 = (const uint32_t *)win;
-			while (i >= 0 && j >= 0 && (i >> 6) == s) {
-				int ii = i & 63, d = j + ii, g = d >> 3;
-				if (g < g_lo) break;
-				uint32_t w = w32[((g - g_lo) * 32 + (ii >> 1)) * 2 + (ii & 1)];
-				int t = (w >> ((d & 7) << 2)) & 15;
-				if (state == 0 || !cont) state = (t & 2) ? 2 : (t & 1);
-				char c1, c2;
-				if (state == 0) { c1 = (char)rch[j]; c2 = (char)qch[i]; i--; j--; }
-				else if (state == 1) { c1 = '-'; c2 = (char)qch[i]; cont = (t >> 2) & 1; i--; }
-				else { c1 = (char)rch[j]; c2 = '-'; cont = (t >> 3) & 1; j--; }
-				if (!STAGE) same += gsa_nt4((unsigned char)c1) == gsa_nt4((unsigned char)c2); // nt4 classes: '-' equals a non-ACGT letter (H7)
-				pos--; t1[pos] = c1; t2[pos] = c2;
-			}
+		// cell of this lane on the current line: (i - lane, j - lane) on a diagonal, (i - lane, j) in E, (i, j - lane) in F
+		const int ik = state == 2 ? i : i - lane, jk = state == 1 ? j : j - lane;
+		const bool in = ik >= 0 && jk >= 0;
+		int t = 0;
+		if (in) {
+			const int ii = ik & 63, d = jk + ii;
+			t = (int)(__ldcg(fw + (((size_t)(ik >> 6) * G + (d >> 3)) * 32 + (ii >> 1)) * 2 + (ii & 1)) >> ((d & 7) << 2)) & 15;
 		}
-		__syncwarp();
-		i = __shfl_sync(DPX_FULL, i, 0); j = __shfl_sync(DPX_FULL, j, 0);
+		if (state == 0) { // fresh cells: the run goes on while neither E nor F wins
+			const unsigned stop = __ballot_sync(DPX_FULL, !in || (t & 3) != 0);
+			const int c = stop ? __ffs(stop) - 1 : 32;
+			if (lane < c) {
+				const char c1 = (char)rch[jk], c2 = (char)qch[ik];
+				if (!STAGE) same += gsa_nt4((unsigned char)c1) == gsa_nt4((unsigned char)c2);
+				t1[pos - 1 - lane] = c1; t2[pos - 1 - lane] = c2;
+			}
+			pos -= c; i -= c; j -= c;
+			if (c < 32) { const int ts = __shfl_sync(DPX_FULL, t, c); state = (ts & 2) ? 2 : (ts & 1); } // 0 only when the line left the matrix
+		} else { // inside a gap: cell k belongs to it if every cell before it had its "extended" bit set
+			const int bit = state == 1 ? 4 : 8;
+			const unsigned stop = __ballot_sync(DPX_FULL, !in || !(t & bit));
+			const int first = stop ? __ffs(stop) - 1 : 32;
+			const bool last_in = __shfl_sync(DPX_FULL, (int)in, first & 31) != 0;
+			const int c = first == 32 ? 32 : first + (last_in ? 1 : 0);   // the cell that clears the bit is still part of the gap
+			if (lane < c) {
+				const char c1 = state == 1 ? '-' : (char)rch[jk], c2 = state == 1 ? (char)qch[ik] : '-';
+				if (!STAGE) same += gsa_nt4((unsigned char)(state == 1 ? c2 : c1)) == 4; // nt4 classes: '-' equals a non-ACGT letter (H7)
+				t1[pos - 1 - lane] = c1; t2[pos - 1 - lane] = c2;
+			}
+			pos -= c;
+			if (state == 1) i -= c; else j -= c;
+			if (first < 32) state = 0;
+		}
 	}
-	if (lane == 0) {
-		for (; i >= 0; i--) { pos--; t1[pos] = '-'; t2[pos] = (char)qch[i]; if (!STAGE) same += gsa_nt4(qch[i]) == 4; }
-		for (; j >= 0; j--) { pos--; t1[pos] = (char)rch[j]; t2[pos] = '-'; if (!STAGE) same += gsa_nt4(rch[j]) == 4; }
-	}
-	pos = __shfl_sync(DPX_FULL, pos, 0);
+	for (int k = i - lane; k >= 0; k -= 32) { t1[pos - 1 - (i - k)] = '-'; t2[pos - 1 - (i - k)] = (char)qch[k]; if (!STAGE) same += gsa_nt4(qch[k]) == 4; }
+	if (i >= 0) { pos -= i + 1; i = -1; }
+	for (int k = j - lane; k >= 0; k -= 32) { t1[pos - 1 - (j - k)] = (char)rch[k]; t2[pos - 1 - (j - k)] = '-'; if (!STAGE) same += gsa_nt4(rch[k]) == 4; }
+	if (j >= 0) { pos -= j + 1; j = -1; }
+	if (!STAGE) for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(DPX_FULL, same, o);
 	const int len = m + n - pos;
 	if (STAGE) { // coalesced copy-out + CountIdenticalPairs (src/ProcessCandidateAlignment.cpp:38-47; '-' is class 4, never equal to ACGT)
 		__syncwarp();

@@ -65,12 +65,10 @@ __host__ __device__ inline PackLayout pack_layout(int LG, int Mx, int Nx)
 	return L;
 }
 
-#define DPX_TBW 16   // traceback window, in 8-step groups (one 256-byte flag row each)
-
 struct DpxLayout { // byte offsets into the shared memory slot of one problem in k_dpx
 	int G;          // 8-step groups per strip
 	int nstrips;    // 64-row strips
-	uint32_t off_bhe, off_a16, off_prog, off_qch, off_rch, off_win, off_st, total;
+	uint32_t off_bhe, off_a16, off_prog, off_qch, off_rch, off_st, total;
 };
 
 // stage: the rows are assembled in shared memory and copied out coalesced (small problems)
@@ -87,7 +85,6 @@ __host__ __device__ inline DpxLayout dpx_layout(int m, int n, bool stage)
 	L.off_qch = o; o += ((uint32_t)n + 3u) & ~3u;
 	L.off_rch = o; o += ((uint32_t)m + 3u) & ~3u;
 	o = (o + 7u) & ~7u;
-	L.off_win = o; o += 256u * (uint32_t)(L.G < DPX_TBW ? L.G : DPX_TBW);
 	L.off_st = o; if (stage) o += 2u * (((uint32_t)(m + n) + 3u) & ~3u);
 	L.total = (o + 15u) & ~15u;
 	return L;

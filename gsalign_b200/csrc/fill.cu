@@ -186,7 +186,7 @@ static int run_dp_binned(gsa_ctx *ctx, Ws3 &ws, const DpProblem *d_prob, DpProbl
 	k_dp_permute<<<gsa_grid(ndp, 256), 256, 0, ctx->stream>>>(d_prob, idx_out, d_sorted, ndp);
 	KERNEL_CHECK(ctx);
 	DpStats *st = (DpStats *)((char *)ctx->h_small.p + 256);
-	CUDA_TRY(ctx, cudaMemcpyAsync(st, d_st, sizeof(DpStats), cudaMemcpyDeviceToHost, ctx->stream));
+	GSA_TRY(gsa_small_d2h(ctx, st, d_st, sizeof(DpStats)));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->tm.dp_cells = (int64_t)st->cells;
 	if (st->count[DP_BIN_TOOLONG]) return gsa_fail(ctx, GSA_ERR_LIMIT, "DP fragment longer than %d", DP_MAX_DIM);
@@ -258,9 +258,9 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 		ctx->tm.launches += 2;
 	}
 	int64_t *hs = (int64_t *)ctx->h_small.p;
-	CUDA_TRY(ctx, cudaMemcpyAsync(hs, row_off + nfr, 8, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaMemcpyAsync(hs + 1, flag_off + nfr, 8, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaMemcpyAsync(hs + 2, d_ndp, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	GSA_TRY(gsa_small_d2h(ctx, hs, row_off + nfr, 8));
+	GSA_TRY(gsa_small_d2h(ctx, hs + 1, flag_off + nfr, 8));
+	GSA_TRY(gsa_small_d2h(ctx, hs + 2, d_ndp, 4));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	int64_t row_bytes = hs[0], flag_bytes = hs[1], ndp = *(int32_t *)(hs + 2);
 	ctx->aln_bytes = row_bytes;
@@ -293,7 +293,7 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln2.p, a2, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
 		}
 	}
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_blocks.p, bsum, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	GSA_TRY(gsa_small_d2h(ctx, ctx->h_blocks.p, bsum, (size_t)nblk * 8));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	// ---- identity filter + final order (src/GSAlign.cpp:529-540): O(#blocks), same std::sort as the reference
 	const unsigned int *hb = (const unsigned int *)ctx->h_blocks.p;

@@ -58,7 +58,7 @@ struct HostBuf { // pinned
 	size_t cap = 0;
 };
 
-// one contig-end table entry of ChrLocMap (reference src/bwt_index.cpp:247-252)
+// one contig-end table entry of ChrLocMap (reference src/bwt_index.cpp:247-252); pad = the contig's length
 struct ContigEnd { int64_t end; int32_t idx; int32_t pad; };
 
 struct BlockHdr { // host-side view of one candidate alignment block (a range of the device seed array)
@@ -135,6 +135,10 @@ struct gsa_ctx {
 	DevBuf d_bsum;                 // per block {aln_len, score}
 	HostBuf h_frag, h_aln1, h_aln2, h_blocks;
 	std::vector<gsa_block> out_blocks;
+	bool have_fill = false;        // d_frag / d_aln1 / d_aln2 hold the result of gsa_fill for the current contig
+
+	// N3 (variants.cu): variant records of the last gsa_fill result
+	DevBuf d_var; HostBuf h_var, h_vrange;
 
 	// multi-GPU record gather (gather.cu): the outbox of this GPU (owner context) and, on the root, the arrived images
 	void *nccl_comm = nullptr; int comm_rank = 0, comm_size = 0;
@@ -152,6 +156,12 @@ struct gsa_ctx {
 int gsa_fail(gsa_ctx *ctx, int code, const char *fmt, ...);
 int gsa_ensure(gsa_ctx *ctx, DevBuf &b, size_t bytes);
 int gsa_ensure_host(gsa_ctx *ctx, HostBuf &b, size_t bytes);
+// small transfers between device memory and PINNED host memory, asynchronous on ctx->stream, done by a few warps over the
+// mapped host pointer instead of a copy engine (capi.cu); sizes above 256 KB fall back to cudaMemcpyAsync
+int gsa_small_d2h(gsa_ctx *ctx, void *host_pinned, const void *dev, size_t bytes);
+int gsa_small_h2d(gsa_ctx *ctx, void *dev, const void *host_pinned, size_t bytes);
+// the first min(*d_count, cap) elements of a device table whose length is only known on the device
+int gsa_small_d2h_counted(gsa_ctx *ctx, void *host_pinned, const void *dev, size_t elem_bytes, const int32_t *d_count, int cap);
 
 #define CUDA_TRY(ctx, call)                                                                          \
 	do {                                                                                             \
@@ -184,5 +194,6 @@ void gsa_host_dedup(const gsa_ctx *ctx, std::vector<BlockHdr> &vec);
 void gsa_host_remove_bad(std::vector<BlockHdr> &vec);
 int gsa_host_chr_idx(const gsa_ctx *ctx, int64_t rpos, int64_t *end_out);
 int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out);
+int gsa_impl_variants(gsa_ctx *ctx, gsa_variant_list *out);
 int gsa_impl_dp_batch(gsa_ctx *ctx, int32_t n_pairs, const char *ref, const int64_t *ref_off, const char *qry,
                       const int64_t *qry_off, char *out1, char *out2, int32_t *out_len, int32_t *out_identical, float *kernel_ms);

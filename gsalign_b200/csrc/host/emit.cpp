@@ -454,12 +454,68 @@ static void scan_fragments(const HostIndex &ix, const std::string &seq, const Co
 	}
 }
 
+void ContigResult::assign_variants(const gsa_variant_list &v)
+{
+	vars.assign(v.variants, v.variants + v.n_variants);
+	var_first.assign(v.block_first, v.block_first + blocks.size());
+	var_count.assign(v.block_count, v.block_count + blocks.size());
+	have_vars = true;
+}
+
+// Records [v_beg, v_end) of the device's variant list (gsa_variants) -> the reference's Variant_t fields: the alleles are
+// substrings of the query and of the reference text at the record's coordinates (include/gsalign_b200.h, gsa_variant_kind)
+static void records_to_variants(const HostIndex &ix, const std::string &seq, const ContigResult &r, int chr_idx, int64_t v_beg, int64_t v_end,
+                                std::vector<Variant> &out, std::string &pool, VarCounts &cnt)
+{
+	Variant v; v.chr_idx = chr_idx;
+	out.reserve((size_t)(v_end - v_beg));
+	for (int64_t k = v_beg; k < v_end; k++) {
+		const gsa_variant &d = r.vars[(size_t)k];
+		v.pos = d.gPos; v.off = pool.size();
+		const bool text_ref = d.kind != GSA_VAR_INS;          // REF comes from the reference text (an in-fragment insertion takes the query base, H6)
+		const bool long_ref = d.kind == GSA_VAR_DEL || d.kind == GSA_VAR_FRAG_DEL;
+		const bool long_alt = d.kind == GSA_VAR_INS || d.kind == GSA_VAR_FRAG_INS;
+		v.ref_len = long_ref ? (uint32_t)d.len + 1u : 1u;
+		if (text_ref) for (uint32_t i = 0; i < v.ref_len; i++) pool += ix.text(d.rPos + i);
+		else pool += seq[(size_t)d.qPos];
+		if (long_alt) { // substr clamps at the end of the string
+			const size_t n = std::min((size_t)d.len + 1, seq.size() - (size_t)d.qPos);
+			pool.append(seq, (size_t)d.qPos, n); v.alt_len = (uint32_t)n;
+		} else if (d.kind == GSA_VAR_DEL) { pool += pool[(size_t)v.off]; v.alt_len = 1; }
+		else { pool += seq[(size_t)d.qPos]; v.alt_len = 1; }
+		if (d.kind == GSA_VAR_SNV) { v.type = 0; cnt.snv++; }
+		else if (long_alt) { v.type = 1; cnt.ins++; }
+		else { v.type = 2; cnt.del++; }
+		out.push_back(v);
+	}
+}
+
 void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, const ContigResult &r, EmitState &st)
 {
 	const std::string &seq = q[(size_t)qidx].seq;
-	for (const gsa_block &b : r.blocks) {
+	for (size_t bi = 0; bi < r.blocks.size(); bi++) {
+		const gsa_block &b = r.blocks[bi];
 		if (b.bDup) continue;
 		const int chr_idx = gen_coordinate(ix, r.frags[(size_t)b.frag_beg].rPos).ChromosomeIdx;
+		if (r.have_vars) { // the device found the records: the host only fetches the alleles
+			const int64_t v0 = r.var_first[bi], nv = r.var_count[bi];
+			const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(st.threads, nv / ((int64_t)emit_chunk() * 4)));
+			std::vector<std::vector<Variant> > part((size_t)nch);
+			std::vector<std::string> pool((size_t)nch);
+			std::vector<VarCounts> cnt((size_t)nch);
+			parallel_chunks(nch, st.threads, [&](int k) {
+				records_to_variants(ix, seq, r, chr_idx, v0 + nv * k / nch, v0 + nv * (k + 1) / nch, part[(size_t)k], pool[(size_t)k], cnt[(size_t)k]);
+			});
+			for (int k = 0; k < nch; k++) {
+				const uint64_t base = st.alleles.size();
+				st.alleles += pool[(size_t)k];
+				size_t at = st.variants.size();
+				st.variants.insert(st.variants.end(), part[(size_t)k].begin(), part[(size_t)k].end());
+				for (size_t i = at; i < st.variants.size(); i++) st.variants[i].off += base;
+				st.iSNV += cnt[(size_t)k].snv; st.iInsertion += cnt[(size_t)k].ins; st.iDeletion += cnt[(size_t)k].del;
+			}
+			continue;
+		}
 		// fragments are independent: big blocks are scanned by several threads and their records appended in fragment order,
 		// i.e. in exactly the order the serial loop pushes them (the order matters: the final sort is unstable)
 		const int64_t nf = b.n_frags;

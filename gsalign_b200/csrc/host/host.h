@@ -68,7 +68,13 @@ struct ContigResult {
 	std::vector<gsa_block> blocks;
 	std::vector<gsa_frag> frags;
 	std::string aln1, aln2;
+	// N3: the variant records found on the device (gsa_variants), with the range of every block; empty + have_vars false =
+	// the host scans the rows itself (records that came through the multi-GPU gather carry no variant list)
+	std::vector<gsa_variant> vars;
+	std::vector<int64_t> var_first, var_count;
+	bool have_vars = false;
 	void assign(const gsa_alignment &a);
+	void assign_variants(const gsa_variant_list &v);
 };
 
 struct EmitState {                 // running totals of GenomeComparison (src/GSAlign.cpp:14-15)

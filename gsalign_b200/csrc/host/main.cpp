@@ -193,6 +193,9 @@ int main(int argc, char *argv[])
 		if (gsa_comm_init_all(owners.data(), ngpu) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(owners[0])); return 1; }
 		for (int g = 0; g < ngpu; g++) for (gsa_ctx *c : ctx[g]) gsa_set_host_results(c, 0);
 	}
+	// GSA_VARIANTS=host: VariantIdentification scans the rows on the host instead of taking the device's records (gsa_variants)
+	const char *vmode = getenv("GSA_VARIANTS");
+	const bool device_variants = !(vmode && strcmp(vmode, "host") == 0);
 	tick("lanes ready");
 
 	// ---- GenomeComparison ------------------------------------------------------------------------------------------------
@@ -209,7 +212,11 @@ int main(int argc, char *argv[])
 			gsa_alignment al;
 			int rc = gsa_align_contig(c, query[qi].seq.data(), (uint32_t)query[qi].seq.size(), &al);
 			if (rc == 0 && nccl_gather) rc = gsa_outbox_append(owners[g], c, qi);
-			else if (rc == 0) results[qi].assign(al); // the copy out of the pinned buffers runs outside the lock: slot qi is this lane's alone
+			else if (rc == 0) { // the copy out of the pinned buffers runs outside the lock: slot qi is this lane's alone
+				results[qi].assign(al);
+				gsa_variant_list vl;
+				if (o.vcf && device_variants && al.n_blocks > 0 && (rc = gsa_variants(c, &vl)) == 0) results[qi].assign_variants(vl);
+			}
 			std::unique_lock<std::mutex> lk(mu);
 			if (rc != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(c)); failed = true; }
 			if (!nccl_gather || rc != 0) done[qi] = 1;

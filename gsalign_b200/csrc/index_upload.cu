@@ -170,9 +170,9 @@ static int build_contig_table(gsa_ctx *ctx, uint64_t n, int64_t l_pac, int n_con
 	ctx->cend.clear(); ctx->contig_off.assign(off, off + n_contigs); ctx->contig_len.assign(len, len + n_contigs);
 	int64_t total = 0;
 	for (int i = 0; i < n_contigs; i++) {
-		ContigEnd f; f.end = total + len[i] - 1; f.idx = i; f.pad = 0;
+		ContigEnd f; f.end = total + len[i] - 1; f.idx = i; f.pad = len[i];
 		total += len[i];
-		ContigEnd r; r.end = ((int64_t)n - total) + len[i] - 1; r.idx = i; r.pad = 0;
+		ContigEnd r; r.end = ((int64_t)n - total) + len[i] - 1; r.idx = i; r.pad = len[i];
 		ctx->cend.push_back(f); ctx->cend.push_back(r);
 	}
 	if (total != l_pac) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_index_upload: contig lengths do not sum to l_pac");

@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <algorithm>
 
+#define SEED_PAD32 336   // 32-base words of padding behind the packed query and its bitmap (> SEED_IWORDS + 4, see k_seed)
+
 // ---- K0: 2-bit packing of the query + invalid-base bitmap -----------------------------------------
 // one thread per 32 bases: reads 32 chars (two 16-byte loads), writes two packed words + one bitmap word
 __global__ void k_pack_query(const unsigned char *seq, uint32_t qlen, uint32_t *qpk, uint32_t *qinv, uint32_t nwords32)
@@ -52,7 +54,8 @@ __global__ void k_pack_query(const unsigned char *seq, uint32_t qlen, uint32_t *
 
 int gsa_impl_pack_query(gsa_ctx *ctx)
 {
-	uint32_t nw = (ctx->qlen >> 5) + 2; // padded: bases past qlen read as invalid
+	// padded: bases past qlen read as invalid; the padding covers the aligned bulk copy K1 stages the last chunk with
+	uint32_t nw = (ctx->qlen >> 5) + 2 + SEED_PAD32;
 	GSA_TRY(gsa_ensure(ctx, ctx->d_qpk, (size_t)nw * 8 + 16));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_qinv, (size_t)nw * 4 + 16));
 	k_pack_query<<<gsa_grid(nw, 256), 256, 0, ctx->stream>>>((const unsigned char *)ctx->d_seq.p, ctx->qlen, (uint32_t *)ctx->d_qpk.p, (uint32_t *)ctx->d_qinv.p, nw);
@@ -389,15 +392,38 @@ __global__ void __launch_bounds__(32 * SEED_WARPS)
 k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 {
 	__shared__ uint32_t s_vis[SEED_WARPS][32][SEED_VIS_WORDS];
-	__shared__ uint32_t s_q[SEED_WARPS][SEED_QWORDS], s_i[SEED_WARPS][SEED_IWORDS];
+	// The chunk's packed query (2.5 KB) and invalid-base bitmap (1.3 KB) are read by every search step of the warp: they are
+	// staged in shared memory by two bulk copies (cp.async.bulk, the TMA unit's linear mode) that complete on the warp's own
+	// mbarrier -- one elected lane issues them, no lane spends load instructions on it.  A bulk copy wants 16-byte aligned
+	// addresses and sizes: it starts at the aligned word below the chunk's first word (the chunk then sits 0..3 words into
+	// the buffer) and the arrays are padded by K0 far enough for the last chunk's copy to stay inside them.
+	__shared__ __align__(16) uint32_t s_q[SEED_WARPS][SEED_QWORDS + 4], s_i[SEED_WARPS][SEED_IWORDS + 4];
+	__shared__ __align__(8) unsigned long long s_bar[SEED_WARPS];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	uint32_t chunk = blockIdx.x * SEED_WARPS + wib;
 	if (chunk >= A.nchunks) return;
 	uint32_t cs = chunk * GSA_SEED_CHUNK, stop = min(cs + GSA_SEED_CHUNK, A.qlen);
-	ChunkQuery Q; Q.sq = s_q[wib]; Q.si = s_i[wib]; Q.qb = cs; Q.ib = cs & ~31u;
-	for (uint32_t w = lane; w < SEED_QWORDS; w += 32) { uint32_t g = (cs >> 4) + w; s_q[wib][w] = g < A.qpk_words ? __ldg(A.qpk + g) : 0u; }
-	for (uint32_t w = lane; w < SEED_IWORDS; w += 32) { uint32_t g = (cs >> 5) + w; s_i[wib][w] = g < A.qinv_words ? __ldg(A.qinv + g) : 0xFFFFFFFFu; }
-	__syncwarp();
+	const uint32_t wq = cs >> 4, wi = cs >> 5;
+	ChunkQuery Q; Q.sq = s_q[wib] + (wq & 3u); Q.si = s_i[wib] + (wi & 3u); Q.qb = cs; Q.ib = cs & ~31u;
+	{
+		const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[wib]);
+		constexpr uint32_t QB = (SEED_QWORDS + 4) * 4, IB = (SEED_IWORDS + 4) * 4;
+		static_assert(QB % 16 == 0 && IB % 16 == 0, "bulk copies move multiples of 16 bytes");
+		if (lane == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(QB + IB) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			             :: "r"((uint32_t)__cvta_generic_to_shared(s_q[wib])), "l"(A.qpk + (wq & ~3u)), "r"(QB), "r"(bar) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			             :: "r"((uint32_t)__cvta_generic_to_shared(s_i[wib])), "l"(A.qinv + (wi & ~3u)), "r"(IB), "r"(bar) : "memory");
+		}
+		__syncwarp();
+		uint32_t done;
+		do {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+		} while (!done);
+	}
 	uint32_t base = min(cs + lane * SEED_SUB, stop), limit = min(base + SEED_SUB, stop);
 	uint32_t *vis = s_vis[wib][lane];
 #pragma unroll
@@ -511,14 +537,14 @@ int gsa_impl_seed(gsa_ctx *ctx)
 		if (nchunks > 0) {
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
 			SeedArgs sa; sa.qpk = (const uint32_t *)ctx->d_qpk.p; sa.qinv = (const uint32_t *)ctx->d_qinv.p; sa.qlen = ctx->qlen; sa.nchunks = nchunks;
-			sa.qpk_words = 2 * ((ctx->qlen >> 5) + 2); sa.qinv_words = (ctx->qlen >> 5) + 2;
+			sa.qpk_words = 2 * ((ctx->qlen >> 5) + 2 + SEED_PAD32); sa.qinv_words = (ctx->qlen >> 5) + 2 + SEED_PAD32;
 			sa.min_seed_len = ctx->prm.min_seed_len; sa.sensitive = ctx->prm.sensitive;
 			if (ctx->ix.wide) k_seed<true><<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so, (uint32_t *)ctx->d_tmp[7].p);
 			else k_seed<false><<<gsa_grid(nchunks, SEED_WARPS), 32 * SEED_WARPS, 0, ctx->stream>>>(ctx->ix, sa, so, (uint32_t *)ctx->d_tmp[7].p);
 			KERNEL_CHECK(ctx);
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
 		}
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small.p, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		GSA_TRY(gsa_small_d2h(ctx, ctx->h_small.p, d_count, 8));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		produced = *(unsigned long long *)ctx->h_small.p;
 		if (produced <= cap) break;
@@ -549,7 +575,7 @@ int gsa_impl_seed(gsa_ctx *ctx)
 		k_seed_keys<<<gsa_grid(nraw, 256), 256, 0, ctx->stream>>>((int32_t *)ctx->d_tmp[0].p, (int64_t *)ctx->d_tmp[1].p, (int32_t *)ctx->d_tmp[2].p, (const uint32_t *)ctx->d_tmp[7].p,
 		                                                         k_in, v_in, nraw, d_count + 1, ctx->qlen, qbits, two_pass ? 1 : 0);
 		KERNEL_CHECK(ctx);
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small.p, d_count + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		GSA_TRY(gsa_small_d2h(ctx, ctx->h_small.p, d_count + 1, 8));
 		if (!two_pass) GSA_TRY(sort_pairs(k_in, k_out, v_in, v_out, pdbits + qbits));
 		else { // stable LSD: by qPos first, then by PosDiff
 			GSA_TRY(sort_pairs(k_in, k_out, v_in, v_out, 32));

@@ -160,6 +160,34 @@ int gsa_set_host_results(gsa_ctx *ctx, int enable);
  * multi-GPU host packs into its outbox for the single record gather over NVLink. */
 int gsa_result_device(gsa_ctx *ctx, gsa_alignment *out);
 
+/* N3  VariantIdentification (src/SeqVariant.cpp:12-119) where the records are: one compact record per sequence variant of
+ * the last gsa_fill() result, found by scanning the aligned rows on the device, in the order the reference pushes them
+ * inside a block (fragment order, column order).  The alleles are not copied: they are substrings of the query contig
+ * and of the reference text at the coordinates below, which the host owns (see gsa_variant_kind). */
+enum gsa_variant_kind {
+	GSA_VAR_SNV = 0,       /* REF = text[rPos], ALT = query[qPos]                                         (SeqVariant.cpp:57-64,97-105) */
+	GSA_VAR_INS = 1,       /* insertion inside an aligned fragment: REF = query[qPos] (sic, hazard H6),
+	                          ALT = query[qPos .. qPos+len]                                               (SeqVariant.cpp:69-81) */
+	GSA_VAR_DEL = 2,       /* deletion inside an aligned fragment: REF = text[rPos .. rPos+len], ALT = text[rPos]   (:83-95) */
+	GSA_VAR_FRAG_INS = 3,  /* fragment with rLen = 0: REF = text[rPos], ALT = query[qPos .. qPos+len]              (:43-54) */
+	GSA_VAR_FRAG_DEL = 4   /* fragment with qLen = 0: REF = text[rPos .. rPos+len], ALT = query[qPos]              (:31-42) */
+};
+typedef struct {
+	int64_t rPos;              /* text coordinate (T = F . revcomp(F)) of the variant's anchor base */
+	int32_t qPos;              /* query coordinate of the anchor base */
+	int32_t gPos;              /* GenCoordinateInfo(rPos).gPos: the VCF POS column (src/tools.cpp:120-140) */
+	int32_t len;               /* SNV: 1; otherwise the number of inserted / deleted bases */
+	int32_t kind;              /* gsa_variant_kind */
+} gsa_variant;
+typedef struct {
+	int64_t n_variants;
+	const gsa_variant *variants;   /* pinned host memory, all fragments of the contig in fragment order */
+	const int64_t *block_first;    /* per block of the last gsa_fill() output (same order): first record of the block ... */
+	const int64_t *block_count;    /* ... and how many (blocks with bDup set are listed too; the reference skips them) */
+} gsa_variant_list;
+/* call after gsa_fill() / gsa_align_contig() on the same context, before the next contig */
+int gsa_variants(gsa_ctx *ctx, gsa_variant_list *out);
+
 /* The three phases back to back on a host buffer: the call GenomeComparison() would make per contig. */
 int gsa_align_contig(gsa_ctx *ctx, const char *seq, uint32_t len, gsa_alignment *out);
 

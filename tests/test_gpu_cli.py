@@ -180,3 +180,60 @@ def test_nccl_gather_cli_same_bytes(workdir):
     for ext in ("maf", "vcf"):
         for other in ("nn", "nh"):
             assert filecmp.cmp(os.path.join(d, f"n1.{ext}"), os.path.join(d, f"{other}.{ext}"), shallow=False), (other, ext)
+
+
+def test_device_variant_records_match_reference_vcf(workdir):
+    """N3: gsa_variants() -- the device scan of the aligned rows -- against the unmodified reference's VCF: every record,
+    with its alleles fetched from the query and the reference text at the record's coordinates, must be a line of the
+    reference's file and vice versa (the CLI tests pin the order)."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/GSAlign not built")
+    from conftest import build_index
+    from test_gpu_pipeline import make_rearranged
+    from gsalign_b200 import bwaidx, capi, synth
+    d = make_rearranged(workdir)
+    if not os.path.exists(os.path.join(d, "ref.sa")):
+        build_index(os.path.join(d, "ref.fa"), os.path.join(d, "ref"))
+    run(REF, d, ["-t", "1", "-i", "ref", "-q", "qry.fa", "-o", "n3ref"])
+    want = sorted(l for l in open(os.path.join(d, "n3ref.vcf")).read().splitlines() if not l.startswith("#"))
+    bi = bwaidx.load(os.path.join(d, "ref"))
+    T = np.frombuffer(b"ACGT", dtype=np.uint8)[bwaidx.text(bi)]
+    ends = np.cumsum(bi.contig_len)                               # forward contig ends (exclusive)
+    al = capi.Aligner(0)
+    al.upload_index(bi)
+    got, kinds = [], set()
+    typ = {0: "SUBSTITUTE", 1: "INSERT", 2: "DELETE", 3: "INSERT", 4: "DELETE"}
+    for _, seq in synth.read_fasta(os.path.join(d, "qry.fa")):
+        s = np.ascontiguousarray(seq)
+        blocks, frags, _, _ = al.align_contig(s)
+        rec, first, count = al.variants(len(blocks))
+        assert len(first) == len(blocks)
+        for b, f0, nv in zip(blocks, first, count):
+            if b["bDup"]:
+                continue
+            r0 = int(frags[int(b["frag_beg"])]["rPos"])
+            fwd = r0 if r0 < bi.l_pac else 2 * bi.l_pac - 1 - r0
+            name = bi.names[int(np.searchsorted(ends, fwd, side="right"))]
+            for v in rec[int(f0):int(f0 + nv)]:
+                r, q, L, k = int(v["rPos"]), int(v["qPos"]), int(v["len"]), int(v["kind"])
+                kinds.add(k)
+                ref = bytes(T[r:r + (L + 1 if k in (2, 4) else 1)]) if k != 1 else bytes(s[q:q + 1])
+                alt = bytes(s[q:q + L + 1]) if k in (1, 3) else bytes(T[r:r + 1]) if k == 2 else bytes(s[q:q + 1])
+                got.append(f"{name}\t{int(v['gPos'])}\t.\t{ref.decode()}\t{alt.decode()}\t100\t*\tTYPE={typ[k]}")
+    al.close()
+    assert len(got) > 3000 and {0, 1, 2} <= kinds
+    assert sorted(got) == want
+
+
+def test_variants_on_device_or_host_same_vcf(workdir):
+    """the CLI takes the device's variant records by default; GSA_VARIANTS=host scans the rows on the host instead"""
+    from conftest import build_index
+    from test_gpu_pipeline import make_rearranged
+    d = make_rearranged(workdir)
+    if not os.path.exists(os.path.join(d, "ref.sa")):
+        build_index(os.path.join(d, "ref.fa"), os.path.join(d, "ref"))
+    for flags, tag in (([], "d"), (["-sen"], "s")):
+        run(OURS, d, ["-t", "4", "-i", "ref", "-q", "qry.fa", "-o", "vdev" + tag] + flags)
+        run(OURS, d, ["-t", "4", "-i", "ref", "-q", "qry.fa", "-o", "vhost" + tag] + flags, env={"GSA_VARIANTS": "host"})
+        assert os.path.getsize(os.path.join(d, f"vdev{tag}.vcf")) > 10_000
+        assert filecmp.cmp(os.path.join(d, f"vdev{tag}.vcf"), os.path.join(d, f"vhost{tag}.vcf"), shallow=False)
