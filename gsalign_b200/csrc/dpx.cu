@@ -411,6 +411,12 @@ static int dpx_launch_size(gsa_ctx *ctx, cudaStream_t stream, int size, int max_
 		default: return launch_pack<32, HASN>(ctx, stream, max_m, max_n, prob, nprob, a1, a2, out_len, out_start, frag, fblk, bsum);
 		}
 	}
+	if (size == DPX_CLS_S2 && nprob <= 1024) {
+		// a handful of long, flat problems (up to 1000 x 256 = four strips of ~1000 steps each): one warp per problem would make
+		// them the critical path of the contig, so their strips run as a four-warp pipeline instead
+		const uint32_t slot = dpx_layout(max_m, max_n, false).total;
+		return launch_dpx<4, 1, false, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);
+	}
 	if (size == DPX_CLS_S1 || size == DPX_CLS_S2) {
 		const uint32_t slot = dpx_layout(max_m, max_n, true).total;
 		if (slot <= 3584) return launch_dpx<1, 2, true, HASN>(ctx, stream, slot, prob, nprob, flags, a1, a2, out_len, out_start, frag, fblk, bsum);

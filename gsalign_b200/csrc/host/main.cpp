@@ -115,6 +115,9 @@ int main(int argc, char *argv[])
 	if (!o.out_prefix) o.out_prefix = "output";
 	else if (!check_output_prefix(o.out_prefix)) return 0;
 
+	// every lane drives its own stream plus side streams: ask for the maximum of hardware work queues before CUDA initialises,
+	// so that a launch of one lane does not queue behind another lane's bulk copy
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 	time_t t_start = time(NULL);
 	tick("start");
 	fprintf(stderr, "Step1. Load the two genome sequences...\n");

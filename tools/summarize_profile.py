@@ -42,23 +42,33 @@ for path in sorted(glob.glob("gpurun_out/prof_*.ncu-rep")):
         if w in hdr:
             i = hdr.index(w)
             out.append(f"| {w} | {rows[1][i]} | " + " | ".join(row[i] for row in rows[2:]) + " |")
-# dram bytes per k_seed launch of the C2 capture -> profiles/traffic.json (bench.py reports it as roofline.traffic)
-kp = "gpurun_out/prof_kseed.ncu-rep"
-if os.path.exists(kp):
+# dram bytes per k_seed launch of the full captures -> profiles/traffic.json (bench.py reports it as roofline.traffic)
+tpath = "profiles/traffic.json"
+tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+for wl, kp, bp, how in (("C2", "gpurun_out/prof_kseed.ncu-rep", 25_000_000, "bench.py --workload C2 --lanes 1"),
+                        ("C4", "gpurun_out/prof_kseed_C4.ncu-rep", 125_000_247, "tools/prof_contig.py --workload C4 --contig 0: one 125 Mbp contig against the 6.2 G-symbol index")):
+    if not os.path.exists(kp):
+        continue
     r = subprocess.run(["ncu", "-i", kp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(r.splitlines()))
-    if len(rows) >= 3:
-        hdr, units = rows[0], rows[1]
-        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = []
-        for row in rows[2:]:
-            b = 0.0
-            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                i = hdr.index(m); b += _num(row[i]) * mult[units[i]]
-            tot.append(b)
-        tj = {"C2": {"k_seed_dram_bytes_per_launch": sum(tot) / len(tot), "launches": len(tot),
-                     "source": f"profiles/{tag}_summary.md, prof_kseed.ncu-rep (ncu --set full, bench.py --workload C2 --lanes 1)"}}
-        json.dump(tj, open("profiles/traffic.json", "w"), indent=1)
+    if len(rows) < 3:
+        continue
+    hdr, units = rows[0], rows[1]
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, ms, sect = [], [], []
+    for row in rows[2:]:
+        b = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m); b += _num(row[i]) * mult[units[i]]
+        tot.append(b)
+        i = hdr.index("gpu__time_duration.sum"); ms.append(_num(row[i]) * {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}[units[i]])
+        if "dram__sectors_read.sum" in hdr:
+            sect.append(_num(row[hdr.index("dram__sectors_read.sum")]))
+    per = sum(tot) / len(tot)
+    tj[wl] = {"k_seed_dram_bytes_per_launch": per, "k_seed_dram_bytes_per_query_bp": per / bp, "launches": len(tot),
+              "k_seed_launch_ms_under_ncu": sum(ms) / len(ms), "dram_sectors_read": sum(sect) / len(sect) if sect else None,
+              "source": f"profiles/{tag}_summary.md, {os.path.basename(kp)} (ncu --set full --clock-control none, {how})"}
+json.dump(tj, open(tpath, "w"), indent=1)
 for extra in ("dp_bench.json", "random_access.json"):
     if os.path.exists("gpurun_out/" + extra):
         out.append(f"\n## {extra}\n\n```json\n{open('gpurun_out/' + extra).read().strip()}\n```")
