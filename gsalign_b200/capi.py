@@ -64,7 +64,7 @@ EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "g
            "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes", "gsa_index_selfcheck",
            "gsa_comm_unique_id", "gsa_comm_init_rank", "gsa_comm_init_all", "gsa_comm_destroy", "gsa_outbox_reset", "gsa_outbox_reserve",
            "gsa_outbox_append", "gsa_outbox_bytes", "gsa_gather_records", "gsa_gather_records_all", "gsa_gather_wait", "gsa_inbox_device",
-           "gsa_inbox_host", "gsa_record_next", "gsa_variants"]
+           "gsa_inbox_host", "gsa_record_next", "gsa_variants", "gsa_contig_prefetch"]
 
 
 def load_library() -> C.CDLL:
@@ -81,6 +81,16 @@ def load_library() -> C.CDLL:
 
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def _torch_first():
+    """The library binds NCCL at run time (dlopen of libnccl.so.2).  PyTorch bundles its own, newer libnccl under the same
+    soname: whichever copy a process loads first is the one both get, and torch does not import against an older one.  A
+    Python host that may import torch later therefore imports it before the library opens NCCL."""
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
 
 
 def _as_array(ptr, n, dtype):
@@ -224,6 +234,10 @@ class Aligner:
             return rec, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
         return rec, _as_array(vl.block_first, n_blocks, np.dtype("<i8")).copy(), _as_array(vl.block_count, n_blocks, np.dtype("<i8")).copy()
 
+    def prefetch(self, a: np.ndarray):
+        """starts the upload of the contig the next align_contig*() call on this context will get (gsa_contig_prefetch)"""
+        self._chk(self.lib.gsa_contig_prefetch(self.ctx, a.ctypes.data_as(C.c_char_p), C.c_uint32(a.shape[0])))
+
     def align_contig_raw(self, a: np.ndarray) -> Alignment:
         """No copies of the result (bench path): returns the struct pointing into the library's pinned buffers."""
         al = Alignment()
@@ -242,6 +256,7 @@ class Aligner:
     # ---- multi-GPU record gather (gather.cu) ----------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:
+        _torch_first()
         buf = C.create_string_buffer(128)
         rc = load_library().gsa_comm_unique_id(buf, C.c_int32(128))
         if rc != 0:
@@ -249,6 +264,7 @@ class Aligner:
         return buf.raw
 
     def comm_init_rank(self, uid: bytes, rank: int, n_ranks: int):
+        _torch_first()
         self._chk(self.lib.gsa_comm_init_rank(self.ctx, C.c_char_p(uid), C.c_int32(rank), C.c_int32(n_ranks)))
 
     def outbox_reset(self):

@@ -163,13 +163,15 @@ void gsa_destroy(gsa_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *bufs[] = {&ctx->d_occ, &ctx->d_txt, &ctx->d_sa, &ctx->d_ktab, &ctx->d_kbits, &ctx->d_cend, &ctx->d_seq, &ctx->d_qpk, &ctx->d_qinv,
 	                  &ctx->d_counter, &ctx->d_chain, &ctx->d_sq, &ctx->d_sr, &ctx->d_sl, &ctx->d_cub, &ctx->d_cq, &ctx->d_cr, &ctx->d_cl, &ctx->d_cb,
-	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum, &ctx->d_var};
+	                  &ctx->d_frag, &ctx->d_fblk, &ctx->d_aln1, &ctx->d_aln2, &ctx->d_bsum, &ctx->d_var, &ctx->pf[0].buf, &ctx->pf[1].buf};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	for (DevBuf &b : ctx->d_tmp) if (b.p) cudaFree(b.p);
 	gsa_comm_destroy(ctx);
 	DevBuf *gb[] = {&ctx->d_outbox, &ctx->d_sizes};
 	for (DevBuf *b : gb) if (b->p) cudaFree(b->p);
 	for (DevBuf &b : ctx->d_inbox) if (b.p) cudaFree(b.p);
+	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+	for (auto &p : ctx->pf) if (p.ev) cudaEventDestroy(p.ev);
 	if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);
 	if (ctx->ev_outbox) cudaEventDestroy(ctx->ev_outbox);
 	if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -252,9 +254,48 @@ static int contig_reset(gsa_ctx *ctx, uint32_t len)
 	return GSA_OK;
 }
 
+// Double buffering of the upload: starts the host-to-device copy of a contig the caller will pass to gsa_contig_begin /
+// gsa_align_contig soon, on a copy stream of its own, so that it runs under the kernels of the contig being processed.
+// seq must stay valid and unchanged until that call (pinned memory for a truly asynchronous copy).
+int gsa_contig_prefetch(gsa_ctx *ctx, const char *seq, uint32_t len)
+{
+	if (!ctx || !seq || len == 0) return GSA_ERR_ARG;
+	if (len >= 0x7FFFFF00u) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_contig_prefetch: contig longer than 2^31");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	gsa_ctx::Prefetch *slot = nullptr;
+	for (auto &p : ctx->pf) if (p.src == seq && p.len == len) return GSA_OK;   // already on its way
+	for (auto &p : ctx->pf) if (!p.src && !slot) slot = &p;
+	if (!slot) return gsa_fail(ctx, GSA_ERR_ARG, "gsa_contig_prefetch: two uploads are already pending");
+	if (!slot->ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming));
+	// the slot's buffer last held a contig whose processing has ended (the API is synchronous per context), or an upload
+	// that was never claimed: that one may still be running
+	CUDA_TRY(ctx, cudaEventSynchronize(slot->ev));
+	GSA_TRY(gsa_ensure(ctx, slot->buf, (size_t)len + 64));
+	CUDA_TRY(ctx, cudaMemcpyAsync(slot->buf.p, seq, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+	CUDA_TRY(ctx, cudaEventRecord(slot->ev, ctx->copy_stream));
+	slot->src = seq; slot->len = len;
+	return GSA_OK;
+}
+
 int gsa_contig_begin(gsa_ctx *ctx, const char *seq, uint32_t len)
 {
 	if (!ctx || (!seq && len)) return GSA_ERR_ARG;
+	for (auto &p : ctx->pf) {
+		if (!p.src || p.src != seq || p.len != len) continue;
+		// the upload is already under way: its buffer becomes the contig buffer, the old contig buffer becomes the slot's
+		CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+		p.src = nullptr;
+		std::swap(ctx->d_seq, p.buf);
+		GSA_TRY(contig_reset(ctx, len));
+		ctx->h_seq = seq;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, p.ev, 0));
+		GSA_TRY(gsa_impl_pack_query(ctx));
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+		ctx->have_contig = true;
+		return GSA_OK;
+	}
 	GSA_TRY(contig_reset(ctx, len));
 	ctx->h_seq = seq;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));

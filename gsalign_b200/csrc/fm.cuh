@@ -120,6 +120,12 @@ template <typename T>
 __device__ __forceinline__ T gsa_peer_sum(unsigned peers, T v, bool &leader)
 {
 	const int lane = threadIdx.x & 31;
+	if (peers == 0xffffffffu) { // the usual case (one block, one window, one bin per warp): a plain butterfly
+		leader = lane == 0;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		return v;
+	}
 	const unsigned rank = __popc(peers & ((1u << lane) - 1));
 	leader = rank == 0;
 #pragma unroll

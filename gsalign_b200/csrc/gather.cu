@@ -13,6 +13,7 @@
 //     gsa_block[n_blocks]  gsa_frag[n_frags]  aln1[aln_bytes]  aln2[aln_bytes]
 #include "gsa_internal.cuh"
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
@@ -155,41 +156,44 @@ int gsa_outbox_append(gsa_ctx *owner, gsa_ctx *lane, int64_t contig)
 	CUDA_TRY(lane, cudaSetDevice(lane->device));
 	const int64_t nb = (int64_t)lane->out_blocks.size(), nf = nb ? lane->n_frags : 0, ab = nb ? lane->aln_bytes : 0;
 	const int64_t need = REC_HDR + pad16(nb * (int64_t)sizeof(gsa_block)) + pad16(nf * (int64_t)sizeof(gsa_frag)) + 2 * pad16(ab);
-	int64_t off;
-	{
-		std::lock_guard<std::mutex> lk(owner->outbox_mu);
-		if ((size_t)(owner->outbox_used + need) > owner->d_outbox.cap) {
-			// grow: wait for the copies in flight, move the image (rare: capacities are remembered across steps)
-			for (cudaEvent_t e : owner->outbox_pending) CUDA_TRY(owner, cudaEventSynchronize(e));
-			DevBuf bigger;
-			GSA_TRY(gsa_ensure(owner, bigger, (size_t)(2 * (owner->outbox_used + need)) + (64u << 20)));
-			if (owner->outbox_used) CUDA_TRY(owner, cudaMemcpy(bigger.p, owner->d_outbox.p, (size_t)owner->outbox_used, cudaMemcpyDeviceToDevice));
-			if (owner->d_outbox.p) CUDA_TRY(owner, cudaFree(owner->d_outbox.p));
-			owner->d_outbox = bigger;
-		}
-		off = owner->outbox_used;
-		owner->outbox_used += need;
-		if (!lane->ev_outbox) CUDA_TRY(lane, cudaEventCreateWithFlags(&lane->ev_outbox, cudaEventDisableTiming));
-		bool known = false;
-		for (cudaEvent_t e : owner->outbox_pending) known |= e == lane->ev_outbox;
-		if (!known) owner->outbox_pending.push_back(lane->ev_outbox);
-	}
-	char *dst = (char *)owner->d_outbox.p + off;
-	if (owner->ev_gather) CUDA_TRY(lane, cudaStreamWaitEvent(lane->stream, owner->ev_gather, 0)); // the previous gather has left the outbox
 	// header + block headers travel in one small pinned staging block of the lane
 	const size_t hb = (size_t)(REC_HDR + nb * (int64_t)sizeof(gsa_block));
 	GSA_TRY(gsa_ensure_host(lane, lane->h_rec, hb));
 	int64_t *hdr = (int64_t *)lane->h_rec.p;
 	hdr[0] = contig; hdr[1] = nb; hdr[2] = nf; hdr[3] = ab;
 	if (nb) memcpy((char *)lane->h_rec.p + REC_HDR, lane->out_blocks.data(), (size_t)nb * sizeof(gsa_block));
-	CUDA_TRY(lane, cudaMemcpyAsync(dst, lane->h_rec.p, hb, cudaMemcpyHostToDevice, lane->stream));
-	char *p = dst + REC_HDR + pad16(nb * (int64_t)sizeof(gsa_block));
-	if (nf) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_frag.p, (size_t)nf * sizeof(gsa_frag), cudaMemcpyDeviceToDevice, lane->stream));
-	p += pad16(nf * (int64_t)sizeof(gsa_frag));
-	if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln1.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
-	p += pad16(ab);
-	if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln2.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
-	CUDA_TRY(lane, cudaEventRecord(lane->ev_outbox, lane->stream));
+	{
+		// Reserving the range and queueing the copies into it happen under the outbox lock: a lane that has to grow the outbox
+		// moves the image after waiting for every lane's last RECORDED append, so no append may sit between its reservation
+		// and its event (its copies would land in the buffer that is being freed).
+		std::lock_guard<std::mutex> lk(owner->outbox_mu);
+		if ((size_t)(owner->outbox_used + need) > owner->d_outbox.cap) {
+			// grow: wait for the copies in flight, move the image (rare: capacities are remembered across steps)
+			for (cudaEvent_t e : owner->outbox_pending) CUDA_TRY(owner, cudaEventSynchronize(e));
+			DevBuf bigger;
+			static const size_t slack = getenv("GSA_OUTBOX_SLACK") ? (size_t)atoll(getenv("GSA_OUTBOX_SLACK")) : ((size_t)64 << 20); // tests shrink it to grow often
+			GSA_TRY(gsa_ensure(owner, bigger, (size_t)(2 * (owner->outbox_used + need)) + slack));
+			if (owner->outbox_used) CUDA_TRY(owner, cudaMemcpy(bigger.p, owner->d_outbox.p, (size_t)owner->outbox_used, cudaMemcpyDeviceToDevice));
+			if (owner->d_outbox.p) CUDA_TRY(owner, cudaFree(owner->d_outbox.p));
+			owner->d_outbox = bigger;
+		}
+		const int64_t off = owner->outbox_used;
+		owner->outbox_used += need;
+		if (!lane->ev_outbox) CUDA_TRY(lane, cudaEventCreateWithFlags(&lane->ev_outbox, cudaEventDisableTiming));
+		bool known = false;
+		for (cudaEvent_t e : owner->outbox_pending) known |= e == lane->ev_outbox;
+		if (!known) owner->outbox_pending.push_back(lane->ev_outbox);
+		char *dst = (char *)owner->d_outbox.p + off;
+		if (owner->ev_gather) CUDA_TRY(lane, cudaStreamWaitEvent(lane->stream, owner->ev_gather, 0)); // the previous gather has left the outbox
+		CUDA_TRY(lane, cudaMemcpyAsync(dst, lane->h_rec.p, hb, cudaMemcpyHostToDevice, lane->stream));
+		char *p = dst + REC_HDR + pad16(nb * (int64_t)sizeof(gsa_block));
+		if (nf) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_frag.p, (size_t)nf * sizeof(gsa_frag), cudaMemcpyDeviceToDevice, lane->stream));
+		p += pad16(nf * (int64_t)sizeof(gsa_frag));
+		if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln1.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
+		p += pad16(ab);
+		if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln2.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
+		CUDA_TRY(lane, cudaEventRecord(lane->ev_outbox, lane->stream));
+	}
 	// the staging block is reused by the next append of this lane: the H2D above must have left it
 	CUDA_TRY(lane, cudaEventSynchronize(lane->ev_outbox));
 	return GSA_OK;

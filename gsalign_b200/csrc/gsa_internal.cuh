@@ -103,6 +103,11 @@ struct gsa_ctx {
 	uint32_t qlen = 0;
 	bool have_contig = false, have_seeds = false, have_cluster = false;
 	DevBuf d_seq, d_qpk, d_qinv;   // raw chars, 2-bit packed, invalid-base bitmap
+	// gsa_contig_prefetch: contigs on their way into spare buffers while the current one is processed.  Two slots: a caller
+	// that announces contig C before it starts on contig B (itself announced earlier) has two uploads pending for a moment.
+	struct Prefetch { DevBuf buf; const char *src = nullptr; uint32_t len = 0; cudaEvent_t ev = nullptr; };
+	Prefetch pf[2];
+	cudaStream_t copy_stream = nullptr;
 	const char *h_seq = nullptr;   // borrowed host pointer (may be null for device-resident contigs)
 
 	// K1 output / K2 working set

@@ -195,6 +195,10 @@ int main(int argc, char *argv[])
 	if (nccl_gather) {
 		if (gsa_comm_init_all(owners.data(), ngpu) != 0) { fprintf(stderr, "FatalError: %s\n", gsa_last_error(owners[0])); return 1; }
 		for (int g = 0; g < ngpu; g++) for (gsa_ctx *c : ctx[g]) gsa_set_host_results(c, 0);
+		// a first guess at every outbox (about one record byte per query base for closely related genomes); it grows on demand
+		// (GSA_OUTBOX_RESERVE=0 starts from nothing: the growth path, for tests)
+		const char *rs = getenv("GSA_OUTBOX_RESERVE");
+		if (!(rs && strcmp(rs, "0") == 0)) for (int g = 0; g < ngpu; g++) gsa_outbox_reserve(owners[g], (int64_t)load[g] + ((int64_t)64 << 20));
 	}
 	// GSA_VARIANTS=host: VariantIdentification scans the rows on the host instead of taking the device's records (gsa_variants)
 	const char *vmode = getenv("GSA_VARIANTS");

@@ -134,6 +134,11 @@ void gsa_default_params(gsa_params *prm);
 /* --- per query contig (the body of the loop at src/GSAlign.cpp:483-548) ----------------------- */
 /* seq: the contig exactly as LoadQueryFile() stores it (any case, IUPAC allowed), host memory. */
 int gsa_contig_begin(gsa_ctx *ctx, const char *seq, uint32_t len);
+/* Double buffering: starts the upload of the contig that will be passed to the NEXT gsa_contig_begin / gsa_align_contig on
+ * this context, on a copy stream of its own, so that it runs under the kernels of the contig being processed (the
+ * reference's loop has nothing to overlap: its contigs are already in host memory).  seq must stay valid and unchanged
+ * until that next call picks the buffer up (same pointer and length); pinned memory makes the copy asynchronous. */
+int gsa_contig_prefetch(gsa_ctx *ctx, const char *seq, uint32_t len);
 /* same, but seq is a DEVICE pointer (inputs already resident in HBM) */
 int gsa_contig_begin_device(gsa_ctx *ctx, const void *dev_seq, uint32_t len);
 

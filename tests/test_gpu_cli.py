@@ -237,3 +237,24 @@ def test_variants_on_device_or_host_same_vcf(workdir):
         run(OURS, d, ["-t", "4", "-i", "ref", "-q", "qry.fa", "-o", "vhost" + tag] + flags, env={"GSA_VARIANTS": "host"})
         assert os.path.getsize(os.path.join(d, f"vdev{tag}.vcf")) > 10_000
         assert filecmp.cmp(os.path.join(d, f"vdev{tag}.vcf"), os.path.join(d, f"vhost{tag}.vcf"), shallow=False)
+
+
+def test_multi_gpu_many_contigs_same_bytes(workdir):
+    """-gpus 2 with several contigs in flight per GPU: every lane appends to its GPU's outbox (which has to grow under them)
+    and the NCCL record gather brings GPU 1's image to GPU 0.  Needs 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from gsalign_b200 import synth
+    d = os.path.join(workdir, "mg")
+    os.makedirs(d, exist_ok=True)
+    if not os.path.exists(os.path.join(d, "ref.sa")):
+        ref, qry = synth.make_pair(12_000_000, 16, 0.01, 0.001, 21)
+        synth.write_fasta(os.path.join(d, "ref.fa"), ref)
+        synth.write_fasta(os.path.join(d, "qry.fa"), qry)
+        run(OUR_INDEX, d, ["ref.fa", "ref"])
+    run(OURS, d, ["-t", "8", "-i", "ref", "-q", "qry.fa", "-o", "one"])
+    for rep in range(3):   # the appends race differently every time
+        run(OURS, d, ["-t", "8", "-i", "ref", "-q", "qry.fa", "-o", "two", "-gpus", "2", "-lanes", "4"], env={"GSA_OUTBOX_RESERVE": "0", "GSA_OUTBOX_SLACK": "4096"} if rep else None)
+        for ext in ("maf", "vcf"):
+            assert filecmp.cmp(os.path.join(d, f"one.{ext}"), os.path.join(d, f"two.{ext}"), shallow=False), (rep, ext)

@@ -112,3 +112,32 @@ def test_degenerate_contigs(workdir, seq, oracle):
     want = oracle.cluster(ix, orc.params(), seq, oq, orr, ol, 2) if len(oq) else []
     assert len(blocks) == len(want)
     al.close()
+
+
+def test_prefetched_upload_same_results(workdir):
+    """gsa_contig_prefetch: a contig whose upload was started ahead (two may be pending) gives the records of the plain call;
+    an announced contig that is not the next one simply waits for its turn; a third pending upload is refused."""
+    import torch
+    from gsalign_b200 import capi
+    bi, qry = _make(workdir)
+    al = capi.Aligner(0)
+    al.upload_index(bi)
+    seqs = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory().numpy() for _, s in qry]
+    want = [_result(al, s) for s in seqs]
+    for rep in range(2):
+        # the bench's pattern: announce the next contig, then work on the current one
+        al.prefetch(seqs[0])
+        got = []
+        for k in range(len(seqs)):
+            if k + 1 < len(seqs):
+                al.prefetch(seqs[k + 1])
+            got.append(_result(al, seqs[k]))
+        assert got == want
+    # out of order: 2 is announced, 0 and 1 run first without an announcement of their own
+    al.prefetch(seqs[2])
+    assert _result(al, seqs[0]) == want[0]
+    al.prefetch(seqs[1])
+    with pytest.raises(capi.GsaError):
+        al.prefetch(seqs[0])                       # two uploads are pending already
+    assert _result(al, seqs[1]) == want[1] and _result(al, seqs[2]) == want[2]
+    al.close()
