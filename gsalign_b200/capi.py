@@ -64,7 +64,7 @@ EXPORTS = ["gsa_create", "gsa_destroy", "gsa_last_error", "gsa_index_upload", "g
            "gsa_set_wide_index", "gsa_index_clone", "gsa_index_bytes", "gsa_index_selfcheck",
            "gsa_comm_unique_id", "gsa_comm_init_rank", "gsa_comm_init_all", "gsa_comm_destroy", "gsa_outbox_reset", "gsa_outbox_reserve",
            "gsa_outbox_append", "gsa_outbox_bytes", "gsa_gather_records", "gsa_gather_records_all", "gsa_gather_wait", "gsa_inbox_device",
-           "gsa_inbox_host", "gsa_record_next", "gsa_variants", "gsa_contig_prefetch"]
+           "gsa_inbox_host", "gsa_record_next", "gsa_record_frags", "gsa_variants", "gsa_contig_prefetch", "gsa_split_hazard"]
 
 
 def load_library() -> C.CDLL:
@@ -98,6 +98,27 @@ def _as_array(ptr, n, dtype):
         return np.empty(0, dtype=dtype)
     buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
     return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+def walk_image(lib, ptr, nbytes: int):
+    """the records of an outbox image in host memory as (contig, blocks, frags, aln1, aln2) numpy copies; fragment lists that
+    travelled in the compact form are expanded by gsa_record_frags"""
+    out, off, contig, al = [], C.c_int64(0), C.c_int64(), Alignment()
+    while True:
+        start = off.value
+        rc = lib.gsa_record_next(ptr, C.c_int64(nbytes), C.byref(off), C.byref(contig), C.byref(al))
+        if rc < 0:
+            raise GsaError("malformed outbox image")
+        if rc == 0:
+            break
+        blocks = _as_array(al.blocks, al.n_blocks, BLOCK_DTYPE).copy()
+        frags = np.zeros(al.n_frags, dtype=FRAG_DTYPE)
+        if al.n_frags and lib.gsa_record_frags(ptr, C.c_int64(nbytes), C.c_int64(start), frags.ctypes.data_as(C.c_void_p), C.c_int32(4)) != 0:
+            raise GsaError("malformed outbox image (fragment list)")
+        a1 = _as_array(al.aln1, al.aln_bytes, np.dtype(np.uint8)).copy()
+        a2 = _as_array(al.aln2, al.aln_bytes, np.dtype(np.uint8)).copy()
+        out.append((contig.value, blocks, frags, a1, a2))
+    return out
 
 
 class Aligner:
@@ -234,6 +255,10 @@ class Aligner:
             return rec, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
         return rec, _as_array(vl.block_first, n_blocks, np.dtype("<i8")).copy(), _as_array(vl.block_count, n_blocks, np.dtype("<i8")).copy()
 
+    def split_hazard(self) -> int:
+        """hazard H14: split phases of the last cluster() whose pushes crossed a power of two (reference behaviour undefined there)"""
+        return int(self.lib.gsa_split_hazard(self.ctx))
+
     def prefetch(self, a: np.ndarray):
         """starts the upload of the contig the next align_contig*() call on this context will get (gsa_contig_prefetch)"""
         self._chk(self.lib.gsa_contig_prefetch(self.ctx, a.ctypes.data_as(C.c_char_p), C.c_uint32(a.shape[0])))
@@ -289,15 +314,7 @@ class Aligner:
         (contig, blocks, frags, aln1, aln2) numpy copies"""
         ptr, nbytes = C.c_void_p(), C.c_int64()
         self._chk(self.lib.gsa_inbox_host(self.ctx, C.c_int32(rank), C.byref(ptr), C.byref(nbytes)))
-        out, off, contig, al = [], C.c_int64(0), C.c_int64(), Alignment()
-        while True:
-            rc = self.lib.gsa_record_next(ptr, nbytes, C.byref(off), C.byref(contig), C.byref(al))
-            if rc < 0:
-                raise GsaError("malformed outbox image")
-            if rc == 0:
-                break
-            out.append((contig.value,) + self._alignment(al))
-        return out
+        return walk_image(self.lib, ptr, nbytes.value)
 
     def timing(self) -> Timing:
         t = Timing()

@@ -42,7 +42,20 @@ static BlockHdr from_piece(const Piece &p, int32_t score)
 	return b;
 }
 
-static void split_phase(const gsa_ctx *ctx, std::vector<BlockHdr> &vec, const std::vector<Piece> &pieces)
+// Hazard H14: the reference splits a block through a reference into AlnBlockVec that it keeps across
+// AlnBlockVec.push_back (src/ProcessCandidateAlignment.cpp:102-116,142-154).  When a push crosses the vector's capacity
+// (libstdc++ doubles it) that reference dangles and what the reference then computes is undefined; parity is only defined
+// where that does not happen.  The block count straddling a power of two during a split phase is the observable trigger:
+// such contigs are counted so that a harness can flag a difference there instead of calling it a failure.
+static bool crosses_power_of_two(size_t before, size_t after)
+{
+	if (after <= before) return false;
+	size_t p = 1;
+	while (p < before) p <<= 1;      // the smallest capacity that held `before` elements
+	return before == 0 || after > p;
+}
+
+static void split_phase(gsa_ctx *ctx, std::vector<BlockHdr> &vec, const std::vector<Piece> &pieces)
 {
 	size_t n0 = vec.size();
 	for (size_t i = 0; i < n0; i++) {
@@ -61,10 +74,11 @@ static void split_phase(const gsa_ctx *ctx, std::vector<BlockHdr> &vec, const st
 			if (sc > ctx->prm.min_block_score) vec.push_back(from_piece(p, sc));
 		}
 	}
+	if (crosses_power_of_two(n0, vec.size())) ctx->split_hazard++;
 	gsa_host_remove_bad(vec);
 }
 
-void gsa_host_split(const gsa_ctx *ctx, std::vector<BlockHdr> &vec, const std::vector<Piece> &p1, const std::vector<Piece> &p2)
+void gsa_host_split(gsa_ctx *ctx, std::vector<BlockHdr> &vec, const std::vector<Piece> &p1, const std::vector<Piece> &p2)
 {
 	split_phase(ctx, vec, p1); // CheckAlnBlockLargeGaps + RemoveBadAlnBlocks, src/GSAlign.cpp:504-505
 	split_phase(ctx, vec, p2); // CheckAlnBlockSpanMultiSeqs + RemoveBadAlnBlocks, src/GSAlign.cpp:507-508

@@ -48,12 +48,25 @@ __global__ void k_copy_words(uint32_t *dst, const uint32_t *src, size_t n)
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// Bulk transfers between pinned host memory and HBM.  GSA_COPY_CHUNK_MB=<n> queues them in pieces of n MB instead of one
+// operation -- an experiment knob: measured at C4 (profiles/r2_summary.md, call N) pieces of 1-4 MB make the end-to-end step
+// 6-15 % slower, so the default is one operation per transfer.
+int gsa_bulk_copy(gsa_ctx *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+	static const size_t piece = [] { const char *e = getenv("GSA_COPY_CHUNK_MB"); long v = e ? atol(e) : 0; return v <= 0 ? (size_t)0 : (size_t)v << 20; }();
+	if (piece == 0 || bytes <= piece) { CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, kind, stream)); return GSA_OK; }
+	for (size_t o = 0; o < bytes; o += piece)
+		CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + o, (const char *)src + o, std::min(piece, bytes - o), kind, stream));
+	return GSA_OK;
+}
+
 static int small_copy(gsa_ctx *ctx, void *dst, const void *src, size_t bytes, bool to_host)
 {
 	if (bytes == 0) return GSA_OK;
+	static const bool use_dma = [] { const char *e = getenv("GSA_SMALL_COPY"); return e && strcmp(e, "dma") == 0; }();
 	void *mapped = nullptr;
 	void *host = to_host ? dst : const_cast<void *>(src);
-	if (bytes <= GSA_SMALL_BYTES && (bytes & 3) == 0 && (((uintptr_t)dst | (uintptr_t)src) & 3) == 0 && cudaHostGetDevicePointer(&mapped, host, 0) == cudaSuccess && mapped) {
+	if (!use_dma && bytes <= GSA_SMALL_BYTES && (bytes & 3) == 0 && (((uintptr_t)dst | (uintptr_t)src) & 3) == 0 && cudaHostGetDevicePointer(&mapped, host, 0) == cudaSuccess && mapped) {
 		const size_t n = bytes >> 2;
 		const unsigned grid = (unsigned)std::min<size_t>(64, (n + 255) / 256);
 		if (to_host) k_copy_words<<<grid, 256, 0, ctx->stream>>>((uint32_t *)mapped, (const uint32_t *)src, n);
@@ -76,7 +89,8 @@ __global__ void k_copy_counted(uint32_t *dst, const uint32_t *src, const int32_t
 int gsa_small_d2h_counted(gsa_ctx *ctx, void *host_pinned, const void *dev, size_t elem_bytes, const int32_t *d_count, int cap)
 {
 	void *mapped = nullptr;
-	if ((elem_bytes & 3) == 0 && cudaHostGetDevicePointer(&mapped, host_pinned, 0) == cudaSuccess && mapped) {
+	static const bool use_dma = [] { const char *e = getenv("GSA_SMALL_COPY"); return e && strcmp(e, "dma") == 0; }();
+	if (!use_dma && (elem_bytes & 3) == 0 && cudaHostGetDevicePointer(&mapped, host_pinned, 0) == cudaSuccess && mapped) {
 		k_copy_counted<<<16, 256, 0, ctx->stream>>>((uint32_t *)mapped, (const uint32_t *)dev, d_count, (int)(elem_bytes >> 2), cap);
 		KERNEL_CHECK(ctx);
 		return GSA_OK;
@@ -167,7 +181,7 @@ void gsa_destroy(gsa_ctx *ctx)
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	for (DevBuf &b : ctx->d_tmp) if (b.p) cudaFree(b.p);
 	gsa_comm_destroy(ctx);
-	DevBuf *gb[] = {&ctx->d_outbox, &ctx->d_sizes};
+	DevBuf *gb[] = {&ctx->d_outbox, &ctx->d_sizes, &ctx->d_cfrag, &ctx->d_anchor, &ctx->d_packst};
 	for (DevBuf *b : gb) if (b->p) cudaFree(b->p);
 	for (DevBuf &b : ctx->d_inbox) if (b.p) cudaFree(b.p);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -248,7 +262,7 @@ static int contig_reset(gsa_ctx *ctx, uint32_t len)
 	if (len >= 0x7FFFFF00u) return gsa_fail(ctx, GSA_ERR_LIMIT, "gsa_contig_begin: contig longer than 2^31 (positions are int in the reference)");
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	ctx->qlen = len; ctx->have_contig = false; ctx->have_seeds = false; ctx->have_cluster = false;
-	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->aln_bytes = 0; ctx->dp_timed = false; ctx->have_fill = false;
+	ctx->n_seeds = 0; ctx->n_cseeds = 0; ctx->n_frags = 0; ctx->aln_bytes = 0; ctx->dp_timed = false; ctx->have_fill = false; ctx->split_hazard = 0;
 	memset(&ctx->tm, 0, sizeof(ctx->tm));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_seq, (size_t)len + 64));
 	return GSA_OK;
@@ -272,7 +286,7 @@ int gsa_contig_prefetch(gsa_ctx *ctx, const char *seq, uint32_t len)
 	// that was never claimed: that one may still be running
 	CUDA_TRY(ctx, cudaEventSynchronize(slot->ev));
 	GSA_TRY(gsa_ensure(ctx, slot->buf, (size_t)len + 64));
-	CUDA_TRY(ctx, cudaMemcpyAsync(slot->buf.p, seq, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+	GSA_TRY(gsa_bulk_copy(ctx, slot->buf.p, seq, len, cudaMemcpyHostToDevice, ctx->copy_stream));
 	CUDA_TRY(ctx, cudaEventRecord(slot->ev, ctx->copy_stream));
 	slot->src = seq; slot->len = len;
 	return GSA_OK;
@@ -299,7 +313,7 @@ int gsa_contig_begin(gsa_ctx *ctx, const char *seq, uint32_t len)
 	GSA_TRY(contig_reset(ctx, len));
 	ctx->h_seq = seq;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_seq.p, seq, len, cudaMemcpyHostToDevice, ctx->stream));
+	GSA_TRY(gsa_bulk_copy(ctx, ctx->d_seq.p, seq, len, cudaMemcpyHostToDevice, ctx->stream));
 	GSA_TRY(gsa_impl_pack_query(ctx));
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 	ctx->have_contig = true;
@@ -386,6 +400,8 @@ int gsa_variants(gsa_ctx *ctx, gsa_variant_list *out)
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	return gsa_impl_variants(ctx, out);
 }
+
+int gsa_split_hazard(const gsa_ctx *ctx) { return ctx ? ctx->split_hazard : 0; }
 
 int gsa_set_host_results(gsa_ctx *ctx, int enable)
 {

@@ -31,6 +31,7 @@ static int dpx_use_pack()
 }
 
 // fragment type codes
+// (values are part of the record format: gsa_frag::reserved, gather.cu)
 enum { FT_SEED = 0, FT_DEL = 1, FT_INS = 2, FT_COPY = 3, FT_DP = 4 };
 
 // ---- classification ----------------------------------------------------------------------------------
@@ -66,6 +67,7 @@ __global__ void k_frag_classify(gsa_frag *frag, int64_t nfr, const unsigned char
 		}
 	}
 	type[t] = ty; mism[t] = mm; row_len[t] = rl; flag_len[t] = fl; is_dp[t] = ty == FT_DP; dp_cls[t] = cls;
+	if (ty != FT_SEED) frag[t].reserved = ty;   // gsa_frag::reserved: how the fragment's rows are produced (its row slot follows from it)
 }
 
 // rows of the non-DP fragment types + per-block sums (src/ProcessCandidateAlignment.cpp:303-331)
@@ -287,10 +289,10 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 		GSA_TRY(gsa_ensure_host(ctx, ctx->h_frag, (size_t)nfr * sizeof(gsa_frag)));
 		GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln1, (size_t)row_bytes + 16));
 		GSA_TRY(gsa_ensure_host(ctx, ctx->h_aln2, (size_t)row_bytes + 16));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_frag.p, frag, (size_t)nfr * sizeof(gsa_frag), cudaMemcpyDeviceToHost, ctx->stream));
+		GSA_TRY(gsa_bulk_copy(ctx, ctx->h_frag.p, frag, (size_t)nfr * sizeof(gsa_frag), cudaMemcpyDeviceToHost, ctx->stream));
 		if (row_bytes) {
-			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln1.p, a1, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_aln2.p, a2, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+			GSA_TRY(gsa_bulk_copy(ctx, ctx->h_aln1.p, a1, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+			GSA_TRY(gsa_bulk_copy(ctx, ctx->h_aln2.p, a2, (size_t)row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
 		}
 	}
 	GSA_TRY(gsa_small_d2h(ctx, ctx->h_blocks.p, bsum, (size_t)nblk * 8));

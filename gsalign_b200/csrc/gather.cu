@@ -12,7 +12,11 @@
 //     int64[4]   {contig index, n_blocks, n_frags, aln_bytes}
 //     gsa_block[n_blocks]  gsa_frag[n_frags]  aln1[aln_bytes]  aln2[aln_bytes]
 #include "gsa_internal.cuh"
+#include "scan.cuh"
 #include <dlfcn.h>
+#include <thread>
+#include <algorithm>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
@@ -63,6 +67,87 @@ static NcclApi *nccl_api()
 
 static inline int64_t pad16(int64_t n) { return (n + 15) & ~(int64_t)15; }
 static const int64_t REC_HDR = 32;
+
+// ---- the compact form of a record -------------------------------------------------------------------------------------------
+// A fragment record is 40 bytes, and a 3 Gbp pair has 54 M of them: they are 85 % of what the gather moves.  Almost all of a
+// record is redundant: inside a block every fragment starts where the previous one ends (both coordinates), a seed's other
+// fields repeat its length, and a gap fragment's row offset is the running sum of the row slots before it (fill.cu lays the
+// rows out by a prefix sum over the fragments; a gapped alignment sits right-aligned in a slot of qLen + rLen).  So a record
+// travels as 8 bytes per fragment -- the three lengths and two flags -- plus an ANCHOR {fragment index, rPos, qPos, row base}
+// wherever the chain of positions restarts (block starts, anything unexpected) and every 256 fragments, so that the host can
+// expand any stretch on its own.  The pack kernel checks every rule it relies on against the real record; a record that breaks
+// one (or needs more anchors than were provided for) travels in the plain form.
+#define PK_STRIDE 256
+#define PK_LEN_BITS 21
+#define PK_ALN_BITS 20
+struct GsaAnchor { int64_t first; int64_t rPos; int32_t qPos; int32_t pad; int64_t row_base; };
+static_assert(sizeof(GsaAnchor) == 32, "anchor layout is part of the image format");
+enum { PK_FT_DEL = 1, PK_FT_INS = 2, PK_FT_COPY = 3, PK_FT_DP = 4 };   // gsa_frag::reserved (fill.cu)
+
+__host__ __device__ inline int64_t pk_row_slot(int32_t qLen, int32_t rLen, bool seed, bool gapped)
+{
+	return seed ? 0 : gapped ? (int64_t)qLen + rLen : qLen == 0 ? rLen : qLen;
+}
+
+struct FPack {
+	const gsa_frag *frag; uint64_t *cfrag; GsaAnchor *anchor; int32_t *st; int anchor_cap;   // st: {n_anchors, broken rule, n_frags}
+	struct Item { gsa_frag f; uint8_t flag; };
+	__device__ Item load(int64_t i) const
+	{
+		Item it; it.f = frag[i];
+		bool restart = true;
+		if (i > 0) { const gsa_frag p = frag[i - 1]; restart = it.f.qPos != p.qPos + p.qLen || it.f.rPos != p.rPos + p.rLen; }
+		it.flag = restart || (i % PK_STRIDE) == 0;
+		return it;
+	}
+	__device__ unsigned long long value(const Item &it) const
+	{
+		return CH_PACK2(it.flag, pk_row_slot(it.f.qLen, it.f.rLen, it.f.bSeed != 0, it.f.reserved == PK_FT_DP));
+	}
+	__device__ void emit(int64_t i, unsigned long long excl, const Item &it, bool valid) const
+	{
+		if (!valid) return;
+		const gsa_frag &f = it.f;
+		const bool seed = f.bSeed != 0, gapped = f.reserved == PK_FT_DP;
+		const int64_t row_base = CH_HI(excl), slot = pk_row_slot(f.qLen, f.rLen, seed, gapped);
+		bool ok = f.qLen >= 0 && f.rLen >= 0 && f.aln_len >= 0 && f.qLen < (1 << PK_LEN_BITS) && f.rLen < (1 << PK_LEN_BITS) && f.aln_len < (1 << PK_ALN_BITS) &&
+		          (f.bSeed == 0 || f.bSeed == 1) && row_base + slot < 0x7FFFFFFFll;
+		if (seed) ok = ok && f.rLen == f.qLen && f.aln_len == f.qLen && f.aln_off == 0 && f.reserved == 0;
+		else {
+			const int expect = f.qLen == 0 ? PK_FT_DEL : f.rLen == 0 ? PK_FT_INS : gapped ? PK_FT_DP : PK_FT_COPY;
+			ok = ok && f.reserved == expect && f.aln_len <= slot && f.aln_off == row_base + (gapped ? slot - f.aln_len : 0);
+		}
+		if (!ok) atomicOr(st + 1, 1);
+		cfrag[i] = (uint64_t)(uint32_t)f.qLen | ((uint64_t)(uint32_t)f.rLen << PK_LEN_BITS) | ((uint64_t)(uint32_t)f.aln_len << (2 * PK_LEN_BITS)) |
+		           ((uint64_t)seed << 62) | ((uint64_t)gapped << 63);
+		if (it.flag) {
+			const int64_t a = CH_LO(excl);
+			if (a < anchor_cap) { GsaAnchor x; x.first = i; x.rPos = f.rPos; x.qPos = f.qPos; x.pad = 0; x.row_base = row_base; anchor[a] = x; }
+		}
+	}
+	__device__ void finish(unsigned long long total) const { st[0] = (int32_t)CH_LO(total); }
+};
+
+__global__ void k_pack_init(int32_t *st, int32_t n) { if (threadIdx.x == 0) { st[0] = 0; st[1] = 0; st[2] = n; st[3] = 0; } }
+
+// expands fragments [a.first, end) of a compact record from their anchor (host)
+static void pk_expand(const uint64_t *cfrag, const GsaAnchor &a, int64_t end, gsa_frag *dst)
+{
+	int64_t r = a.rPos, row = a.row_base; int32_t q = a.qPos;
+	for (int64_t i = a.first; i < end; i++) {
+		const uint64_t c = cfrag[i];
+		const int32_t qLen = (int32_t)(c & ((1u << PK_LEN_BITS) - 1)), rLen = (int32_t)((c >> PK_LEN_BITS) & ((1u << PK_LEN_BITS) - 1));
+		const int32_t alen = (int32_t)((c >> (2 * PK_LEN_BITS)) & ((1u << PK_ALN_BITS) - 1));
+		const bool seed = (c >> 62) & 1, gapped = (c >> 63) & 1;
+		const int64_t slot = pk_row_slot(qLen, rLen, seed, gapped);
+		gsa_frag f;
+		f.rPos = r; f.qPos = q; f.qLen = qLen; f.rLen = rLen; f.bSeed = seed ? 1 : 0; f.aln_len = alen;
+		f.aln_off = seed ? 0 : row + (gapped ? slot - alen : 0);
+		f.reserved = seed ? 0 : qLen == 0 ? PK_FT_DEL : rLen == 0 ? PK_FT_INS : gapped ? PK_FT_DP : PK_FT_COPY;
+		dst[i] = f;
+		r += rLen; q += qLen; row += slot;
+	}
+}
 
 static int comm_common_init(gsa_ctx *ctx)
 {
@@ -147,21 +232,51 @@ int gsa_outbox_reserve(gsa_ctx *owner, int64_t bytes)
 }
 
 // Packs the result of the last gsa_fill() of `lane` (a context on the owner's GPU, possibly the owner itself) into the
-// owner's outbox, asynchronously on the lane's stream: fragments and rows are copied device to device, the O(#blocks)
-// headers come from the host.
+// owner's outbox, asynchronously on the lane's stream: the fragment list goes through the pack kernel (compact form) or is
+// copied as it is (plain form: GSA_GATHER_RAW=1, or a record the compact form cannot carry), rows are copied device to
+// device, the O(#blocks) headers come from the host.
 int gsa_outbox_append(gsa_ctx *owner, gsa_ctx *lane, int64_t contig)
 {
 	if (!owner || !lane || owner->device != lane->device) return GSA_ERR_ARG;
 	if (!lane->have_cluster) return gsa_fail(lane, GSA_ERR_ARG, "gsa_outbox_append: call gsa_fill first");
+	if (contig < 0) return gsa_fail(lane, GSA_ERR_ARG, "gsa_outbox_append: negative contig index");
 	CUDA_TRY(lane, cudaSetDevice(lane->device));
 	const int64_t nb = (int64_t)lane->out_blocks.size(), nf = nb ? lane->n_frags : 0, ab = nb ? lane->aln_bytes : 0;
-	const int64_t need = REC_HDR + pad16(nb * (int64_t)sizeof(gsa_block)) + pad16(nf * (int64_t)sizeof(gsa_frag)) + 2 * pad16(ab);
-	// header + block headers travel in one small pinned staging block of the lane
-	const size_t hb = (size_t)(REC_HDR + nb * (int64_t)sizeof(gsa_block));
+	const char *rawenv = getenv("GSA_GATHER_RAW");
+	bool compact = !(rawenv && rawenv[0] == '1') && nf > 0 && ab < (1ll << 30) && lane->qlen < (1u << 29);
+	int64_t n_anchor = 0;
+	if (compact) { // the fragment list in its compact form, in scratch of the lane; the host learns how many anchors it took
+		const int64_t cap = nf / PK_STRIDE + 2 + 4 * (int64_t)lane->final_blocks.size() + 1024;
+		const int64_t tiles = chain_tiles(nf);
+		GSA_TRY(gsa_ensure(lane, lane->d_cfrag, (size_t)nf * 8));
+		GSA_TRY(gsa_ensure(lane, lane->d_anchor, (size_t)cap * sizeof(GsaAnchor)));
+		GSA_TRY(gsa_ensure(lane, lane->d_packst, 64 + (size_t)(tiles + 2) * 8));
+		int32_t *st = (int32_t *)lane->d_packst.p;
+		unsigned long long *chain = (unsigned long long *)((char *)lane->d_packst.p + 64);
+		CUDA_TRY(lane, cudaMemsetAsync(chain, 0, (size_t)(tiles + 2) * 8, lane->stream));
+		k_pack_init<<<1, 32, 0, lane->stream>>>(st, (int32_t)nf);
+		FPack f; f.frag = (const gsa_frag *)lane->d_frag.p; f.cfrag = (uint64_t *)lane->d_cfrag.p; f.anchor = (GsaAnchor *)lane->d_anchor.p; f.st = st; f.anchor_cap = (int)cap;
+		ChainState cs; cs.ticket = (unsigned int *)chain; cs.total = nullptr; cs.status = chain + 2;
+		k_chain<FPack><<<(unsigned)tiles, CH_THREADS, 0, lane->stream>>>(f, st + 2, cs);
+		lane->tm.launches += 2;
+		CUDA_TRY(lane, cudaGetLastError());
+		GSA_TRY(gsa_ensure_host(lane, lane->h_rec, 64));
+		GSA_TRY(gsa_small_d2h(lane, lane->h_rec.p, st, 16));
+		CUDA_TRY(lane, cudaStreamSynchronize(lane->stream));
+		const int32_t *hs = (const int32_t *)lane->h_rec.p;
+		n_anchor = hs[0];
+		if (hs[1] != 0 || n_anchor > cap) compact = false;   // a rule of the compact form does not hold for this record: send it as it is
+	}
+	const int64_t hdr_bytes = compact ? 2 * REC_HDR : REC_HDR;
+	const int64_t frag_bytes = compact ? pad16(nf * 8) + n_anchor * (int64_t)sizeof(GsaAnchor) : pad16(nf * (int64_t)sizeof(gsa_frag));
+	const int64_t need = hdr_bytes + pad16(nb * (int64_t)sizeof(gsa_block)) + frag_bytes + 2 * pad16(ab);
+	// header(s) + block headers travel in one small pinned staging block of the lane
+	const size_t hb = (size_t)(hdr_bytes + nb * (int64_t)sizeof(gsa_block));
 	GSA_TRY(gsa_ensure_host(lane, lane->h_rec, hb));
 	int64_t *hdr = (int64_t *)lane->h_rec.p;
-	hdr[0] = contig; hdr[1] = nb; hdr[2] = nf; hdr[3] = ab;
-	if (nb) memcpy((char *)lane->h_rec.p + REC_HDR, lane->out_blocks.data(), (size_t)nb * sizeof(gsa_block));
+	hdr[0] = compact ? -1 - contig : contig; hdr[1] = nb; hdr[2] = nf; hdr[3] = ab;
+	if (compact) { hdr[4] = n_anchor; hdr[5] = hdr[6] = hdr[7] = 0; }
+	if (nb) memcpy((char *)lane->h_rec.p + hdr_bytes, lane->out_blocks.data(), (size_t)nb * sizeof(gsa_block));
 	{
 		// Reserving the range and queueing the copies into it happen under the outbox lock: a lane that has to grow the outbox
 		// moves the image after waiting for every lane's last RECORDED append, so no append may sit between its reservation
@@ -186,9 +301,16 @@ int gsa_outbox_append(gsa_ctx *owner, gsa_ctx *lane, int64_t contig)
 		char *dst = (char *)owner->d_outbox.p + off;
 		if (owner->ev_gather) CUDA_TRY(lane, cudaStreamWaitEvent(lane->stream, owner->ev_gather, 0)); // the previous gather has left the outbox
 		CUDA_TRY(lane, cudaMemcpyAsync(dst, lane->h_rec.p, hb, cudaMemcpyHostToDevice, lane->stream));
-		char *p = dst + REC_HDR + pad16(nb * (int64_t)sizeof(gsa_block));
-		if (nf) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_frag.p, (size_t)nf * sizeof(gsa_frag), cudaMemcpyDeviceToDevice, lane->stream));
-		p += pad16(nf * (int64_t)sizeof(gsa_frag));
+		char *p = dst + hdr_bytes + pad16(nb * (int64_t)sizeof(gsa_block));
+		if (compact) {
+			CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_cfrag.p, (size_t)nf * 8, cudaMemcpyDeviceToDevice, lane->stream));
+			p += pad16(nf * 8);
+			if (n_anchor) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_anchor.p, (size_t)n_anchor * sizeof(GsaAnchor), cudaMemcpyDeviceToDevice, lane->stream));
+			p += n_anchor * (int64_t)sizeof(GsaAnchor);
+		} else {
+			if (nf) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_frag.p, (size_t)nf * sizeof(gsa_frag), cudaMemcpyDeviceToDevice, lane->stream));
+			p += pad16(nf * (int64_t)sizeof(gsa_frag));
+		}
 		if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln1.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
 		p += pad16(ab);
 		if (ab) CUDA_TRY(lane, cudaMemcpyAsync(p, lane->d_aln2.p, (size_t)ab, cudaMemcpyDeviceToDevice, lane->stream));
@@ -308,27 +430,71 @@ int gsa_inbox_host(gsa_ctx *root, int32_t rank, const void **host_ptr, int64_t *
 }
 
 // Host-side walk over an outbox image: fills *out with pointers into the image for the record at *offset and advances it.
-// Returns 1 while there is a record, 0 at the end, < 0 on a malformed image.
-int gsa_record_next(const void *image, int64_t bytes, int64_t *offset, int64_t *contig, gsa_alignment *out)
+// Returns 1 while there is a record, 0 at the end, < 0 on a malformed image.  For a record in the compact form out->frags
+// stays NULL: gsa_record_frags expands its fragment list.
+struct RecView { bool compact; int64_t contig, nb, nf, ab, n_anchor; const char *blocks, *frags, *anchors, *aln1, *aln2; int64_t end; };
+static int rec_view(const void *image, int64_t bytes, int64_t o, RecView &v)
 {
-	if (!image || !offset || !contig || !out) return GSA_ERR_ARG;
-	int64_t o = *offset;
-	if (o >= bytes) return 0;
 	if (o + REC_HDR > bytes) return GSA_ERR_ARG;
 	const char *base = (const char *)image;
 	int64_t h[4]; memcpy(h, base + o, sizeof(h)); o += REC_HDR;
-	const int64_t nb = h[1], nf = h[2], ab = h[3];
-	if (nb < 0 || nf < 0 || ab < 0) return GSA_ERR_ARG;
-	const int64_t end = o + pad16(nb * (int64_t)sizeof(gsa_block)) + pad16(nf * (int64_t)sizeof(gsa_frag)) + 2 * pad16(ab);
-	if (end > bytes) return GSA_ERR_ARG;
+	v.compact = h[0] < 0; v.contig = v.compact ? -1 - h[0] : h[0];
+	v.nb = h[1]; v.nf = h[2]; v.ab = h[3]; v.n_anchor = 0;
+	if (v.nb < 0 || v.nf < 0 || v.ab < 0 || v.nb > bytes || v.nf > bytes || v.ab > bytes) return GSA_ERR_ARG;
+	if (v.compact) {
+		if (o + REC_HDR > bytes) return GSA_ERR_ARG;
+		memcpy(h, base + o, sizeof(h)); o += REC_HDR;
+		v.n_anchor = h[0];
+		if (v.n_anchor < 0 || v.n_anchor > v.nf || (v.nf > 0 && v.n_anchor == 0)) return GSA_ERR_ARG;
+	}
+	const int64_t fb = v.compact ? pad16(v.nf * 8) + v.n_anchor * (int64_t)sizeof(GsaAnchor) : pad16(v.nf * (int64_t)sizeof(gsa_frag));
+	v.end = o + pad16(v.nb * (int64_t)sizeof(gsa_block)) + fb + 2 * pad16(v.ab);
+	if (v.end > bytes) return GSA_ERR_ARG;
+	v.blocks = base + o; o += pad16(v.nb * (int64_t)sizeof(gsa_block));
+	v.frags = base + o; v.anchors = v.compact ? base + o + pad16(v.nf * 8) : nullptr; o += fb;
+	v.aln1 = base + o; o += pad16(v.ab);
+	v.aln2 = base + o;
+	return GSA_OK;
+}
+
+int gsa_record_next(const void *image, int64_t bytes, int64_t *offset, int64_t *contig, gsa_alignment *out)
+{
+	if (!image || !offset || !contig || !out) return GSA_ERR_ARG;
+	if (*offset >= bytes) return 0;
+	RecView v;
+	if (rec_view(image, bytes, *offset, v) != GSA_OK) return GSA_ERR_ARG;
 	memset(out, 0, sizeof(*out));
-	*contig = h[0];
-	out->n_blocks = (int32_t)nb; out->blocks = (const gsa_block *)(base + o); o += pad16(nb * (int64_t)sizeof(gsa_block));
-	out->n_frags = nf; out->frags = (const gsa_frag *)(base + o); o += pad16(nf * (int64_t)sizeof(gsa_frag));
-	out->aln_bytes = ab; out->aln1 = base + o; o += pad16(ab);
-	out->aln2 = base + o; o += pad16(ab);
-	*offset = o;
+	*contig = v.contig;
+	out->n_blocks = (int32_t)v.nb; out->blocks = (const gsa_block *)v.blocks;
+	out->n_frags = v.nf; out->frags = v.compact ? nullptr : (const gsa_frag *)v.frags;
+	out->aln_bytes = v.ab; out->aln1 = v.aln1; out->aln2 = v.aln2;
+	*offset = v.end;
 	return 1;
+}
+
+int gsa_record_frags(const void *image, int64_t bytes, int64_t record_offset, gsa_frag *dst, int32_t n_threads)
+{
+	if (!image || record_offset < 0 || record_offset >= bytes) return GSA_ERR_ARG;
+	RecView v;
+	if (rec_view(image, bytes, record_offset, v) != GSA_OK) return GSA_ERR_ARG;
+	if (v.nf == 0) return GSA_OK;
+	if (!dst) return GSA_ERR_ARG;
+	if (!v.compact) { memcpy(dst, v.frags, (size_t)v.nf * sizeof(gsa_frag)); return GSA_OK; }
+	const uint64_t *cfrag = (const uint64_t *)v.frags;
+	const GsaAnchor *an = (const GsaAnchor *)v.anchors;
+	// anchors are in fragment order and the first one sits on fragment 0: every stretch between two anchors is independent
+	if (an[0].first != 0) return GSA_ERR_ARG;
+	for (int64_t k = 0; k < v.n_anchor; k++) {
+		const int64_t end = k + 1 < v.n_anchor ? an[k + 1].first : v.nf;
+		if (an[k].first < 0 || an[k].first >= end || end > v.nf) return GSA_ERR_ARG;
+	}
+	const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, v.n_anchor / 64));
+	auto work = [&](int t) {
+		for (int64_t k = v.n_anchor * t / nt; k < v.n_anchor * (t + 1) / nt; k++) pk_expand(cfrag, an[k], k + 1 < v.n_anchor ? an[k + 1].first : v.nf, dst);
+	};
+	if (nt == 1) work(0);
+	else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
+	return GSA_OK;
 }
 
 } // extern "C"

@@ -130,6 +130,7 @@ struct gsa_ctx {
 	bool keep_dumps = false;
 	bool host_results = true;      // gsa_fill copies fragments and rows to pinned host memory
 	std::vector<BlockHdr> final_blocks;   // after dedup, reference order
+	int split_hazard = 0;                 // hazard H14: split phases of this contig whose pushes crossed a power of two (gsa_split_hazard)
 
 	// fragments (after FillAlnBlockGaps) and K3 output
 	int64_t n_frags = 0;
@@ -151,6 +152,7 @@ struct gsa_ctx {
 	cudaEvent_t ev_gather = nullptr;       // end of this rank's part of the last gather (the next step's appends order after it)
 	cudaEvent_t ev_outbox = nullptr;       // per lane: its last append
 	DevBuf d_outbox, d_sizes;
+	DevBuf d_cfrag, d_anchor, d_packst;    // per lane: a record's compact fragment list on its way into the outbox
 	int64_t outbox_used = 0;
 	std::mutex outbox_mu;                  // lanes of one GPU append from their own host threads
 	std::vector<cudaEvent_t> outbox_pending;
@@ -165,6 +167,8 @@ int gsa_ensure_host(gsa_ctx *ctx, HostBuf &b, size_t bytes);
 // mapped host pointer instead of a copy engine (capi.cu); sizes above 256 KB fall back to cudaMemcpyAsync
 int gsa_small_d2h(gsa_ctx *ctx, void *host_pinned, const void *dev, size_t bytes);
 int gsa_small_h2d(gsa_ctx *ctx, void *dev, const void *host_pinned, size_t bytes);
+// bulk transfer between pinned host memory and HBM, queued in pieces of a few MB (capi.cu)
+int gsa_bulk_copy(gsa_ctx *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream);
 // the first min(*d_count, cap) elements of a device table whose length is only known on the device
 int gsa_small_d2h_counted(gsa_ctx *ctx, void *host_pinned, const void *dev, size_t elem_bytes, const int32_t *d_count, int cap);
 
@@ -194,7 +198,7 @@ int gsa_impl_pack_query(gsa_ctx *ctx);
 int gsa_impl_seed(gsa_ctx *ctx);
 int gsa_impl_cluster(gsa_ctx *ctx);
 // host block logic (block_logic.cpp): exact restatement of the reference's O(#blocks) serial phases
-void gsa_host_split(const gsa_ctx *ctx, std::vector<BlockHdr> &vec, const std::vector<Piece> &p1, const std::vector<Piece> &p2);
+void gsa_host_split(gsa_ctx *ctx, std::vector<BlockHdr> &vec, const std::vector<Piece> &p1, const std::vector<Piece> &p2);
 void gsa_host_dedup(const gsa_ctx *ctx, std::vector<BlockHdr> &vec);
 void gsa_host_remove_bad(std::vector<BlockHdr> &vec);
 int gsa_host_chr_idx(const gsa_ctx *ctx, int64_t rpos, int64_t *end_out);

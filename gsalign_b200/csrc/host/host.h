@@ -74,6 +74,8 @@ struct ContigResult {
 	std::vector<int64_t> var_first, var_count;
 	bool have_vars = false;
 	void assign(const gsa_alignment &a);
+	// a record of a gathered outbox image (gsa_record_next): the fragment list may have travelled in the compact form
+	int assign_record(const gsa_alignment &a, const void *image, int64_t bytes, int64_t record_offset);
 	void assign_variants(const gsa_variant_list &v);
 };
 

@@ -10,6 +10,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include "host.h"
@@ -244,12 +245,17 @@ int main(int argc, char *argv[])
 				if (gsa_inbox_host(owners[0], r, &img, &bytes) != 0) { bad = true; break; }
 				std::vector<std::thread> cp; std::vector<int64_t> got;
 				gsa_alignment al; int rc;
-				while ((rc = gsa_record_next(img, bytes, &off, &contig, &al)) == 1) {
+				std::deque<int> cp_rc;   // one result per copy thread; a deque keeps their addresses stable
+				for (int64_t start = off; (rc = gsa_record_next(img, bytes, &off, &contig, &al)) == 1; start = off) {
 					if (contig < 0 || contig >= nq) { rc = -1; break; }
 					got.push_back(contig);
-					cp.emplace_back([&results, contig, al] { results[(size_t)contig].assign(al); });
+					cp_rc.push_back(0);
+					int *prc = &cp_rc.back();
+					// blocks and rows are copied out of the image; the fragment list is expanded from its compact form (or copied)
+					cp.emplace_back([&results, contig, al, img, bytes, start, prc] { *prc = results[(size_t)contig].assign_record(al, img, bytes, start); });
 				}
 				for (auto &t : cp) t.join();
+				for (int x : cp_rc) if (x != 0) rc = -1;
 				if (rc < 0) { bad = true; break; }
 				std::unique_lock<std::mutex> lk(mu);
 				for (int64_t qi : got) done[(size_t)qi] = 1;

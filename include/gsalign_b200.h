@@ -69,7 +69,8 @@ typedef struct {
 	int32_t bSeed;             /* 1 = exact seed, 0 = gap fragment between two seeds */
 	int64_t aln_off;           /* gap fragments: offset of the two aligned rows in gsa_alignment::aln1/aln2 */
 	int32_t aln_len;           /* gap fragments: number of alignment columns; seeds: qLen */
-	int32_t reserved;
+	int32_t reserved;          /* seeds: 0; gap fragments: how the rows were produced -- 1 deletion, 2 insertion, 3 copied (equal
+	                              lengths, <= 5 mismatches), 4 gapped alignment (ksw2 semantics) */
 } gsa_frag;
 
 /* AlnBlock_t (src/structure.h:115-122); coor is left to the emitter (GenCoordinateInfo is host logic). */
@@ -198,6 +199,12 @@ int gsa_align_contig(gsa_ctx *ctx, const char *seq, uint32_t len, gsa_alignment 
 
 int gsa_get_timing(const gsa_ctx *ctx, gsa_timing *out);
 
+/* Hazard detector: number of block-split phases of the last gsa_cluster() in which the block list grew
+ * across a power of two.  There the reference splits through a reference into a std::vector it is pushing to
+ * (src/ProcessCandidateAlignment.cpp:102-116,142-154): its result is undefined, so a difference against the reference on
+ * such a contig is to be flagged, not counted as a mismatch.  0 = parity is defined. */
+int gsa_split_hazard(const gsa_ctx *ctx);
+
 /* keep (1) or drop (0, default) the intermediate block lists gsa_dump_blocks() serves */
 int gsa_set_dump(gsa_ctx *ctx, int enable);
 
@@ -220,8 +227,12 @@ int gsa_index_selfcheck(gsa_ctx *ctx, int64_t n_samples, int64_t *n_bad);
  * Query contigs are dealt to GPUs, every GPU holds an index replica, and the finished records of all GPUs are collected
  * on the root GPU by ONE gather per job: grouped ncclSend / ncclRecv over NVLink.  NCCL is bound at run time (dlopen);
  * these calls fail with GSA_ERR_CUDA where it is absent, everything else works without it.
- * Outbox image (little-endian, every section padded to 16 bytes), one record per finished contig:
- *   int64[4] {contig, n_blocks, n_frags, aln_bytes}, gsa_block[n_blocks], gsa_frag[n_frags], aln1[aln_bytes], aln2[aln_bytes] */
+ * Outbox image (little-endian, every section padded to 16 bytes), one record per finished contig, either plain
+ *   int64[4] {contig, n_blocks, n_frags, aln_bytes}, gsa_block[n_blocks], gsa_frag[n_frags], aln1[aln_bytes], aln2[aln_bytes]
+ * or compact (the default; GSA_GATHER_RAW=1 keeps the plain form)
+ *   int64[4] {-1 - contig, n_blocks, n_frags, aln_bytes}, int64[4] {n_anchors, 0, 0, 0}, gsa_block[n_blocks],
+ *   uint64[n_frags] {qLen:21, rLen:21, aln_len:20, bSeed:1, gapped:1}, anchor[n_anchors] {int64 first_frag, rPos; int32 qPos, 0;
+ *   int64 row_base}, aln1[aln_bytes], aln2[aln_bytes] */
 /* one process per GPU: rank 0 makes the 128-byte id, the host hands it to every rank (MPI, torch.distributed, a file ...) */
 int gsa_comm_unique_id(void *id, int32_t id_bytes);
 int gsa_comm_init_rank(gsa_ctx *ctx, const void *id, int32_t rank, int32_t n_ranks);
@@ -243,8 +254,13 @@ int gsa_gather_wait(gsa_ctx *owner);
 int gsa_inbox_device(gsa_ctx *root, int32_t rank, const void **dev_ptr, int64_t *bytes);
 int gsa_inbox_host(gsa_ctx *root, int32_t rank, const void **host_ptr, int64_t *bytes);
 /* host-side walk over an image: returns 1 and fills *contig / *out (pointers into the image) for the record at *offset,
- * which it advances; 0 at the end; < 0 on a malformed image */
+ * which it advances; 0 at the end; < 0 on a malformed image.  Records travel in a compact form by default (8 bytes per
+ * fragment instead of 40: lengths only, positions and row offsets follow from an anchor every 256 fragments); for those
+ * out->frags is NULL and gsa_record_frags() writes the fragment list where the caller wants it. */
 int gsa_record_next(const void *image, int64_t bytes, int64_t *offset, int64_t *contig, gsa_alignment *out);
+/* the n_frags fragment records of the record that STARTS at record_offset (the value *offset had before gsa_record_next
+ * returned it), expanded or copied into dst; n_threads > 1 spreads the work over host threads */
+int gsa_record_frags(const void *image, int64_t bytes, int64_t record_offset, gsa_frag *dst, int32_t n_threads);
 
 /* Stand-alone batch of global alignments through K3's DP kernel (ksw2_alignment semantics):
  * pair i aligns ref[ref_off[i] .. ref_off[i+1]) with qry[qry_off[i] .. qry_off[i+1]); rows are written

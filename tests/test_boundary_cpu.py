@@ -241,3 +241,50 @@ def test_record_walk_host_only():
     assert lib.gsa_record_next(buf, C.c_int64(len(img)), C.byref(off), C.byref(contig), C.byref(al)) == 0
     off = C.c_int64(0)
     assert lib.gsa_record_next(buf, C.c_int64(len(rec0) - 16), C.byref(off), C.byref(contig), C.byref(al)) < 0
+
+
+def test_compact_record_expansion_host_only():
+    """gsa_record_frags is host code: a hand-built record in the compact form (8 bytes per fragment + anchors) expands to the
+    fragment records the rule in gather.cu defines -- positions chained from the anchors, row offsets from the running row
+    slots, gapped alignments right-aligned in a slot of qLen + rLen -- and malformed anchors are rejected"""
+    import ctypes as C
+    from gsalign_b200 import capi
+    lib = capi.load_library()
+
+    def pad(b):
+        return b + b"\0" * (-len(b) % 16)
+    # (bSeed, qLen, rLen, aln_len, gapped) ; a second block restarts the positions at fragment 5
+    spec = [(1, 20, 20, 20, 0), (0, 3, 5, 6, 1), (1, 10, 10, 10, 0), (0, 0, 4, 4, 0), (1, 7, 7, 7, 0),
+            (1, 15, 15, 15, 0), (0, 2, 2, 2, 0), (1, 9, 9, 9, 0), (0, 6, 0, 6, 0), (1, 30, 30, 30, 0)]
+    anchors = [(0, 1000, 50, 0), (5, 70_000_000_000, 400, 12)]     # (first fragment, rPos, qPos, row base); rows before fragment 5: 8 + 4
+    want = np.zeros(len(spec), dtype=capi.FRAG_DTYPE)
+    k = -1
+    for i, (seed, ql, rl, al_, gp) in enumerate(spec):
+        if k + 1 < len(anchors) and anchors[k + 1][0] == i:
+            k += 1
+            r, q, row = anchors[k][1], anchors[k][2], anchors[k][3]
+        slot = 0 if seed else (ql + rl if gp else (rl if ql == 0 else ql))
+        typ = 0 if seed else (1 if ql == 0 else 2 if rl == 0 else 4 if gp else 3)
+        want[i] = (r, q, ql, rl, seed, 0 if seed else row + (slot - al_ if gp else 0), al_, typ)
+        r += rl; q += ql; row += slot
+    cfrag = np.array([ql | (rl << 21) | (al_ << 42) | (seed << 62) | (gp << 63) for seed, ql, rl, al_, gp in spec], dtype=np.uint64)
+    anc = b"".join(np.array([f, r], dtype=np.int64).tobytes() + np.array([q, 0], dtype=np.int32).tobytes() + np.array([row], dtype=np.int64).tobytes() for f, r, q, row in anchors)
+    blocks = np.zeros(2, dtype=capi.BLOCK_DTYPE); blocks["n_frags"] = [5, 5]; blocks["frag_beg"] = [0, 5]
+    rows = 8 + 4 + 2 + 6
+    a1, a2 = bytes(range(65, 65 + rows)), bytes(range(97, 97 + rows))
+
+    def image(anchor_bytes, n_anchor):
+        return (np.array([-1 - 4, 2, len(spec), rows], dtype=np.int64).tobytes() + np.array([n_anchor, 0, 0, 0], dtype=np.int64).tobytes() +
+                pad(blocks.tobytes()) + pad(cfrag.tobytes()) + anchor_bytes + pad(a1) + pad(a2))
+    img = image(anc, 2) + np.array([9, 0, 0, 0], dtype=np.int64).tobytes()       # a plain, empty record follows
+    buf = C.create_string_buffer(img, len(img))
+    recs = capi.walk_image(lib, buf, len(img))
+    assert [r[0] for r in recs] == [4, 9]
+    assert recs[0][2].tobytes() == want.tobytes()
+    assert recs[0][3].tobytes() == a1 and recs[0][4].tobytes() == a2 and list(recs[0][1]["frag_beg"]) == [0, 5]
+    # the first anchor must sit on fragment 0, anchors must be in order
+    for bad in (anc[32:] + anc[:32], anc.replace(np.array([5], dtype=np.int64).tobytes(), np.array([50], dtype=np.int64).tobytes(), 1)):
+        b = image(bad, 2)
+        bb = C.create_string_buffer(b, len(b))
+        out = np.zeros(len(spec), dtype=capi.FRAG_DTYPE)
+        assert lib.gsa_record_frags(bb, C.c_int64(len(b)), C.c_int64(0), out.ctypes.data_as(C.c_void_p), C.c_int32(1)) < 0

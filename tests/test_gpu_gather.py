@@ -23,10 +23,13 @@ def _records_equal(a, b):
     return True
 
 
-def test_outbox_roundtrip_one_rank(ecoli):
+@pytest.mark.parametrize("form", ["compact", "plain"])
+def test_outbox_roundtrip_one_rank(ecoli, form, monkeypatch):
     """one-rank communicator: two lanes append their contigs (device to device), the gather leaves the image where it is, and the
-    records read back on the host equal what gsa_fill hands out directly"""
+    records read back on the host equal what gsa_fill hands out directly -- in the compact form records travel in by default
+    (8 bytes per fragment, expanded by gsa_record_frags) and in the plain one (GSA_GATHER_RAW=1)"""
     from gsalign_b200 import capi
+    monkeypatch.setenv("GSA_GATHER_RAW", "1" if form == "plain" else "0")
     al = capi.Aligner(0)
     al.upload_index(ecoli["index"])
     lane = capi.Aligner(0, owner=al)
@@ -42,6 +45,8 @@ def test_outbox_roundtrip_one_rank(ecoli):
             ln.contig_begin(p); ln.seed(); ln.cluster(); ln.fill()
             al.outbox_append(ln, 10 + i)
         assert al.outbox_bytes() > 0
+        raw_bytes = sum(len(d[1]) * capi.FRAG_DTYPE.itemsize for d in direct)
+        assert (al.outbox_bytes() < raw_bytes) == (form == "compact")   # 40 bytes per fragment shrink to 8 (+ anchors)
         al.gather_records(0); al.gather_wait()
         recs = al.inbox_records(0)
         al.outbox_reset()
