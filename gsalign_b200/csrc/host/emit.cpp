@@ -126,15 +126,6 @@ void ContigResult::assign(const gsa_alignment &a)
 	aln2.assign(a.aln2 ? a.aln2 : "", (size_t)a.aln_bytes);
 }
 
-int ContigResult::assign_record(const gsa_alignment &a, const void *image, int64_t bytes, int64_t record_offset)
-{
-	blocks.assign(a.blocks, a.blocks + a.n_blocks);
-	frags.resize((size_t)a.n_frags);
-	aln1.assign(a.aln1 ? a.aln1 : "", (size_t)a.aln_bytes);
-	aln2.assign(a.aln2 ? a.aln2 : "", (size_t)a.aln_bytes);
-	return gsa_record_frags(image, bytes, record_offset, frags.data(), 4);
-}
-
 static inline int nt4(char ch)
 { // nst_nt4_table
 	switch (ch) {

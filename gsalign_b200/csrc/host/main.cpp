@@ -72,6 +72,16 @@ static void tick(const char *what)
 	last = now;
 }
 
+// (lives here, not in emit.cpp: the emitters build without the library -- tests/emit_harness.cpp -- and this calls into it)
+int ContigResult::assign_record(const gsa_alignment &a, const void *image, int64_t bytes, int64_t record_offset)
+{
+	blocks.assign(a.blocks, a.blocks + a.n_blocks);
+	frags.resize((size_t)a.n_frags);
+	aln1.assign(a.aln1 ? a.aln1 : "", (size_t)a.aln_bytes);
+	aln2.assign(a.aln2 ? a.aln2 : "", (size_t)a.aln_bytes);
+	return gsa_record_frags(image, bytes, record_offset, frags.data(), 4);
+}
+
 struct Worker {
 	gsa_ctx *ctx = nullptr;
 	std::thread th;
@@ -147,8 +157,14 @@ int main(int argc, char *argv[])
 		gsa_index_view view; ix.view(&view);
 		// GPU 0 gets the index files and derives the HBM layout; the other GPUs receive a copy of the finished layout over
 		// NVLink (the derived structures are several times the size of the files), all of them at the same time
-		for (int g = 0; g < n_dev; g++)
-			if (gsa_create(g, &owners[g]) != 0) { idx_err = "FatalError: cannot open CUDA device " + std::to_string(g) + " (this build has no CPU path)\n"; return; }
+		{ // a CUDA context takes a second or two to come up: all GPUs at once
+			std::vector<std::thread> mk;
+			std::vector<int> mk_rc((size_t)n_dev, 0);
+			for (int g = 0; g < n_dev; g++) mk.emplace_back([&, g] { mk_rc[(size_t)g] = gsa_create(g, &owners[g]); });
+			for (auto &t : mk) t.join();
+			for (int g = 0; g < n_dev; g++)
+				if (mk_rc[(size_t)g] != 0) { idx_err = "FatalError: cannot open CUDA device " + std::to_string(g) + " (this build has no CPU path)\n"; return; }
+		}
 		if (gsa_set_params(owners[0], &prm) != 0 || gsa_index_upload(owners[0], &view) != 0) { idx_err = std::string("FatalError: ") + gsa_last_error(owners[0]) + "\n"; return; }
 		tick("index uploaded");
 		std::vector<std::thread> cl;
