@@ -158,7 +158,7 @@ __device__ __forceinline__ int64_t pd_of(const GroupView &v, int64_t i) { return
 // UniqueArr (src/GSAlign.cpp:316-325) and the positions where a window may close: unique, and PosDiff differs from the
 // previous element (:328-331); U = inclusive count of unique seeds, C = list of the candidates
 struct FUniq {
-	GroupView v; int32_t *uq, *U; uint8_t *cand; int32_t *C, *dc;
+	GroupView v; int32_t *uq, *U; uint8_t *cand; int32_t *C, *cpos, *dc;   // cpos[i] = index of candidate i in C
 	struct Item { uint8_t uq, cand; };
 	__device__ Item load(int64_t i) const
 	{
@@ -174,22 +174,26 @@ struct FUniq {
 	{
 		if (!valid) return;
 		uq[i] = it.uq; U[i] = (int32_t)CH_LO(excl) + it.uq; cand[i] = it.cand;
-		if (it.cand) C[CH_HI(excl)] = (int32_t)i;
+		if (it.cand) { C[CH_HI(excl)] = (int32_t)i; cpos[i] = (int32_t)CH_HI(excl); }
 	}
 	__device__ void finish(unsigned long long total) const { dc[DC_NC] = (int32_t)CH_HI(total); }
 };
 
 // next window start after a window that starts at i (src/GSAlign.cpp:326-337): the first candidate j > i with
-// (#unique in the window so far) >= 30 and q[j] - q[i] > 3000; reach[] starts at the group starts
-__global__ void k_next(GroupView v, const int32_t *uq, const int32_t *U, const uint8_t *cand, const int32_t *C, const int32_t *d_nC, int32_t *nxt, int32_t *reach)
+// (#unique in the window so far) >= 30 and q[j] - q[i] > 3000.  Only group starts and candidates can start a window, and a
+// window's successor is always a candidate: the chain of window starts lives on the candidate list C.  So the successor is
+// kept as an INDEX INTO C (nC = none): jump[c] for candidate c, and creach[] -- "candidate c starts a window" -- is seeded with
+// the successors of the group starts.  reach[] (per seed) starts as the group starts.
+__global__ void k_next(GroupView v, const int32_t *uq, const int32_t *U, const uint8_t *cand, const int32_t *C, const int32_t *cpos, const int32_t *d_nC,
+                       int32_t *jump, int32_t *creach, int32_t *reach)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int64_t n = *v.dn;
-	if (i > n) return;
-	if (i == n) { nxt[i] = (int32_t)n; reach[i] = 0; return; }
+	if (i >= n) return;
 	int gs = v.gstart[v.dg[i]], ge = v.gstart[v.dg[i] + 1];
 	reach[i] = i == gs;
-	if (i != gs && !cand[i]) { nxt[i] = (int32_t)n; return; }
+	if (i != gs && !cand[i]) return;
+	const int nC = *d_nC;
 	int baseU = i == gs ? U[i] - uq[i] : U[i]; // the first window counts its own first element, later ones restart at 0
 	int lo = (int)i + 1, hi = ge;
 	while (lo < hi) { int m = (lo + hi) >> 1; if (U[m] - baseU >= 30) hi = m; else lo = m + 1; }
@@ -198,24 +202,43 @@ __global__ void k_next(GroupView v, const int32_t *uq, const int32_t *U, const u
 	int qi = v.q[i];
 	while (lo < hi) { int m = (lo + hi) >> 1; if (v.q[m] - qi > 3000) hi = m; else lo = m + 1; }
 	int j0 = max(jA, lo);
-	int res = (int)n;
+	int res = nC;
 	if (j0 < ge) {
-		int nC = *d_nC; lo = 0; hi = nC;
+		lo = 0; hi = nC;
 		while (lo < hi) { int m = (lo + hi) >> 1; if (C[m] < j0) lo = m + 1; else hi = m; }
-		if (lo < nC && C[lo] < ge) res = C[lo];
+		if (lo < nC && C[lo] < ge) res = lo;
 	}
-	nxt[i] = res;
+	if (i == gs) { if (res < nC) creach[res] = 1; }
+	else jump[cpos[i]] = res;
 }
 
-// pointer jumping: reach is monotone and updated in place, the jump table is ping-ponged
-__global__ void k_jump(int32_t *reach, const int32_t *nin, int32_t *nout, const int32_t *dn)
+// Pointer jumping over the candidate list in one persistent launch: every round doubles the reach of jump[] (ping-ponged
+// between two tables) and marks the candidates it lands on; creach is monotone and updated in place.  The rounds are
+// separated by a grid-wide barrier (a counter in global memory; the launch is cooperative, so all CTAs are resident).
+// At the end the marks go back to the seeds: reach[C[c]] = 1.
+__global__ void __launch_bounds__(512) k_jump_all(int32_t *creach, int32_t *ja, int32_t *jb, const int32_t *C, const int32_t *d_nC, int32_t *reach, int rounds, unsigned int *bar)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const int64_t n = *dn;
-	if (i > n) return;
-	int32_t j = nin[i];
-	if (reach[i] && j < n) reach[j] = 1;
-	nout[i] = nin[j];
+	const int nC = *d_nC;
+	const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+	for (int r = 0; r < rounds; r++) {
+		for (int c = t0; c < nC; c += stride) {
+			const int j = ja[c];
+			int jj = nC;
+			if (j < nC) { if (creach[c]) creach[j] = 1; jj = ja[j]; }
+			jb[c] = jj;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			__threadfence();
+			atomicAdd(bar, 1u);
+			const unsigned int want = (unsigned int)(r + 1) * gridDim.x;
+			while (*(volatile unsigned int *)bar < want) { }
+			__threadfence();
+		}
+		__syncthreads();
+		int32_t *t = ja; ja = jb; jb = t;
+	}
+	for (int c = t0; c < nC; c += stride) if (creach[c]) reach[C[c]] = 1;
 }
 
 #define HASH_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -765,11 +788,28 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 	uint8_t *cand = ws.get<uint8_t>(n + 2);
 	int32_t *nxtA = ws.get<int32_t>(n + 2), *nxtB = ws.get<int32_t>(n + 2), *reach = ws.get<int32_t>(n + 2), *wid1 = ws.get<int32_t>(n + 2);
 	if (ws.rc) return ws.rc;
-	{ FUniq f; f.v = gv; f.uq = uq; f.U = U; f.cand = cand; f.C = C; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N2, n)); }
-	LAUNCH(k_next, n + 1, gv, uq, U, cand, C, dc + DC_NC, nxtA, reach);
+	int32_t *cpos = ws.get<int32_t>(n + 2), *creach = ws.get<int32_t>(n + 2);
+	if (ws.rc) return ws.rc;
+	{ FUniq f; f.v = gv; f.uq = uq; f.U = U; f.cand = cand; f.C = C; f.cpos = cpos; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N2, n)); }
+	CUDA_TRY(ctx, cudaMemsetAsync(creach, 0, (size_t)(n + 2) * 4, ctx->stream));
+	LAUNCH(k_next, n, gv, uq, U, cand, C, cpos, dc + DC_NC, nxtA, creach, reach);
 	{
+		// a window holds at least 30 unique seeds: a chain has at most n / 30 + 1 links
 		int rounds = 1; while ((1ll << rounds) < n / 30 + 2) rounds++;
-		for (int k = 0; k <= rounds; k++) { LAUNCH(k_jump, n + 1, reach, nxtA, nxtB, dc + DC_N2); std::swap(nxtA, nxtB); }
+		rounds++;
+		unsigned int *bar = (unsigned int *)ctx->d_counter.p + 96;
+		CUDA_TRY(ctx, cudaMemsetAsync(bar, 0, 4, ctx->stream));
+		static int jump_ctas = 0;   // CTAs of k_jump_all that are resident at once (the grid barrier needs them all)
+		if (jump_ctas == 0) {
+			int per_sm = 0, sms = 0;
+			CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jump_all, 512, 0));
+			CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+			jump_ctas = std::max(1, std::min(per_sm, 1) * sms);
+		}
+		const int32_t *Cc = C, *dnc = dc + DC_NC;
+		void *args[] = {&creach, &nxtA, &nxtB, &Cc, &dnc, &reach, &rounds, &bar};
+		CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void *)k_jump_all, dim3((unsigned)jump_ctas), dim3(512), args, 0, ctx->stream));
+		KERNEL_CHECK(ctx);
 	}
 	// per-window histogram of PosDiff>>4 over unique seeds -> mode, average, outlier kill
 	int64_t hsize = 1024; while (hsize < 2 * n) hsize <<= 1;
