@@ -1,16 +1,17 @@
-// block_logic.cpp -- the O(#blocks) serial phases of GenomeComparison that stay on the host.
+// block_logic.cpp -- the O(#blocks) serial phases of GenomeComparison, host form.
 //
-// These are not kernels and not a fallback: the reference itself runs them serially on a handful of
-// block headers, they use float/double comparisons and libstdc++'s unstable std::sort whose tie order
-// is observable in the MAF record order (SURVEY.md hazards H9, H14, appendix D).  To be byte-exact we
-// run the SAME std::sort calls on the same element order with the same comparators:
+// The reference runs these serially on a handful of block headers; they use float/double comparisons and libstdc++'s
+// unstable std::sort whose tie order is observable in the MAF record order (SURVEY.md hazards H9, H14, appendix D).  To be
+// byte-exact this file runs the SAME std::sort calls on the same element order with the same comparators:
 //   RemoveBadAlnBlocks                  reference src/ProcessCandidateAlignment.cpp:72-79
 //   CheckGapsBetweenSeeds (tail)        reference src/ProcessCandidateAlignment.cpp:140-155
 //   CheckAlnBlockSpanMultipleRefChrs    reference src/ProcessCandidateAlignment.cpp:100-117
 //   EstChromosomeSimilarity             reference src/GSAlign.cpp:393-407
 //   RemoveRedundantAlnBlocks            reference src/GSAlign.cpp:415-471
-// All O(#seeds) work (break-point detection, piece sums) was done on the device; this file only sees
-// block headers and piece tables.
+// All O(#seeds) work (break-point detection, piece sums) was done on the device; this file only sees block headers and
+// piece tables.  By default the same logic runs in a kernel (block_logic.cuh + stdsort.cuh, cluster.cu: k_block_logic) so
+// that K2 needs one host wait per contig; this form is the path of contigs the kernel declines (more than 1 024 blocks,
+// another RemoveOverlaps round), of GSA_BLOCK_LOGIC=host, and the checker of the array form in tests/test_boundary_cpu.py.
 #include <algorithm>
 #include "gsa_internal.cuh"
 

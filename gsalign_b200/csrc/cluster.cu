@@ -20,6 +20,7 @@
 // Only O(#blocks) headers go to the host (block_logic.cpp) for the reference's float/std::sort logic.
 #include "fm.cuh"
 #include "scan.cuh"
+#include "block_logic.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 
@@ -663,12 +664,13 @@ __device__ __forceinline__ void np_locate(const NpBlock *nb, int nblk, int64_t t
 }
 
 struct FNormalPairs {
-	const NpBlock *nb; int nblk; const int32_t *q; const int64_t *r; const int32_t *l; gsa_frag *frag; int32_t *fblk; int64_t *blk_frag_beg; int32_t *dc;
+	const NpBlock *nb; int nblk; const int32_t *d_nblk;   // the block count: on the host, or (d_nblk != null) where the device block logic left it
+	const int32_t *q; const int64_t *r; const int32_t *l; gsa_frag *frag; int32_t *fblk; int64_t *blk_frag_beg; int32_t *dc;
 	struct Item { int32_t k, q, l, qg, rg; int64_t r; uint8_t first; };
 	__device__ Item load(int64_t t) const
 	{
 		Item it; int64_t s;
-		np_locate(nb, nblk, t, it.k, s);
+		np_locate(nb, d_nblk ? *d_nblk : nblk, t, it.k, s);
 		it.q = q[s]; it.r = r[s]; it.l = l[s]; it.qg = it.rg = 0; it.first = t == nb[it.k].dst_beg;
 		if (t + 1 < nb[it.k].dst_beg + nb[it.k].n) { // not the last seed of its block
 			it.qg = q[s + 1] - (it.q + it.l); it.rg = (int32_t)(r[s + 1] - (it.r + it.l));
@@ -690,6 +692,53 @@ struct FNormalPairs {
 	}
 	__device__ void finish(unsigned long long total) const { dc[DC_NFR] = (int32_t)total; }
 };
+
+// ------------------------------------------------------------------------------------------------
+// 5. the block logic on the device (SURVEY rows A8 tail + N4): block headers from the piece tables, the two split phases,
+// EstChromosomeSimilarity + RemoveRedundantAlnBlocks, and the table IdentifyNormalPairs works from -- block_logic.cuh, the
+// same statements as the host path (block_logic.cpp) with libstdc++'s introsort restated (stdsort.cuh).  One thread: the
+// work is O(#blocks) with a handful of blocks per contig and the order of every step is part of the result.  It exists so
+// that the phase needs no host round trip between the piece tables and the fragment list: everything after RemoveOverlaps
+// is queued blindly and the host looks at the outcome once, at the end.  A contig with more blocks than the kernel's list
+// holds, or whose RemoveOverlaps needed another round, takes the host path instead.
+// ------------------------------------------------------------------------------------------------
+#define BLK_DEV_CAP 1024
+enum { BR_NFINAL = 0, BR_STATUS, BR_HAZARD, BR_N1, BR_N2, BR_COUNT = 8 };   // res[]: status 0 ok, 1 list too small, 2 inconsistent counts
+struct BlkLogicArgs {
+	const Piece *pt0, *pt1, *pt2; const int32_t *kept_score; int32_t *dc;
+	BlockHdr *vec; NpBlock *npb; BlkParams P;
+	BlockHdr *stage1, *stage2;      // snapshots for the dump hook (may be null)
+	int32_t *res;
+};
+
+__global__ void k_block_logic(BlkLogicArgs A)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	int32_t *res = A.res;
+	for (int i = 0; i < BR_COUNT; i++) res[i] = 0;
+	A.dc[DC_N0] = 0;
+	const int np0 = A.dc[DC_NP0], np1 = A.dc[DC_NP1], np2 = A.dc[DC_NP2];
+	if (np0 != A.dc[DC_NB1]) { res[BR_STATUS] = 2; return; }   // RemoveOverlaps must not change the number of blocks
+	if (np0 > BLK_DEV_CAP) { res[BR_STATUS] = 1; return; }
+	for (int i = 0; i < np0; i++) A.vec[i] = blk_from_piece(A.pt0[i], A.kept_score[i]); // blocks keep their pre-overlap score
+	res[BR_N1] = np0;
+	if (A.stage1) for (int i = 0; i < np0; i++) A.stage1[i] = A.vec[i];
+	int hz = 0;
+	int n = blk_split(A.P, A.vec, np0, BLK_DEV_CAP, A.pt1, np1, &hz);      // CheckAlnBlockLargeGaps + RemoveBadAlnBlocks
+	if (n >= 0) n = blk_split(A.P, A.vec, n, BLK_DEV_CAP, A.pt2, np2, &hz); // CheckAlnBlockSpanMultiSeqs + RemoveBadAlnBlocks
+	if (n < 0) { res[BR_STATUS] = 1; return; }
+	res[BR_N2] = n; res[BR_HAZARD] = hz;
+	if (A.stage2) for (int i = 0; i < n; i++) A.stage2[i] = A.vec[i];
+	n = blk_dedup(A.P, A.vec, n);
+	long long total = 0;
+	for (int k = 0; k < n; k++) {
+		NpBlock b; b.src_beg = A.vec[k].beg; b.dst_beg = total; b.n = (int32_t)(A.vec[k].end - A.vec[k].beg); b.pad = 0;
+		A.npb[k] = b; total += b.n;
+	}
+	if (total >= 0x3FFFFFF0ll) { res[BR_STATUS] = 2; return; }
+	res[BR_NFINAL] = n;
+	A.dc[DC_N0] = (int32_t)total;   // element count of the IdentifyNormalPairs chain
+}
 
 // ------------------------------------------------------------------------------------------------
 // host driver
@@ -879,6 +928,9 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 	uint8_t *gapf = alive;
 	int32_t *gcand = reach;
 	PieceTable pt0, pt1, pt2;
+	// GSA_BLOCK_LOGIC=host: the O(#blocks) logic on the host (two waits per contig) instead of in a kernel (one)
+	const char *blenv = getenv("GSA_BLOCK_LOGIC");
+	const bool dev_logic = !(blenv && strcmp(blenv, "host") == 0);
 	for (int round = 0;; round++) {
 		{ FOverlap f; f.q = cq; f.r = cr; f.l = cl; f.b = cb; f.dn = dc + (round == 0 ? DC_N5 : DC_N6); f.oq = tq; f.orr = tr; f.ol = tl; f.ob = tb; f.dc = dc; f.slot_n = DC_N6A;
 		  if (round > 0) { // every earlier chain has run (the host waited): all chain states are free again
@@ -896,6 +948,55 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 0, DC_NP0, pt0)); // blocks keep their push order; only the ranges moved
 		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 1, DC_NP1, pt1));
 		GSA_TRY(queue_pieces(ctx, ws2, ch, dc, dc + DC_N6, n, cq, cr, cl, cb, gapf, 3, DC_NP2, pt2));
+		if (round == 0 && dev_logic) {
+			// ---- 6-7 on the device: block logic and IdentifyNormalPairs queued blindly, ONE wait for the whole phase ------------------
+			const int nctg = (int)ctx->contig_len.size();
+			BlockHdr *d_vec = ws2.get<BlockHdr>(BLK_DEV_CAP), *d_st1 = nullptr, *d_st2 = nullptr;
+			NpBlock *d_npb = ws2.get<NpBlock>(BLK_DEV_CAP);
+			int64_t *d_fbeg = ws2.get<int64_t>(BLK_DEV_CAP + 1), *d_chr = ws2.get<int64_t>(nctg + 1);
+			int32_t *d_res = ws2.get<int32_t>(BR_COUNT);
+			if (ctx->keep_dumps) { d_st1 = ws2.get<BlockHdr>(BLK_DEV_CAP); d_st2 = ws2.get<BlockHdr>(BLK_DEV_CAP); }
+			if (ws2.rc) return ws2.rc;
+			GSA_TRY(gsa_ensure(ctx, ctx->d_frag, (size_t)(2 * n + 2) * sizeof(gsa_frag)));
+			GSA_TRY(gsa_ensure(ctx, ctx->d_fblk, (size_t)(2 * n + 2) * 4));
+			BlkLogicArgs A;
+			A.pt0 = pt0.d; A.pt1 = pt1.d; A.pt2 = pt2.d; A.kept_score = kept_score; A.dc = dc; A.vec = d_vec; A.npb = d_npb; A.stage1 = d_st1; A.stage2 = d_st2; A.res = d_res;
+			A.P.ce = (const ContigEnd *)ctx->d_cend.p; A.P.nce = (int)ctx->cend.size(); A.P.genome = ctx->N; A.P.min_aln_len = P.min_aln_len;
+			A.P.min_block_score = P.min_block_score; A.P.one_on_one = P.one_on_one; A.P.chr_score = d_chr; A.P.n_contigs = nctg;
+			k_block_logic<<<1, 32, 0, ctx->stream>>>(A);
+			KERNEL_CHECK(ctx);
+			{ FNormalPairs f; f.nb = d_npb; f.nblk = 0; f.d_nblk = d_res + BR_NFINAL; f.q = cq; f.r = cr; f.l = cl; f.frag = (gsa_frag *)ctx->d_frag.p; f.fblk = (int32_t *)ctx->d_fblk.p;
+			  f.blk_frag_beg = d_fbeg; f.dc = dc; GSA_TRY(run_chain(ctx, ch, f, dc + DC_N0, n)); }
+			// what the host needs of it all: counters, outcome, the final block list, where each block's fragments start
+			GSA_TRY(gsa_ensure_host(ctx, ctx->h_stage, 3 * (size_t)BLK_DEV_CAP * sizeof(BlockHdr) + (size_t)(BLK_DEV_CAP + 1) * 8 + 256));
+			int32_t *h_res = (int32_t *)ctx->h_stage.p;
+			BlockHdr *h_vec = (BlockHdr *)((char *)ctx->h_stage.p + 64), *h_st1 = h_vec + BLK_DEV_CAP, *h_st2 = h_st1 + BLK_DEV_CAP;
+			int64_t *h_fb = (int64_t *)(h_st2 + BLK_DEV_CAP);
+			GSA_TRY(gsa_small_d2h(ctx, hc, dc, DC_COUNT * 4));
+			GSA_TRY(gsa_small_d2h(ctx, h_res, d_res, BR_COUNT * 4));
+			GSA_TRY(gsa_small_d2h_counted(ctx, h_vec, d_vec, sizeof(BlockHdr), d_res + BR_NFINAL, BLK_DEV_CAP));
+			GSA_TRY(gsa_small_d2h_counted(ctx, h_fb, d_fbeg, 8, d_res + BR_NFINAL, BLK_DEV_CAP));
+			if (ctx->keep_dumps) {
+				GSA_TRY(gsa_small_d2h_counted(ctx, h_st1, d_st1, sizeof(BlockHdr), d_res + BR_N1, BLK_DEV_CAP));
+				GSA_TRY(gsa_small_d2h_counted(ctx, h_st2, d_st2, sizeof(BlockHdr), d_res + BR_N2, BLK_DEV_CAP));
+			}
+			CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // ---- the one wait of the phase
+			if (hc[DC_KILLS] == 0 && h_res[BR_STATUS] == 0) {
+				ctx->n_cseeds = hc[DC_N6];
+				ctx->split_hazard = h_res[BR_HAZARD];
+				if (ctx->keep_dumps) { ctx->blocks_stage[1].assign(h_st1, h_st1 + h_res[BR_N1]); ctx->blocks_stage[2].assign(h_st2, h_st2 + h_res[BR_N2]); }
+				const int nblk = h_res[BR_NFINAL];
+				const int64_t nfr = hc[DC_NFR];
+				ctx->final_blocks.assign(h_vec, h_vec + nblk);
+				for (int k = 0; k < nblk; k++) {
+					ctx->final_blocks[k].frag_beg = h_fb[k];
+					ctx->final_blocks[k].n_frags = (int32_t)((k + 1 < nblk ? h_fb[k + 1] : nfr) - h_fb[k]);
+				}
+				ctx->n_frags = nblk ? nfr : 0;
+				return GSA_OK;
+			}
+			// otherwise: the host path below, from the piece tables that are still where they were
+		}
 		const int64_t first = std::min<int64_t>(PIECE_FIRST, n + 1);
 		GSA_TRY(gsa_small_d2h(ctx, hc, dc, DC_COUNT * 4));
 		GSA_TRY(gsa_small_d2h_counted(ctx, h_first, pt0.d, sizeof(Piece), dc + DC_NP0, (int)first));
@@ -948,7 +1049,7 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 	GSA_TRY(gsa_small_h2d(ctx, d_npb, ctx->h_stage.p, (size_t)nblk * sizeof(NpBlock)));
 	k_k2_init<<<1, 64, 0, ctx->stream>>>(dc, (int32_t)total); // dc[DC_N0] = element count of the last chain
 	KERNEL_CHECK(ctx);
-	{ FNormalPairs f; f.nb = d_npb; f.nblk = nblk; f.q = cq; f.r = cr; f.l = cl; f.frag = (gsa_frag *)ctx->d_frag.p; f.fblk = (int32_t *)ctx->d_fblk.p; f.blk_frag_beg = d_fbeg; f.dc = dc;
+	{ FNormalPairs f; f.nb = d_npb; f.nblk = nblk; f.d_nblk = nullptr; f.q = cq; f.r = cr; f.l = cl; f.frag = (gsa_frag *)ctx->d_frag.p; f.fblk = (int32_t *)ctx->d_fblk.p; f.blk_frag_beg = d_fbeg; f.dc = dc;
 	  GSA_TRY(run_chain(ctx, ch, f, dc + DC_N0, total)); }
 	int64_t *h_fb = (int64_t *)((char *)ctx->h_stage.p + (size_t)nblk * sizeof(NpBlock) + 8);
 	h_fb = (int64_t *)(((uintptr_t)h_fb + 7) & ~(uintptr_t)7);

@@ -387,10 +387,10 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 //           entry).  From the merge point on the speculative chain IS the true chain, so the lane's speculative seeds
 //           are valid from there on and void before: the merge point goes to merge_from[] and k_seed_keys drops the rest.
 // Results are exactly the serial chain's; every search of the true chain is done once.
-// MB = CTAs per SM the register allocation aims at: 6 (80 registers, no spills) or 8 (64 registers, a few spilled words, a
-// third more warps to keep random sectors in flight); GSA_SEED_OCC picks one.
-template <bool W, int MB>
-__global__ void __launch_bounds__(32 * SEED_WARPS, MB)
+// 80 registers, 6 CTAs per SM.  Squeezing it to 64 registers for 8 CTAs per SM (a third more warps) was measured 4 % SLOWER
+// on a C4 contig (0.90 vs 0.86 ms): the kernel sits at the memory system's random-sector rate, not at a lack of warps.
+template <bool W>
+__global__ void __launch_bounds__(32 * SEED_WARPS, 6)
 k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 {
 	__shared__ uint32_t s_vis[SEED_WARPS][32][SEED_VIS_WORDS];
@@ -541,11 +541,10 @@ int gsa_impl_seed(gsa_ctx *ctx)
 			SeedArgs sa; sa.qpk = (const uint32_t *)ctx->d_qpk.p; sa.qinv = (const uint32_t *)ctx->d_qinv.p; sa.qlen = ctx->qlen; sa.nchunks = nchunks;
 			sa.qpk_words = 2 * ((ctx->qlen >> 5) + 2 + SEED_PAD32); sa.qinv_words = (ctx->qlen >> 5) + 2 + SEED_PAD32;
 			sa.min_seed_len = ctx->prm.min_seed_len; sa.sensitive = ctx->prm.sensitive;
-			static const int occ = [] { const char *e = getenv("GSA_SEED_OCC"); return e && atoi(e) == 8 ? 8 : 6; }();
 			const dim3 grid(gsa_grid(nchunks, SEED_WARPS)), block(32 * SEED_WARPS);
 			uint32_t *mf = (uint32_t *)ctx->d_tmp[7].p;
-			if (ctx->ix.wide) { if (occ == 8) k_seed<true, 8><<<grid, block, 0, ctx->stream>>>(ctx->ix, sa, so, mf); else k_seed<true, 6><<<grid, block, 0, ctx->stream>>>(ctx->ix, sa, so, mf); }
-			else { if (occ == 8) k_seed<false, 8><<<grid, block, 0, ctx->stream>>>(ctx->ix, sa, so, mf); else k_seed<false, 6><<<grid, block, 0, ctx->stream>>>(ctx->ix, sa, so, mf); }
+			if (ctx->ix.wide) k_seed<true><<<grid, block, 0, ctx->stream>>>(ctx->ix, sa, so, mf);
+			else k_seed<false><<<grid, block, 0, ctx->stream>>>(ctx->ix, sa, so, mf);
 			KERNEL_CHECK(ctx);
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
 		}

@@ -288,3 +288,16 @@ def test_compact_record_expansion_host_only():
         bb = C.create_string_buffer(b, len(b))
         out = np.zeros(len(spec), dtype=capi.FRAG_DTYPE)
         assert lib.gsa_record_frags(bb, C.c_int64(len(b)), C.c_int64(0), out.ctypes.data_as(C.c_void_p), C.c_int32(1)) < 0
+
+
+def test_block_logic_array_form_and_sort_restatement(tmp_path):
+    """The block logic also runs in a kernel (block_logic.cuh on plain arrays, with libstdc++'s std::sort restated in
+    stdsort.cuh because the order it leaves ties in is observable).  Compiled for the host, both are pinned here: the sort
+    against std::sort (tie-heavy, sorted, reversed and median-of-three-killer inputs), the split / dedup logic against the
+    std::vector + std::sort form of block_logic.cpp on 3 000 random block lists (duplicates, overlaps, both strands, -one)."""
+    csrc = os.path.join(ROOT, "gsalign_b200", "csrc")
+    exe = str(tmp_path / "blocklogic_harness")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", "-I", csrc, "-I", "/usr/local/cuda/include", "-o", exe,
+                    os.path.join(ROOT, "tests", "blocklogic_harness.cpp"), os.path.join(csrc, "block_logic.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("same"), out.stdout + out.stderr

@@ -36,7 +36,7 @@ strip = lambda l: re.sub(r"\s+/\* 0x[0-9a-f]+ \*/", "", l).rstrip()
 for name, (n, c, f) in keep.items():
     d = dm[name]
     lines = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", l)]
-    if d.startswith("void k_seed<true, 6>"):
+    if d.startswith("void k_seed<true>"):
         idx = [i for i, l in enumerate(lines) if "UBLKCP" in l or "SYNCS" in l]
         out.append("\n## `k_seed<true>`: the chunk's query staged by two bulk copies on the warp's mbarrier\n\n```")
         out += [strip(l) for l in lines[max(0, idx[0] - 3):idx[4] + 2]]
