@@ -387,10 +387,11 @@ __device__ __forceinline__ uint32_t seed_walk_pipe(const DevIndex &ix, const See
 //           entry).  From the merge point on the speculative chain IS the true chain, so the lane's speculative seeds
 //           are valid from there on and void before: the merge point goes to merge_from[] and k_seed_keys drops the rest.
 // Results are exactly the serial chain's; every search of the true chain is done once.
-// 80 registers, 6 CTAs per SM.  Squeezing it to 64 registers for 8 CTAs per SM (a third more warps) was measured 4 % SLOWER
-// on a C4 contig (0.90 vs 0.86 ms): the kernel sits at the memory system's random-sector rate, not at a lack of warps.
+// 80 registers (64-bit rows; 70 with 32-bit rows), 6-7 CTAs per SM.  Squeezing it to 64 registers for 8 CTAs per SM (a third
+// more warps) was measured 4 % SLOWER on a C4 contig (0.90 vs 0.86 ms): the kernel sits at the memory system's
+// random-sector rate, not at a lack of warps.
 template <bool W>
-__global__ void __launch_bounds__(32 * SEED_WARPS, 6)
+__global__ void __launch_bounds__(32 * SEED_WARPS)
 k_seed(DevIndex ix, SeedArgs A, SeedOut out, uint32_t *merge_from)
 {
 	__shared__ uint32_t s_vis[SEED_WARPS][32][SEED_VIS_WORDS];

@@ -76,5 +76,17 @@ for path in sorted(glob.glob("gpurun_out/bench_*.json")):
     txt = open(path).read().strip()
     if txt:
         out.append(f"\n## {os.path.basename(path)}\n\n```json\n{txt}\n```")
+# multi-GPU bench lines (strong scaling over the contig shards) and the A/B experiments of the round, as run
+for path, title in (("gpurun_out/r2p_bench_C4_n2.json", "N = 2, compact records (tools/gpu_r2_p.sh)"), ("gpurun_out/r2m_bench_C4_n4.json", "N = 4, plain records (tools/gpu_r2_m.sh)"),
+                    ("gpurun_out/r2q_bench_C4_n8_compact.json", "N = 8, compact records (tools/gpu_r2_q.sh)"), ("gpurun_out/r2q_bench_C4_n8_plain.json", "N = 8, plain records, same box")):
+    if os.path.exists(path) and open(path).read().strip():
+        out.append(f"\n## multi-GPU: {title}\n\n```json\n{open(path).read().strip()}\n```")
+for path, title in (("gpurun_out/r2h_l2fetch.txt", "K1 vs cudaLimitMaxL2FetchGranularity (tools/gpu_r2_h.sh): no effect"),
+                    ("gpurun_out/r2t_seed_occ.txt", "K1 at 6 vs 8 CTAs per SM (tools/gpu_r2_t.sh): 8 is slower"),
+                    ("gpurun_out/r2s_pcie.txt", "PCIe link of the box, idle and under an HBM-streaming kernel (tools/pcie_probe.py)"),
+                    ("gpurun_out/r2_e2e_experiments.txt", "e2e leg: hardware work queues, bulk copies in pieces, small copies by kernel or DMA, one direction only (calls J, N, L)"),
+                    ("gpurun_out/r2v_c3_cli.txt", "bin/GSAlign at C3 (1 Gbp x 1 Gbp), stages"), ("gpurun_out/r2u_contig.txt", "one C4 contig, phase times: block logic in the kernel (two lines) / on the host (last line)")):
+    if os.path.exists(path):
+        out.append(f"\n## {title}\n\n```\n{open(path).read().strip()}\n```")
 open(f"profiles/{tag}_summary.md", "w").write("\n".join(out) + "\n")
 print("wrote", f"profiles/{tag}_summary.md")
