@@ -94,11 +94,24 @@ __global__ void k_frag_simple(gsa_frag *frag, int64_t nfr, const int32_t *fblk, 
 			alen = (unsigned)f.qLen; sc = (unsigned)(f.qLen - mism[t]); frag[t].aln_off = o; frag[t].aln_len = f.qLen;
 		}
 	}
-	// per-block sums: fragments are in block order, so a warp usually feeds one block -> one atomic pair per warp
+	// per-block sums: fragments are in block order, so a warp usually feeds one block (peers summed in registers), and so does
+	// the whole CTA: the warps' sums for the CTA's first block meet in shared memory and leave as ONE pair of global atomics.
+	// (A collinear contig is one block: every warp of the grid adding to the same two words serialises in the L2.)
+	__shared__ int s_blk;
+	__shared__ unsigned int s_len, s_sc;
+	if (threadIdx.x == 0) { s_blk = -1; s_len = 0; s_sc = 0; }
+	__syncthreads();
+	if (threadIdx.x == 0 && t < nfr) s_blk = fblk[t];
+	__syncthreads();
 	unsigned peers = __match_any_sync(0xffffffffu, b);
 	bool leader;
 	unsigned long long both = gsa_peer_sum(peers, ((unsigned long long)alen << 32) | sc, leader); // a warp adds < 2^32 to either half
-	if (leader && b >= 0) { atomicAdd(bsum + 2 * b, (unsigned)(both >> 32)); atomicAdd(bsum + 2 * b + 1, (unsigned)both); }
+	if (leader && b >= 0) {
+		if (b == s_blk) { atomicAdd(&s_len, (unsigned)(both >> 32)); atomicAdd(&s_sc, (unsigned)both); }
+		else { atomicAdd(bsum + 2 * b, (unsigned)(both >> 32)); atomicAdd(bsum + 2 * b + 1, (unsigned)both); }
+	}
+	__syncthreads();
+	if (threadIdx.x == 0 && s_blk >= 0 && (s_len | s_sc)) { atomicAdd(bsum + 2 * s_blk, s_len); atomicAdd(bsum + 2 * s_blk + 1, s_sc); }
 }
 
 __global__ void k_dp_problems(const int32_t *dp_idx, int64_t ndp, const gsa_frag *frag, const int64_t *row_off, const int64_t *flag_off,
@@ -269,7 +282,7 @@ int gsa_impl_fill(gsa_ctx *ctx, gsa_alignment *out)
 	GSA_TRY(gsa_ensure(ctx, ctx->d_aln1, (size_t)row_bytes + 16));
 	GSA_TRY(gsa_ensure(ctx, ctx->d_aln2, (size_t)row_bytes + 16));
 	char *a1 = (char *)ctx->d_aln1.p, *a2 = (char *)ctx->d_aln2.p;
-	k_frag_simple<<<gsa_grid(nfr, 128), 128, 0, ctx->stream>>>(frag, nfr, fblk, type, mism, row_off, seq, ctx->ix, a1, a2, bsum);
+	k_frag_simple<<<gsa_grid(nfr, 256), 256, 0, ctx->stream>>>(frag, nfr, fblk, type, mism, row_off, seq, ctx->ix, a1, a2, bsum);
 	KERNEL_CHECK(ctx);
 	ctx->tm.n_dp = ndp; ctx->tm.dp_cells = 0;
 	if (ndp > 0) {
