@@ -709,6 +709,7 @@ struct BlkLogicArgs {
 	BlockHdr *vec; NpBlock *npb; BlkParams P;
 	BlockHdr *stage1, *stage2;      // snapshots for the dump hook (may be null)
 	int32_t *res;
+	int cap;                        // blocks the list may hold (<= BLK_DEV_CAP; tests lower it to reach the declining path)
 };
 
 __global__ void k_block_logic(BlkLogicArgs A)
@@ -719,13 +720,13 @@ __global__ void k_block_logic(BlkLogicArgs A)
 	A.dc[DC_N0] = 0;
 	const int np0 = A.dc[DC_NP0], np1 = A.dc[DC_NP1], np2 = A.dc[DC_NP2];
 	if (np0 != A.dc[DC_NB1]) { res[BR_STATUS] = 2; return; }   // RemoveOverlaps must not change the number of blocks
-	if (np0 > BLK_DEV_CAP) { res[BR_STATUS] = 1; return; }
+	if (np0 > A.cap) { res[BR_STATUS] = 1; return; }
 	for (int i = 0; i < np0; i++) A.vec[i] = blk_from_piece(A.pt0[i], A.kept_score[i]); // blocks keep their pre-overlap score
 	res[BR_N1] = np0;
 	if (A.stage1) for (int i = 0; i < np0; i++) A.stage1[i] = A.vec[i];
 	int hz = 0;
-	int n = blk_split(A.P, A.vec, np0, BLK_DEV_CAP, A.pt1, np1, &hz);      // CheckAlnBlockLargeGaps + RemoveBadAlnBlocks
-	if (n >= 0) n = blk_split(A.P, A.vec, n, BLK_DEV_CAP, A.pt2, np2, &hz); // CheckAlnBlockSpanMultiSeqs + RemoveBadAlnBlocks
+	int n = blk_split(A.P, A.vec, np0, A.cap, A.pt1, np1, &hz);      // CheckAlnBlockLargeGaps + RemoveBadAlnBlocks
+	if (n >= 0) n = blk_split(A.P, A.vec, n, A.cap, A.pt2, np2, &hz); // CheckAlnBlockSpanMultiSeqs + RemoveBadAlnBlocks
 	if (n < 0) { res[BR_STATUS] = 1; return; }
 	res[BR_N2] = n; res[BR_HAZARD] = hz;
 	if (A.stage2) for (int i = 0; i < n; i++) A.stage2[i] = A.vec[i];
@@ -960,6 +961,8 @@ int gsa_impl_cluster(gsa_ctx *ctx)
 			GSA_TRY(gsa_ensure(ctx, ctx->d_frag, (size_t)(2 * n + 2) * sizeof(gsa_frag)));
 			GSA_TRY(gsa_ensure(ctx, ctx->d_fblk, (size_t)(2 * n + 2) * 4));
 			BlkLogicArgs A;
+			static const int dev_cap = [] { const char *e = getenv("GSA_BLOCK_DEV_CAP"); int v = e ? atoi(e) : BLK_DEV_CAP; return v < 1 ? 1 : v > BLK_DEV_CAP ? BLK_DEV_CAP : v; }();
+			A.cap = dev_cap;
 			A.pt0 = pt0.d; A.pt1 = pt1.d; A.pt2 = pt2.d; A.kept_score = kept_score; A.dc = dc; A.vec = d_vec; A.npb = d_npb; A.stage1 = d_st1; A.stage2 = d_st2; A.res = d_res;
 			A.P.ce = (const ContigEnd *)ctx->d_cend.p; A.P.nce = (int)ctx->cend.size(); A.P.genome = ctx->N; A.P.min_aln_len = P.min_aln_len;
 			A.P.min_block_score = P.min_block_score; A.P.one_on_one = P.one_on_one; A.P.chr_score = d_chr; A.P.n_contigs = nctg;

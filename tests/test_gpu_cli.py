@@ -311,10 +311,13 @@ def test_repeat_rich_block_logic_device_host_reference(workdir, flags):
     tag = "_".join(f.strip("-") for f in flags) or "default"
     run(OURS, d, ["-t", "4", "-i", "ref", "-q", "qry.fa", "-o", "dev_" + tag] + flags)
     run(OURS, d, ["-t", "4", "-i", "ref", "-q", "qry.fa", "-o", "host_" + tag] + flags, env={"GSA_BLOCK_LOGIC": "host"})
+    # a list of 8 blocks is too small for these contigs: the kernel declines and the host form takes over mid-phase
+    run(OURS, d, ["-t", "4", "-i", "ref", "-q", "qry.fa", "-o", "decl_" + tag] + flags, env={"GSA_BLOCK_DEV_CAP": "8"})
     n_blocks = sum(1 for l in open(os.path.join(d, f"dev_{tag}.maf")) if l.startswith("a score="))
     assert n_blocks >= 60, n_blocks
     for ext in ("maf", "vcf"):
         assert filecmp.cmp(os.path.join(d, f"dev_{tag}.{ext}"), os.path.join(d, f"host_{tag}.{ext}"), shallow=False), ext
+        assert filecmp.cmp(os.path.join(d, f"dev_{tag}.{ext}"), os.path.join(d, f"decl_{tag}.{ext}"), shallow=False), ("declined", ext)
     if not os.path.exists(REF):
         pytest.skip("oracle/_ref/GSAlign not built")
     run(REF, d, ["-t", "1", "-i", "ref", "-q", "qry.fa", "-o", "ref_" + tag] + flags)
