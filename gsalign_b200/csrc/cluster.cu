@@ -11,13 +11,14 @@
 // following the exact restatement of SURVEY.md appendix B.  Everything is expressed as radix sorts
 // (diagonal,qpos) / (group,qpos) and single-pass chained scans whose input and output are functors (scan.cuh: flag or
 // count per seed -> prefix -> scatter / segment id / hash insert in ONE launch) over ALL groups at once, so the one giant
-// main-diagonal group of a collinear contig costs the same as many small ones.  Element counts stay in device memory;
-// the host waits twice per contig (piece tables for its block logic, fragment count):
+// main-diagonal group of a collinear contig costs the same as many small ones.  Element counts stay in device memory and
+// the O(#blocks) logic runs in a kernel too, so the host waits ONCE per contig (final block list + fragment count):
 //   * the greedy outlier windows (data-dependent resets) become "next window start" pointers computed
-//     by binary search per seed and resolved by pointer jumping;
+//     by binary search per seed and resolved by pointer jumping over the candidate list (one cooperative launch);
 //   * the per-window PosDiff histograms become one global (window,bin) hash table with atomic counts;
 //   * overlap trimming, gap / contig-span break points and normal-pair insertion are adjacent-pair maps.
-// Only O(#blocks) headers go to the host (block_logic.cpp) for the reference's float/std::sort logic.
+// The reference's float / std::sort logic over the O(#blocks) headers is block_logic.cuh (k_block_logic); contigs the kernel
+// declines take its host form, block_logic.cpp (two waits).
 #include "fm.cuh"
 #include "scan.cuh"
 #include "block_logic.cuh"
@@ -28,8 +29,8 @@
 // scratch, device counters, chain launches
 // ------------------------------------------------------------------------------------------------
 // Every element count of the phase lives in device memory (dc[]): the kernels of one contig are queued back to back and
-// sized by a host-side upper bound (the seed count), so the host only waits twice -- for the piece tables its block logic
-// needs, and for the fragment count at the end.
+// sized by a host-side upper bound (the seed count), so the host only waits once, for the final block list and the fragment
+// count (twice on the host path of the block logic: piece tables first).
 enum { DC_N0 = 0, DC_NGROUPS, DC_N2, DC_NG2, DC_NC, DC_NLU, DC_N3, DC_N4, DC_NB0, DC_NB1, DC_N5, DC_N6A, DC_N6, DC_KILLS, DC_NCAND,
        DC_NP0, DC_NP1, DC_NP2, DC_NPL0, DC_NFR, DC_NPTOT, DC_COUNT };
 #define K2_CHAINS 24
