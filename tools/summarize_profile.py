@@ -87,6 +87,7 @@ for path, title in (("gpurun_out/r2h_l2fetch.txt", "K1 vs cudaLimitMaxL2FetchGra
                     ("gpurun_out/r2_e2e_experiments.txt", "e2e leg: hardware work queues, bulk copies in pieces, small copies by kernel or DMA, one direction only (calls J, N, L)"),
                     ("gpurun_out/r2y_bg_copies.txt", "ONE device-resident C4 contig, nothing else on the GPU, while unrelated bulk copies keep the PCIe link busy (tools/prof_contig.py --bg)"),
                     ("gpurun_out/r2w_contig.txt", "chained-scan tile size: 1024 elements (committed) vs 2048 (rebuilt on the box): cluster 1.05 vs 1.23 ms; C5 contig in between"),
+                    ("gpurun_out/r2_lanes_sweep.txt", "contigs in flight per GPU (bench.py --lanes), same box, final tree"),
                     ("gpurun_out/r2v_c3_cli.txt", "bin/GSAlign at C3 (1 Gbp x 1 Gbp), stages"), ("gpurun_out/r2u_contig.txt", "one C4 contig, phase times: block logic in the kernel (two lines) / on the host (last line)")):
     if os.path.exists(path):
         out.append(f"\n## {title}\n\n```\n{open(path).read().strip()}\n```")
