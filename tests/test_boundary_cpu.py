@@ -301,3 +301,12 @@ def test_block_logic_array_form_and_sort_restatement(tmp_path):
                     os.path.join(ROOT, "tests", "blocklogic_harness.cpp"), os.path.join(csrc, "block_logic.cpp")], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("same"), out.stdout + out.stderr
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/gsalign_b200.h is the drop-in boundary: it must compile as C99 on its own (no C++ or CUDA types in the signatures)"""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "gsalign_b200.h"\nint main(void) { gsa_variant v; gsa_variant_list l; gsa_alignment a; (void)v; (void)l; (void)a;\n'
+                   '  return (int)sizeof(gsa_frag) - 40 + (int)sizeof(gsa_block) - 24 + (int)sizeof(gsa_variant) - 24; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "hdr"), str(src)], check=True)
+    assert subprocess.run([str(tmp_path / "hdr")]).returncode == 0   # the record sizes the image formats rely on
