@@ -77,8 +77,8 @@ for path in sorted(glob.glob("gpurun_out/bench_*.json")):
     if txt:
         out.append(f"\n## {os.path.basename(path)}\n\n```json\n{txt}\n```")
 # multi-GPU bench lines (strong scaling over the contig shards) and the A/B experiments of the round, as run
-for path, title in (("gpurun_out/r2p_bench_C4_n2.json", "N = 2, compact records (tools/gpu_r2_p.sh)"), ("gpurun_out/r2m_bench_C4_n4.json", "N = 4, plain records (tools/gpu_r2_m.sh)"),
-                    ("gpurun_out/r2q_bench_C4_n8_compact.json", "N = 8, compact records (tools/gpu_r2_q.sh)"), ("gpurun_out/r2q_bench_C4_n8_plain.json", "N = 8, plain records, same box")):
+for path, title in (("gpurun_out/r2m_bench_C4_n4.json", "N = 4, plain records, earlier in the round (tools/gpu_r2_m.sh)"),
+                    ("gpurun_out/r2q_bench_C4_n8_compact.json", "N = 8, compact records, before N4 / 6 lanes (tools/gpu_r2_q.sh)"), ("gpurun_out/r2q_bench_C4_n8_plain.json", "N = 8, plain records, same box as the previous line")):
     if os.path.exists(path) and open(path).read().strip():
         out.append(f"\n## multi-GPU: {title}\n\n```json\n{open(path).read().strip()}\n```")
 for path, title in (("gpurun_out/r2h_l2fetch.txt", "K1 vs cudaLimitMaxL2FetchGranularity (tools/gpu_r2_h.sh): no effect"),
