@@ -310,3 +310,46 @@ def test_header_is_plain_c(tmp_path):
                    '  return (int)sizeof(gsa_frag) - 40 + (int)sizeof(gsa_block) - 24 + (int)sizeof(gsa_variant) - 24; }\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "hdr"), str(src)], check=True)
     assert subprocess.run([str(tmp_path / "hdr")]).returncode == 0   # the record sizes the image formats rely on
+
+
+def test_compact_record_expansion_threads_agree():
+    """a long compact record (60 000 fragments, an anchor every 256 and at every block start): gsa_record_frags spreads the
+    stretches between anchors over host threads; 1 and 4 threads must write the same fragment list, and the list must chain"""
+    import ctypes as C
+    from gsalign_b200 import capi
+    lib = capi.load_library()
+    rng = np.random.default_rng(5)
+    nf = 60_000
+    seed = (np.arange(nf) % 2 == 0).astype(np.uint64)
+    ql = np.where(seed == 1, rng.integers(15, 200, nf), rng.integers(0, 30, nf)).astype(np.uint64)
+    rl = np.where(seed == 1, ql, rng.integers(0, 30, nf)).astype(np.uint64)
+    rl[(seed == 0) & (ql == 0) & (rl == 0)] = 3
+    gp = ((seed == 0) & (ql > 0) & (rl > 0) & (rng.random(nf) < 0.5)).astype(np.uint64)
+    slot = np.where(seed == 1, 0, np.where(gp == 1, ql + rl, np.where(ql == 0, rl, ql))).astype(np.int64)
+    al_ = np.where(seed == 1, ql, np.where(gp == 1, np.maximum(ql, rl), slot)).astype(np.uint64)
+    cfrag = (ql | (rl << np.uint64(21)) | (al_ << np.uint64(42)) | (seed << np.uint64(62)) | (gp << np.uint64(63))).astype(np.uint64)
+    starts = sorted(set(range(0, nf, 256)) | {int(x) for x in rng.integers(1, nf, 40)})     # block starts restart the positions
+    qpos, rpos, row = np.zeros(nf, np.int64), np.zeros(nf, np.int64), np.concatenate([[0], np.cumsum(slot)[:-1]])
+    q = r = 0
+    restart = set(starts) - set(range(0, nf, 256))
+    for i in range(nf):
+        if i in restart:
+            q, r = int(rng.integers(0, 1 << 27)), int(rng.integers(0, 1 << 33))
+        qpos[i], rpos[i] = q, r
+        q += int(ql[i]); r += int(rl[i])
+    anc = b"".join(np.array([i, rpos[i]], dtype=np.int64).tobytes() + np.array([qpos[i], 0], dtype=np.int32).tobytes() + np.array([row[i]], dtype=np.int64).tobytes() for i in starts)
+    ab = int(slot.sum())
+    pad = lambda b: b + b"\0" * (-len(b) % 16)
+    img = (np.array([-1 - 0, 0, nf, ab], dtype=np.int64).tobytes() + np.array([len(starts), 0, 0, 0], dtype=np.int64).tobytes() +
+           pad(cfrag.tobytes()) + anc + pad(b"x" * ab) + pad(b"y" * ab))
+    buf = C.create_string_buffer(img, len(img))
+    outs = []
+    for nt in (1, 4):
+        out = np.zeros(nf, dtype=capi.FRAG_DTYPE)
+        assert lib.gsa_record_frags(buf, C.c_int64(len(img)), C.c_int64(0), out.ctypes.data_as(C.c_void_p), C.c_int32(nt)) == 0
+        outs.append(out)
+    assert outs[0].tobytes() == outs[1].tobytes()
+    got = outs[0]
+    assert np.array_equal(got["qPos"], qpos) and np.array_equal(got["rPos"], rpos) and np.array_equal(got["qLen"], ql.astype(np.int32))
+    gaps = got["bSeed"] == 0
+    assert np.array_equal(got["aln_off"][gaps], (row + np.where(gp == 1, slot - al_.astype(np.int64), 0))[gaps]) and not got["aln_off"][~gaps].any()
