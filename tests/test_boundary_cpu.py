@@ -213,6 +213,41 @@ def test_query_fasta_reader_edge_cases(tmp_path):
     big = b">a\n" + b"ACGT" * 50_000 + b"\n" + b"".join(b">s%d\n%s\n" % (i, b"GATTACA" * (i + 1)) for i in range(40))
     out, _ = run(big)
     assert out[0] == "ok=1 n=41" and out[1].startswith("[a] 200000 ACGTACGT") and out[41] == "[s39] 280 " + "GATTACA" * 40
+    # a file large enough (> 4 MB per slice) for the record-start scan to be cut into slices on several threads: records of
+    # every size, so that slice borders fall inside names, inside sequence lines, on the '>' itself and on the newline before it
+    import hashlib
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)
+    recs, parts = [], []
+    for i in range(700):
+        L = int(rng.integers(0, 120_000)) if i % 50 else int(rng.integers(2_000_000, 5_000_000))
+        seq = acgt[rng.integers(0, len(acgt), size=L)].tobytes()
+        w = int(rng.integers(50, 90))
+        recs.append((f"r{i}", seq))
+        parts.append(b">r%d with > inside the comment\n" % i + b"\n".join(seq[k:k + w] for k in range(0, L, w)) + (b"\n" if L else b""))
+    f = tmp_path / "big.fa"
+    f.write_bytes(b"".join(parts))
+    assert f.stat().st_size > 40_000_000
+    src2 = tmp_path / "ld2.cpp"
+    src2.write_text(_LOADER_HARNESS.replace('printf("[%s] %zu %s\\n", c.name.c_str(), c.seq.size(), c.seq.c_str());',
+                                            '{ unsigned long long h = 1469598103934665603ull; for (char ch : c.seq) h = (h ^ (unsigned char)ch) * 1099511628211ull; printf("[%s] %zu %llx\\n", c.name.c_str(), c.seq.size(), h); }'))
+    exe2 = str(tmp_path / "ld2")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", host, "-o", exe2, str(src2), os.path.join(host, "io.cpp"), "-lpthread"], check=True)
+    got = subprocess.run([exe2, str(f)], capture_output=True, text=True).stdout.splitlines()
+
+    def fnv(b):
+        h = 1469598103934665603
+        for x in np.frombuffer(b, dtype=np.uint8).tolist():
+            h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+    assert got[0] == f"ok=1 n={len(recs)}"
+    for line, (name, seq) in zip(got[1:], recs):
+        nm, ln, hx = line.split()
+        assert nm == f"[{name}]" and int(ln) == len(seq), (line, name, len(seq))
+    # hashing 60 MB byte by byte in Python is slow: check the hash of every 10th record and of the short ones
+    for line, (name, seq) in list(zip(got[1:], recs))[::10]:
+        if len(seq) < 200_000:
+            assert int(line.split()[2], 16) == fnv(seq), name
 
 
 def test_record_walk_host_only():
