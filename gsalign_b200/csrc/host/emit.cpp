@@ -7,6 +7,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <thread>
 #include "host.h"
@@ -19,6 +20,10 @@ static int64_t emit_chunk()
 	return v;
 }
 
+// GSA_TIMING=1: wall clock of the emitters' inner stages on stderr (development aid, silent otherwise)
+static double emit_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool emit_timing() { static const bool on = getenv("GSA_TIMING") != nullptr; return on; }
+
 // runs fn(k) for k in [0, n) on up to `threads` host threads (k = chunk index; the caller splits its range)
 static void parallel_chunks(int n, int threads, const std::function<void(int)> &fn)
 {
@@ -29,13 +34,16 @@ static void parallel_chunks(int n, int threads, const std::function<void(int)> &
 	for (auto &t : th) t.join();
 }
 
-// ---- output files written through a mapping ---------------------------------------------------------------------------
-// The alignment file of a human-size pair is 2 bytes per aligned base (6 GB at 3 Gbp); one thread pushing it through
-// write() is the floor of the whole run.  The file is grown with ftruncate and the new range mapped instead, so that the
-// emitter threads assemble the rows straight into the page cache, all of them at once.
+// ---- output files ---------------------------------------------------------------------------------------------------------
+// The alignment file of a human-size pair is 2 bytes per aligned base (6 GB at 3 Gbp); pushing it into the page cache is the
+// floor of the whole run.  Rows are assembled by all emitter threads in an anonymous buffer that lives as long as the process
+// (faulted in once, 250 MB for a 125 Mbp block) and leave with one pwrite per block.  Assembling straight into a shared
+// mapping of the file was measured too: every 4 KB page of the mapping faults on its own and the faults do not scale with
+// threads -- 2.7-3.3 GB/s whatever the thread count, against 5.9 GB/s for pwrite from memory on the same file system.
 struct MappedOut {
 	int fd = -1; size_t end = 0;               // logical end of the file
-	char *map = nullptr; size_t map_off = 0, map_len = 0;
+	size_t pending = 0;                        // bytes of the buffer not yet written
+	static std::vector<char> &buffer() { static std::vector<char> b; return b; }   // one emitter thread per process
 	bool open_file(const char *path, bool truncate)
 	{
 		fd = open(path, O_RDWR | O_CREAT | (truncate ? O_TRUNC : 0), 0644);
@@ -44,31 +52,29 @@ struct MappedOut {
 		end = fstat(fd, &sb) == 0 ? (size_t)sb.st_size : 0;
 		return true;
 	}
-	// appends n bytes to the file and returns where to write them (valid until the next reserve / close)
+	// writes [p, p + n) at the end of the file
+	bool append(const char *p, size_t n)
+	{
+		while (n > 0) {
+			ssize_t w = pwrite(fd, p, n, (off_t)end);
+			if (w <= 0) return false;
+			p += w; n -= (size_t)w; end += (size_t)w;
+		}
+		return true;
+	}
+	// room for n bytes that will be appended to the file by the next reserve / close (valid until then)
 	char *reserve(size_t n)
 	{
 		release();
 		if (n == 0) return nullptr;
-		const size_t page = 4096, lo = end & ~(page - 1);
-		if (ftruncate(fd, (off_t)(end + n)) != 0) return nullptr;
-		void *m = mmap(nullptr, end + n - lo, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)lo);
-		if (m == MAP_FAILED) return nullptr;
-		map = (char *)m; map_off = lo; map_len = end + n - lo;
-		char *p = map + (end - lo);
-		end += n;
-		return p;
+		std::vector<char> &b = buffer();
+		if (b.size() < n) { std::vector<char>().swap(b); b.resize(n + n / 4); }   // contents are dead: no copy on growth
+		pending = n;
+		return b.data();
 	}
-	void release() { if (map) { munmap(map, map_len); map = nullptr; } }
+	void release() { if (pending) { append(buffer().data(), pending); pending = 0; } }
 	void close_file() { release(); if (fd >= 0) { close(fd); fd = -1; } }
 };
-
-// copies [src, src + n) to dst on up to `threads` threads
-static void parallel_copy(char *dst, const char *src, size_t n, int threads)
-{
-	const size_t piece = (size_t)8 << 20;
-	int nch = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / piece));
-	parallel_chunks(nch, threads, [&](int k) { size_t a = n * (size_t)k / (size_t)nch, b = n * (size_t)(k + 1) / (size_t)nch; memcpy(dst + a, src + a, b - a); });
-}
 
 // ---- std::sort, bit for bit, on several threads ---------------------------------------------------------------------------
 // The order of records with equal keys in the reference's output is whatever libstdc++'s introsort makes of the input order
@@ -358,8 +364,8 @@ void output_maf(const Options &o, const HostIndex &ix, const std::vector<QueryCh
 			txt += num; row(a2);
 		}
 		txt += "\n\n";
-		char *p = out.reserve(txt.size());
-		if (p) parallel_copy(p, txt.data(), txt.size(), o.threads);
+		out.release();
+		out.append(txt.data(), txt.size());
 	}
 	out.close_file();
 }
@@ -557,9 +563,13 @@ void output_variants(const Options &o, const HostIndex &ix, EmitState &st)
 {
 	static const char *MutType[3] = {"SUBSTITUTE", "INSERT", "DELETE"};
 	if (st.variants.size() >= 0xFFFFFFFFull) { fprintf(stderr, "too many variants for this build\n"); return; }
+	const double t_a = emit_now();
 	std::vector<VarKey> keys(st.variants.size());
 	for (size_t i = 0; i < keys.size(); i++) { keys[i].key = ((uint64_t)(uint32_t)st.variants[i].chr_idx << 32) | (uint32_t)st.variants[i].pos; keys[i].idx = (uint32_t)i; }
+	const double t_b = emit_now();
 	sort_like_std(keys.begin(), keys.end(), by_variant_pos, st.threads); // std::sort's own moves, its recursive calls on threads
+	const double t_c = emit_now();
+	double t_fmt = 0, t_wr = 0;
 	st.iSNV = st.iInsertion = st.iDeletion = 0;
 	MappedOut out;
 	if (!out.open_file(o.vcf_name.c_str(), true)) return;
@@ -572,34 +582,53 @@ void output_variants(const Options &o, const HostIndex &ix, EmitState &st)
 		hdr += "#CHROM	POS	ID	REF	ALT	QUAL	FILTER	INFO\n";
 		put_bytes(out, hdr.data(), hdr.size());
 	}
-	// records are formatted into per-thread buffers, a batch at a time, and copied to their place in the mapped file by the
-	// same threads.  "%s" of an allele stops at a NUL, which an allele cannot hold (query letters are alphabetic, reference
-	// letters ACGT), so lengths can be used as they are.
+	// Records are formatted straight into the process-wide output buffer (already resident after the alignment file), a
+	// round of batches at a time: every thread first adds up the bytes of its batch, the batches' offsets follow, then every
+	// thread writes its lines where they belong and the round leaves with one pwrite.  "%s" of an allele stops at a NUL, which
+	// an allele cannot hold (query letters are alphabetic, reference letters ACGT), so lengths can be used as they are.
+	static const size_t MutLen[3] = {10, 6, 6};
 	const size_t batch = (size_t)emit_chunk() * 16;
 	const int nth = std::max(1, st.threads);
-	std::vector<std::string> buf((size_t)nth);
+	std::vector<size_t> name_len(ix.names.size());
+	for (size_t i = 0; i < ix.names.size(); i++) name_len[i] = ix.names[i].size();
 	for (size_t b0 = 0; b0 < keys.size(); b0 += batch * (size_t)nth) {
 		const int nch = (int)std::min<size_t>((size_t)nth, (keys.size() - b0 + batch - 1) / batch);
+		const double t_d = emit_now();
+		std::vector<size_t> at((size_t)nch + 1, 0);
 		parallel_chunks(nch, nth, [&](int k) {
-			std::string &s = buf[(size_t)k];
-			s.clear();
 			const size_t lo = b0 + (size_t)k * batch, hi = std::min(keys.size(), lo + batch);
-			char num[16];
+			size_t n = 0;
 			for (size_t i = lo; i < hi; i++) {
 				const Variant &v = st.variants[keys[i].idx];
-				s += ix.names[(size_t)v.chr_idx]; s += '\t';
-				s.append(num, (size_t)(put_int(num, v.pos) - num));
-				s += "\t.\t";
-				s.append(st.alleles, (size_t)v.off, v.ref_len); s += '\t';
-				s.append(st.alleles, (size_t)(v.off + v.ref_len), v.alt_len);
-				s += "\t100\t*\tTYPE="; s += MutType[v.type]; s += '\n';
+				unsigned u = v.pos < 0 ? 0u - (unsigned)v.pos : (unsigned)v.pos;
+				size_t digits = 1; while (u >= 10) { u /= 10; digits++; }
+				// name \t pos \t . \t ref \t alt \t 100 \t * \t TYPE= type \n
+				n += name_len[(size_t)v.chr_idx] + 1 + digits + (v.pos < 0) + 3 + v.ref_len + 1 + v.alt_len + 12 + MutLen[v.type] + 1;
+			}
+			at[(size_t)k + 1] = n;
+		});
+		for (int k = 0; k < nch; k++) at[(size_t)k + 1] += at[(size_t)k];
+		char *base = out.reserve(at[(size_t)nch]);
+		if (!base && at[(size_t)nch]) break;
+		parallel_chunks(nch, nth, [&](int k) {
+			const size_t lo = b0 + (size_t)k * batch, hi = std::min(keys.size(), lo + batch);
+			char *p = base + at[(size_t)k];
+			for (size_t i = lo; i < hi; i++) {
+				const Variant &v = st.variants[keys[i].idx];
+				const std::string &nm = ix.names[(size_t)v.chr_idx];
+				memcpy(p, nm.data(), nm.size()); p += nm.size(); *p++ = '\t';
+				p = put_int(p, v.pos);
+				memcpy(p, "\t.\t", 3); p += 3;
+				memcpy(p, st.alleles.data() + v.off, v.ref_len); p += v.ref_len; *p++ = '\t';
+				memcpy(p, st.alleles.data() + v.off + v.ref_len, v.alt_len); p += v.alt_len;
+				memcpy(p, "\t100\t*\tTYPE=", 12); p += 12;
+				memcpy(p, MutType[v.type], MutLen[v.type]); p += MutLen[v.type]; *p++ = '\n';
 			}
 		});
-		std::vector<size_t> at((size_t)nch + 1, 0);
-		for (int k = 0; k < nch; k++) at[(size_t)k + 1] = at[(size_t)k] + buf[(size_t)k].size();
-		char *p = out.reserve(at[(size_t)nch]);
-		if (!p) break;
-		parallel_chunks(nch, nth, [&](int k) { memcpy(p + at[(size_t)k], buf[(size_t)k].data(), buf[(size_t)k].size()); });
+		const double t_e = emit_now();
+		out.release();
+		t_fmt += t_e - t_d; t_wr += emit_now() - t_e;
 	}
 	out.close_file();
+	if (emit_timing()) fprintf(stderr, "[timing] variants: keys %.3f s, sort %.3f s, format %.3f s, write %.3f s (%zu records)\n", t_b - t_a, t_c - t_b, t_fmt, t_wr, keys.size());
 }
