@@ -8,7 +8,11 @@
 #include <unistd.h>
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <thread>
 #include "host.h"
 
@@ -36,44 +40,128 @@ static void parallel_chunks(int n, int threads, const std::function<void(int)> &
 
 // ---- output files ---------------------------------------------------------------------------------------------------------
 // The alignment file of a human-size pair is 2 bytes per aligned base (6 GB at 3 Gbp); pushing it into the page cache is the
-// floor of the whole run.  Rows are assembled by all emitter threads in an anonymous buffer that lives as long as the process
-// (faulted in once, 250 MB for a 125 Mbp block) and leave with one pwrite per block.  Assembling straight into a shared
-// mapping of the file was measured too: every 4 KB page of the mapping faults on its own and the faults do not scale with
-// threads -- 2.7-3.3 GB/s whatever the thread count, against 5.9 GB/s for pwrite from memory on the same file system.
-struct MappedOut {
-	int fd = -1; size_t end = 0;               // logical end of the file
-	size_t pending = 0;                        // bytes of the buffer not yet written
-	static std::vector<char> &buffer() { static std::vector<char> b; return b; }   // one emitter thread per process
-	bool open_file(const char *path, bool truncate)
+// floor of the whole run.  Rows are assembled by all emitter threads in one of two anonymous buffers that live as long as the
+// process (250 MB for a 125 Mbp block, first touched by the assembling threads themselves) and leave with one pwrite per
+// buffer on a writer thread, so that the next block is assembled while the previous one is on its way into the page cache.
+// Assembling straight into a shared mapping of the file was measured too: every 4 KB page of the mapping faults on its own
+// and the faults do not scale with threads -- 2.7-3.3 GB/s whatever the thread count, against 5.9 GB/s for pwrite from memory
+// on the same file system.
+class OutWriter {
+public:
+	static const int SLOTS = 2;
+	static OutWriter &get() { static OutWriter w; return w; }
+	// a buffer of at least n bytes that no write is reading (waits for one); its contents are dead
+	int acquire(size_t n)
 	{
-		fd = open(path, O_RDWR | O_CREAT | (truncate ? O_TRUNC : 0), 0644);
+		std::unique_lock<std::mutex> lk(mu);
+		cv.wait(lk, [&] { for (int i = 0; i < SLOTS; i++) if (!busy[i]) return true; return false; });
+		int s = -1;
+		for (int i = 0; i < SLOTS; i++) if (!busy[i] && (s < 0 || (cap[s] < n && cap[i] > cap[s]))) s = i;
+		busy[s] = true;
+		lk.unlock();
+		if (cap[s] < n) {
+			if (mem[s]) munmap(mem[s], cap[s]);
+			const size_t want = (n + n / 4 + 4095) & ~(size_t)4095;
+			void *m = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+			if (m == MAP_FAILED) { mem[s] = nullptr; cap[s] = 0; lk.lock(); busy[s] = false; failed = true; cv.notify_all(); return -1; }
+			madvise(m, want, MADV_HUGEPAGE);
+			mem[s] = (char *)m; cap[s] = want;
+		}
+		return s;
+	}
+	char *data(int s) const { return mem[s]; }
+	size_t capacity(int s) const { return cap[s]; }
+	// queues the first n bytes of buffer s for offset `off` of the file behind fd (the job keeps its own descriptor)
+	void submit(int fd, int s, size_t n, size_t off)
+	{
+		Job j; j.fd = n ? dup(fd) : -1; j.slot = s; j.n = n; j.off = off;
+		std::unique_lock<std::mutex> lk(mu);
+		if (n && j.fd < 0) failed = true;
+		if (!started) { started = true; worker = std::thread([this] { run(); }); }
+		jobs.push_back(j);
+		cv.notify_all();
+	}
+	// every queued byte is in the page cache; false if any write failed since the process started
+	bool drain()
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		cv.wait(lk, [&] { return jobs.empty() && !active; });
+		return !failed;
+	}
+	// logical end of an output file this process has been writing (writes may still be queued); -1 = not known
+	long long known_end(const std::string &path) { std::unique_lock<std::mutex> lk(mu); auto it = ends.find(path); return it == ends.end() ? -1 : (long long)it->second; }
+	void set_end(const std::string &path, size_t end) { std::unique_lock<std::mutex> lk(mu); ends[path] = end; }
+	~OutWriter()
+	{
+		{ std::unique_lock<std::mutex> lk(mu); quit = true; cv.notify_all(); }
+		if (worker.joinable()) worker.join();
+	}
+private:
+	struct Job { int fd, slot; size_t n, off; };
+	std::mutex mu; std::condition_variable cv;
+	std::deque<Job> jobs;
+	std::map<std::string, size_t> ends;
+	std::thread worker;
+	char *mem[SLOTS] = {nullptr, nullptr}; size_t cap[SLOTS] = {0, 0}; bool busy[SLOTS] = {false, false};
+	bool started = false, quit = false, active = false, failed = false;
+	void run()
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		for (;;) {
+			cv.wait(lk, [&] { return quit || !jobs.empty(); });
+			if (jobs.empty()) return;   // quit, and nothing left to write
+			Job j = jobs.front(); jobs.pop_front();
+			active = true;
+			lk.unlock();
+			bool ok = true;
+			const char *p = mem[j.slot];
+			for (size_t left = j.n, off = j.off; left > 0;) {
+				ssize_t w = pwrite(j.fd, p, left, (off_t)off);
+				if (w <= 0) { ok = false; break; }
+				p += w; left -= (size_t)w; off += (size_t)w;
+			}
+			if (j.fd >= 0) close(j.fd);
+			lk.lock();
+			if (!ok) failed = true;
+			busy[j.slot] = false; active = false;
+			cv.notify_all();
+		}
+	}
+};
+
+bool emit_drain() { return OutWriter::get().drain(); }
+
+// An output file that grows at its end.  reserve() hands out room in the current buffer (small pieces share one buffer and one
+// write); a full buffer, and the last one at close, go to the writer thread.
+struct MappedOut {
+	int fd = -1; size_t end = 0;               // logical end of the file (bytes handed to the writer included)
+	int slot = -1; size_t fill = 0;            // current buffer and the bytes of it in use
+	std::string path;
+	bool open_file(const char *name, bool truncate)
+	{
+		OutWriter &w = OutWriter::get();
+		path = name;
+		long long known = truncate ? -1 : w.known_end(path);
+		if (known < 0) w.drain();               // nothing of an earlier writer may land after a truncation / before the size is read
+		fd = open(name, O_RDWR | O_CREAT | (truncate ? O_TRUNC : 0), 0644);
 		if (fd < 0) return false;
 		struct stat sb;
-		end = fstat(fd, &sb) == 0 ? (size_t)sb.st_size : 0;
+		end = known >= 0 ? (size_t)known : (fstat(fd, &sb) == 0 ? (size_t)sb.st_size : 0);
 		return true;
 	}
-	// writes [p, p + n) at the end of the file
-	bool append(const char *p, size_t n)
-	{
-		while (n > 0) {
-			ssize_t w = pwrite(fd, p, n, (off_t)end);
-			if (w <= 0) return false;
-			p += w; n -= (size_t)w; end += (size_t)w;
-		}
-		return true;
-	}
-	// room for n bytes that will be appended to the file by the next reserve / close (valid until then)
+	// room for n bytes at the end of the file (valid until the next reserve / close)
 	char *reserve(size_t n)
 	{
-		release();
 		if (n == 0) return nullptr;
-		std::vector<char> &b = buffer();
-		if (b.size() < n) { std::vector<char>().swap(b); b.resize(n + n / 4); }   // contents are dead: no copy on growth
-		pending = n;
-		return b.data();
+		OutWriter &w = OutWriter::get();
+		if (slot >= 0 && fill + n > w.capacity(slot)) release();
+		if (slot < 0) { slot = w.acquire(std::max<size_t>(n, (size_t)8 << 20)); fill = 0; if (slot < 0) return nullptr; }
+		char *p = w.data(slot) + fill;
+		fill += n;
+		return p;
 	}
-	void release() { if (pending) { append(buffer().data(), pending); pending = 0; } }
-	void close_file() { release(); if (fd >= 0) { close(fd); fd = -1; } }
+	void release() { if (slot >= 0) { OutWriter::get().submit(fd, slot, fill, end); end += fill; slot = -1; fill = 0; } }
+	void close_file() { release(); if (fd >= 0) { OutWriter::get().set_end(path, end); close(fd); fd = -1; } }
 };
 
 // ---- std::sort, bit for bit, on several threads ---------------------------------------------------------------------------
@@ -364,8 +452,7 @@ void output_maf(const Options &o, const HostIndex &ix, const std::vector<QueryCh
 			txt += num; row(a2);
 		}
 		txt += "\n\n";
-		out.release();
-		out.append(txt.data(), txt.size());
+		put_bytes(out, txt.data(), txt.size());
 	}
 	out.close_file();
 }

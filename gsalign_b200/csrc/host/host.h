@@ -93,3 +93,6 @@ void output_maf(const Options &o, const HostIndex &ix, const std::vector<QueryCh
 void output_aln(const Options &o, const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, ContigResult &r);
 void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, const ContigResult &r, EmitState &st); // src/SeqVariant.cpp:12-119
 void output_variants(const Options &o, const HostIndex &ix, EmitState &st);                                                      // src/SeqVariant.cpp:121-143
+// The MAF and VCF writers hand their buffers to a writer thread: this waits until every byte is in the page cache (false if a
+// write failed).  Static destruction does the same; a process that leaves through _exit() must call it first.
+bool emit_drain();

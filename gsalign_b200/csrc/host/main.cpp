@@ -316,6 +316,7 @@ int main(int argc, char *argv[])
 	tick("align + emit");
 	if (failed) { // a device or limit failure mid-run: no partial files are left behind and the exit code says so (the reference's
 		// always-0 convention covers usage errors, not an aborted run)
+		emit_drain();
 		if (!o.maf.empty()) remove(o.maf.c_str());
 		if (!o.aln.empty()) remove(o.aln.c_str());
 		fflush(NULL);
@@ -329,6 +330,7 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "\nGSAlign identifies %d SNVs, %d insertions, and %d deletions [%s].\n\n", st.iSNV, st.iInsertion, st.iDeletion, o.vcf_name.c_str());
 		output_variants(o, ix, st);
 	}
+	if (!emit_drain()) { fprintf(stderr, "FatalError: cannot write the output files\n"); fflush(NULL); _exit(1); }
 	tick("variants written");
 	// the process ends here: files are closed, device and pinned memory go back with the process (tearing contexts down one
 	// buffer at a time costs more than the whole alignment of a small genome)
