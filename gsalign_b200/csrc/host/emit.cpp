@@ -171,19 +171,87 @@ struct MappedOut {
 // Running the recursive call on another thread changes no comparison and no move: same partition pivots
 // (std::__unguarded_partition_pivot), same depth limit and heap-sort fallback (std::__partial_sort), same final insertion
 // sort, all libstdc++'s own.
+//
+// The partition itself runs on threads too where the range is long (the first levels would otherwise be one thread walking
+// tens of millions of records).  std::__unguarded_partition(lo, hi, pivot) swaps the k-th element from the left that is not
+// below the pivot (a "left stopper", i_k) with the k-th from the right that is not above it (j_k) for as long as i_k < j_k,
+// and returns where its left scan stops after the last swap: min(i_K, j_{K-1}) -- the scan may run into the element the last
+// swap brought there.  With L(x) = left stoppers in [lo, x) and R(x) = right stoppers in [x, hi) of the ORIGINAL range that
+// position is the largest x with L(x) <= R(x), and K = L(x).  So: count both kinds per chunk, find x from the chunk sums and
+// one short scan, list the K left stoppers below x and the K rightmost right stoppers, swap them pairwise.  Same swaps, same
+// return value, no other moves.
+static size_t sort_par_min()
+{
+	static const size_t v = [] { const char *e = getenv("GSA_SORT_PAR_MIN"); long long x = e ? atoll(e) : 0; return x > 0 ? (size_t)x : (size_t)1 << 20; }();
+	return v;
+}
+
 template <typename It, typename Cmp>
-static void introsort_loop_threads(It first, It last, long depth_limit, Cmp comp, int spawn_levels)
+static It partition_threads(It lo, It hi, It pivot, Cmp comp, int threads)
+{
+	const size_t n = (size_t)(hi - lo);
+	const int nch = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / 16));
+	auto chunk_at = [&](int c) { return n * (size_t)c / (size_t)nch; };
+	std::vector<size_t> lsum((size_t)nch + 1, 0), rsum((size_t)nch + 1, 0);   // lsum[c]: left stoppers before chunk c; rsum[c]: right stoppers from chunk c on
+	parallel_chunks(nch, threads, [&](int c) {
+		size_t l = 0, r = 0;
+		for (It p = lo + (ptrdiff_t)chunk_at(c), e = lo + (ptrdiff_t)chunk_at(c + 1); p != e; ++p) { l += !comp(p, pivot); r += !comp(pivot, p); }
+		lsum[(size_t)c + 1] = l; rsum[(size_t)c] = r;
+	});
+	for (int c = 0; c < nch; c++) lsum[(size_t)c + 1] += lsum[(size_t)c];
+	for (int c = nch - 1; c >= 0; c--) rsum[(size_t)c] += rsum[(size_t)c + 1];
+	int cc = 0;                                            // the last chunk whose start still has L <= R
+	while (cc + 1 < nch && lsum[(size_t)cc + 1] <= rsum[(size_t)cc + 1]) cc++;
+	size_t cut = chunk_at(cc), L = lsum[(size_t)cc], R = rsum[(size_t)cc];
+	for (const size_t e = chunk_at(cc + 1); cut < e; cut++) {
+		It p = lo + (ptrdiff_t)cut;
+		const size_t l2 = L + !comp(p, pivot), r2 = R - !comp(pivot, p);
+		if (l2 > r2) break;
+		L = l2; R = r2;
+	}
+	const size_t K = L;
+	if (K == 0) return lo + (ptrdiff_t)cut;
+	std::vector<uint32_t> I(K), J(K);
+	parallel_chunks(nch, threads, [&](int c) {
+		const size_t a = chunk_at(c), b = chunk_at(c + 1);
+		if (a < cut) { // left stoppers of [a, min(b, cut)) in ascending order
+			size_t k = lsum[(size_t)c];
+			for (size_t x = a, e = std::min(b, cut); x < e; x++) if (!comp(lo + (ptrdiff_t)x, pivot)) I[k++] = (uint32_t)x;
+		}
+		if (b > cut) { // right stoppers of [max(a, cut), b) in descending order; only the K rightmost of the range take part
+			size_t k = rsum[(size_t)c + 1];
+			for (size_t x = b, e = std::max(a, cut); x > e && k < K; x--) if (!comp(pivot, lo + (ptrdiff_t)(x - 1))) J[k++] = (uint32_t)(x - 1);
+		}
+	});
+	const int sch = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, K / 4096));
+	parallel_chunks(sch, threads, [&](int c) {
+		for (size_t k = K * (size_t)c / (size_t)sch, e = K * (size_t)(c + 1) / (size_t)sch; k < e; k++) std::iter_swap(lo + (ptrdiff_t)I[k], lo + (ptrdiff_t)J[k]);
+	});
+	return lo + (ptrdiff_t)cut;
+}
+
+// `threads` = the host threads this call may keep busy: long ranges are partitioned by all of them, then the budget is split
+// between the two parts by their sizes
+template <typename It, typename Cmp>
+static void introsort_loop_threads(It first, It last, long depth_limit, Cmp comp, int threads)
 {
 	std::vector<std::thread> kids;
 	while (last - first > 16) { // _S_threshold
 		if (depth_limit == 0) { std::__partial_sort(first, last, last, comp); break; }
 		--depth_limit;
-		It cut = std::__unguarded_partition_pivot(first, last, comp);
-		if (spawn_levels > 0 && last - cut > (1 << 15)) {
-			--spawn_levels;
-			const long d = depth_limit; const int sl = spawn_levels;
-			kids.emplace_back([cut, last, d, comp, sl] { introsort_loop_threads(cut, last, d, comp, sl); });
-		} else introsort_loop_threads(cut, last, depth_limit, comp, 0);
+		const size_t n = (size_t)(last - first);
+		It cut;
+		if (threads > 1 && n >= sort_par_min() && n < 0xFFFFFFFFull) { // std::__unguarded_partition_pivot, its partition on threads
+			std::__move_median_to_first(first, first + 1, first + (last - first) / 2, last - 1, comp);
+			cut = partition_threads(first + 1, last, first, comp, threads);
+		} else cut = std::__unguarded_partition_pivot(first, last, comp);
+		if (threads > 1 && last - cut > 4096) {
+			int tr = (int)((double)threads * (double)(last - cut) / (double)n + 0.5);
+			tr = std::max(1, std::min(threads - 1, tr));
+			const long d = depth_limit;
+			kids.emplace_back([cut, last, d, comp, tr] { introsort_loop_threads(cut, last, d, comp, tr); });
+			threads -= tr;
+		} else introsort_loop_threads(cut, last, depth_limit, comp, 1);
 		last = cut;
 	}
 	for (auto &t : kids) t.join();
@@ -194,9 +262,9 @@ static void sort_like_std(It first, It last, Compare comp, int threads)
 {
 	if (first == last) return;
 	auto c = __gnu_cxx::__ops::__iter_comp_iter(comp);
-	int levels = 0;
-	while ((1 << levels) < threads) levels++;
-	introsort_loop_threads(first, last, (long)std::__lg(last - first) * 2, c, threads > 1 ? levels + 2 : 0);
+	// twice the thread count as the budget: the parts of a partition are rarely even, and a thread whose part is done early
+	// has nothing else to take
+	introsort_loop_threads(first, last, (long)std::__lg(last - first) * 2, c, threads > 1 ? threads * 2 : 1);
 	std::__final_insertion_sort(first, last, c);
 }
 
@@ -651,8 +719,25 @@ void output_variants(const Options &o, const HostIndex &ix, EmitState &st)
 	static const char *MutType[3] = {"SUBSTITUTE", "INSERT", "DELETE"};
 	if (st.variants.size() >= 0xFFFFFFFFull) { fprintf(stderr, "too many variants for this build\n"); return; }
 	const double t_a = emit_now();
-	std::vector<VarKey> keys(st.variants.size());
-	for (size_t i = 0; i < keys.size(); i++) { keys[i].key = ((uint64_t)(uint32_t)st.variants[i].chr_idx << 32) | (uint32_t)st.variants[i].pos; keys[i].idx = (uint32_t)i; }
+	// the key array is first touched by the threads that fill it (half a gigabyte for a human-size pair)
+	struct KeyArray {
+		VarKey *p; size_t n;
+		explicit KeyArray(size_t n_) : p((VarKey *)malloc(std::max<size_t>(1, n_) * sizeof(VarKey))), n(n_) {}
+		~KeyArray() { free(p); }
+		size_t size() const { return n; }
+		VarKey *begin() const { return p; }
+		VarKey *end() const { return p + n; }
+		VarKey &operator[](size_t i) const { return p[i]; }
+	} keys(st.variants.size());
+	if (!keys.p) { fprintf(stderr, "out of memory while sorting the variants\n"); return; }
+	{
+		const int nch = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, st.threads), keys.size() / 65536));
+		parallel_chunks(nch, st.threads, [&](int k) {
+			for (size_t i = keys.size() * (size_t)k / (size_t)nch, e = keys.size() * (size_t)(k + 1) / (size_t)nch; i < e; i++) {
+				keys[i].key = ((uint64_t)(uint32_t)st.variants[i].chr_idx << 32) | (uint32_t)st.variants[i].pos; keys[i].idx = (uint32_t)i;
+			}
+		});
+	}
 	const double t_b = emit_now();
 	sort_like_std(keys.begin(), keys.end(), by_variant_pos, st.threads); // std::sort's own moves, its recursive calls on threads
 	const double t_c = emit_now();

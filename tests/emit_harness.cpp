@@ -12,9 +12,10 @@ template <typename T> static bool rd(FILE *f, T *p, size_t n) { return n == 0 ||
 
 void gsa_test_sort_keys(uint64_t *keys, uint32_t *idx, size_t n, int threads); // emit.cpp
 
-// emit_harness sort <n> <distinct keys> <threads> <seed>: the emitters' threaded sort against std::sort on the same
-// (key, index) records -- the order of equal keys must come out the same (hazard H5)
-static int sort_mode(char **argv)
+// emit_harness sort <n> <distinct keys> <threads> <seed> [pattern]: the emitters' threaded sort against std::sort on the same
+// (key, index) records -- the order of equal keys must come out the same (hazard H5).  pattern 0: random keys; 1: ascending
+// runs with repeated neighbours (what VariantIdentification pushes: one sorted stretch per block); 2: descending; 3: sorted
+static int sort_mode(char **argv, int pattern)
 {
 	size_t n = (size_t)atoll(argv[2]); uint64_t distinct = (uint64_t)atoll(argv[3]); int threads = atoi(argv[4]);
 	uint64_t x = (uint64_t)atoll(argv[5]) * 0x9E3779B97F4A7C15ull + 1;
@@ -25,6 +26,18 @@ static int sort_mode(char **argv)
 		x ^= x << 13; x ^= x >> 7; x ^= x << 17;
 		keys[i] = want[i].key = x % distinct; idx[i] = want[i].idx = (uint32_t)i;
 	}
+	if (pattern == 1) { // runs: a new run starts with probability 1/50000, inside a run the key grows by 0 (1 in 16) or a small step
+		uint64_t k = 0;
+		for (size_t i = 0; i < n; i++) {
+			const uint64_t r = keys[i] ^ (keys[i] >> 29);
+			if (i == 0 || r % 50000 == 0) k = r % distinct; else k += (r >> 20) % 16 == 0 ? 0 : 1 + (r >> 24) % 200;
+			keys[i] = want[i].key = k;
+		}
+	} else if (pattern == 2 || pattern == 3) {
+		std::sort(keys.begin(), keys.end());
+		if (pattern == 2) std::reverse(keys.begin(), keys.end());
+		for (size_t i = 0; i < n; i++) want[i].key = keys[i];
+	}
 	std::sort(want.begin(), want.end(), [](const K &a, const K &b) { return a.key < b.key; });
 	gsa_test_sort_keys(keys.data(), idx.data(), n, threads);
 	for (size_t i = 0; i < n; i++) if (keys[i] != want[i].key || idx[i] != want[i].idx) { printf("differs at %zu\n", i); return 1; }
@@ -34,7 +47,7 @@ static int sort_mode(char **argv)
 
 int main(int argc, char **argv)
 {
-	if (argc == 6 && std::string(argv[1]) == "sort") return sort_mode(argv);
+	if ((argc == 6 || argc == 7) && std::string(argv[1]) == "sort") return sort_mode(argv, argc == 7 ? atoi(argv[6]) : 0);
 	if (argc != 7) return 2;
 	Options o;
 	o.index_prefix = argv[1]; o.query = argv[2];

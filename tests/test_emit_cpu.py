@@ -84,3 +84,17 @@ def test_threaded_sort_moves_like_std_sort(harness, n, distinct, threads):
     threaded sort must produce std::sort's exact permutation, ties included."""
     out = subprocess.run([harness, "sort", str(n), str(distinct), str(threads), "7"], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "same", out.stdout
+
+
+@pytest.mark.parametrize("pattern", [0, 1, 2, 3])
+@pytest.mark.parametrize("par_min", [64, 5000, 200_000])
+@pytest.mark.parametrize("n,distinct,threads", [(100_000, 50, 8), (700_000, 30_000, 5), (1_500_000, 100_000_000, 16), (5000, 5, 3)])
+def test_threaded_partition_swaps_like_std_sort(harness, n, distinct, threads, par_min, pattern):
+    """Long ranges are partitioned by several threads (partition_threads: stoppers counted per chunk, the cut found from the
+    sums, the same pairs swapped).  GSA_SORT_PAR_MIN lowers the range length from which that happens so that every level of
+    a small sort goes through it; the inputs are random keys, ascending runs with repeated neighbours (the shape
+    VariantIdentification pushes), descending and sorted keys.  The permutation must be std::sort's."""
+    env = dict(os.environ, GSA_SORT_PAR_MIN=str(par_min))
+    for seed in (1, 2):
+        out = subprocess.run([harness, "sort", str(n), str(distinct), str(threads), str(seed), str(pattern)], capture_output=True, text=True, env=env)
+        assert out.returncode == 0 and out.stdout.strip() == "same", (out.stdout, seed)
