@@ -6,6 +6,7 @@
 // int64 aln_bytes; char aln1[aln_bytes]; char aln2[aln_bytes]
 #include <stdlib.h>
 #include <algorithm>
+#include <chrono>
 #include "host.h"
 
 template <typename T> static bool rd(FILE *f, T *p, size_t n) { return n == 0 || fread(p, sizeof(T), n, f) == n; }
@@ -45,8 +46,13 @@ static int sort_mode(char **argv, int pattern)
 	return 0;
 }
 
+// GSA_TIMING=1: wall clock per stage on stderr (tools/emit_rig.cpp makes human-scale inputs for this)
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int main(int argc, char **argv)
 {
+	const bool timing = getenv("GSA_TIMING") != nullptr;
+	double t_read = 0, t_maf = 0, t_var = 0, t0 = now_s();
 	if ((argc == 6 || argc == 7) && std::string(argv[1]) == "sort") return sort_mode(argv, argc == 7 ? atoi(argv[6]) : 0);
 	if (argc != 7) return 2;
 	Options o;
@@ -60,11 +66,13 @@ int main(int argc, char **argv)
 	if (!ix.load(argv[1], err)) { fprintf(stderr, "index: %s\n", err.c_str()); return 1; }
 	std::vector<QueryChr> query;
 	if (!load_query_file(argv[2], query)) return 1;
+	if (timing) fprintf(stderr, "[timing] index + query loaded %.3f s\n", now_s() - t0);
 	FILE *f = fopen(argv[3], "rb");
 	if (!f) return 1;
 	EmitState st; st.threads = o.threads > 0 ? o.threads : 1;
 	for (int qi = 0; qi < (int)query.size(); qi++) {
 		ContigResult r;
+		double t1 = now_s();
 		int32_t nb = 0; int64_t nf = 0, ab = 0;
 		if (!rd(f, &nb, 1)) return 1;
 		r.blocks.resize((size_t)nb);
@@ -74,11 +82,18 @@ int main(int argc, char **argv)
 		r.aln1.resize((size_t)ab); r.aln2.resize((size_t)ab);
 		if (!rd(f, &r.aln1[0], (size_t)ab) || !rd(f, &r.aln2[0], (size_t)ab)) return 1;
 		if (nb == 0) continue; // src/GSAlign.cpp:541: a contig without alignments never reaches the writers
+		double t2 = now_s();
 		if (o.out_format == 1) output_maf(o, ix, query, qi, r);
 		if (o.out_format == 2) output_aln(o, ix, query, qi, r);
+		double t3 = now_s();
 		variant_identification(ix, query, qi, r, st);
+		t_read += t2 - t1; t_maf += t3 - t2; t_var += now_s() - t3;
 	}
 	fclose(f);
+	double t4 = now_s();
 	output_variants(o, ix, st);
-	return 0;
+	double t5 = now_s();
+	bool ok = emit_drain();
+	if (timing) fprintf(stderr, "[timing] records read %.3f s, alignment file %.3f s, variant scan %.3f s, output_variants %.3f s, drain %.3f s\n", t_read, t_maf, t_var, t5 - t4, now_s() - t5);
+	return ok ? 0 : 1;
 }
