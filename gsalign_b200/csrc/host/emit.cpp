@@ -624,31 +624,36 @@ void ContigResult::assign_variants(const gsa_variant_list &v)
 }
 
 // Records [v_beg, v_end) of the device's variant list (gsa_variants) -> the reference's Variant_t fields: the alleles are
-// substrings of the query and of the reference text at the record's coordinates (include/gsalign_b200.h, gsa_variant_kind)
-static void records_to_variants(const HostIndex &ix, const std::string &seq, const ContigResult &r, int chr_idx, int64_t v_beg, int64_t v_end,
-                                std::vector<Variant> &out, std::string &pool, VarCounts &cnt)
+// substrings of the query and of the reference text at the record's coordinates (include/gsalign_b200.h, gsa_variant_kind).
+// The allele lengths follow from the record alone, so a first pass sizes a stretch of records (WRITE = false) and a second
+// one writes records and alleles straight into their final places: `out` = the stretch's slots in EmitState::variants,
+// `pool` = the whole allele array, `at` = where this stretch's alleles start in it.
+template <bool WRITE>
+static size_t records_to_variants(const HostIndex &ix, const std::string &seq, const ContigResult &r, int chr_idx, int64_t v_beg, int64_t v_end,
+                                  Variant *out, char *pool, size_t at, VarCounts &cnt)
 {
-	Variant v; v.chr_idx = chr_idx;
-	out.reserve((size_t)(v_end - v_beg));
 	for (int64_t k = v_beg; k < v_end; k++) {
 		const gsa_variant &d = r.vars[(size_t)k];
-		v.pos = d.gPos; v.off = pool.size();
 		const bool text_ref = d.kind != GSA_VAR_INS;          // REF comes from the reference text (an in-fragment insertion takes the query base, H6)
 		const bool long_ref = d.kind == GSA_VAR_DEL || d.kind == GSA_VAR_FRAG_DEL;
 		const bool long_alt = d.kind == GSA_VAR_INS || d.kind == GSA_VAR_FRAG_INS;
-		v.ref_len = long_ref ? (uint32_t)d.len + 1u : 1u;
-		if (text_ref) for (uint32_t i = 0; i < v.ref_len; i++) pool += ix.text(d.rPos + i);
-		else pool += seq[(size_t)d.qPos];
-		if (long_alt) { // substr clamps at the end of the string
-			const size_t n = std::min((size_t)d.len + 1, seq.size() - (size_t)d.qPos);
-			pool.append(seq, (size_t)d.qPos, n); v.alt_len = (uint32_t)n;
-		} else if (d.kind == GSA_VAR_DEL) { pool += pool[(size_t)v.off]; v.alt_len = 1; }
-		else { pool += seq[(size_t)d.qPos]; v.alt_len = 1; }
-		if (d.kind == GSA_VAR_SNV) { v.type = 0; cnt.snv++; }
-		else if (long_alt) { v.type = 1; cnt.ins++; }
-		else { v.type = 2; cnt.del++; }
-		out.push_back(v);
+		const uint32_t ref_len = long_ref ? (uint32_t)d.len + 1u : 1u;
+		const uint32_t alt_len = long_alt ? (uint32_t)std::min((size_t)d.len + 1, seq.size() - (size_t)d.qPos) : 1u;   // substr clamps at the end of the string
+		if (WRITE) {
+			Variant &v = *out++;
+			v.chr_idx = chr_idx; v.pos = d.gPos; v.off = at; v.ref_len = ref_len; v.alt_len = alt_len;
+			char *ref = pool + at, *alt = ref + ref_len;
+			if (text_ref) for (uint32_t i = 0; i < ref_len; i++) ref[i] = ix.text(d.rPos + i);
+			else ref[0] = seq[(size_t)d.qPos];
+			if (long_alt) memcpy(alt, seq.data() + d.qPos, alt_len);
+			else alt[0] = d.kind == GSA_VAR_DEL ? ref[0] : seq[(size_t)d.qPos];
+			if (d.kind == GSA_VAR_SNV) { v.type = 0; cnt.snv++; }
+			else if (long_alt) { v.type = 1; cnt.ins++; }
+			else { v.type = 2; cnt.del++; }
+		}
+		at += (size_t)ref_len + alt_len;
 	}
+	return at;
 }
 
 void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, const ContigResult &r, EmitState &st)
@@ -658,23 +663,22 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 		const gsa_block &b = r.blocks[bi];
 		if (b.bDup) continue;
 		const int chr_idx = gen_coordinate(ix, r.frags[(size_t)b.frag_beg].rPos).ChromosomeIdx;
-		if (r.have_vars) { // the device found the records: the host only fetches the alleles
+		if (r.have_vars) { // the device found the records: the host only fetches the alleles, every thread into its own stretch
 			const int64_t v0 = r.var_first[bi], nv = r.var_count[bi];
-			const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(st.threads, nv / ((int64_t)emit_chunk() * 4)));
-			std::vector<std::vector<Variant> > part((size_t)nch);
-			std::vector<std::string> pool((size_t)nch);
+			if (nv <= 0) continue;
+			const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(st.threads, nv / emit_chunk()));
+			std::vector<size_t> at((size_t)nch + 1, 0);
 			std::vector<VarCounts> cnt((size_t)nch);
-			parallel_chunks(nch, st.threads, [&](int k) {
-				records_to_variants(ix, seq, r, chr_idx, v0 + nv * k / nch, v0 + nv * (k + 1) / nch, part[(size_t)k], pool[(size_t)k], cnt[(size_t)k]);
-			});
-			for (int k = 0; k < nch; k++) {
-				const uint64_t base = st.alleles.size();
-				st.alleles += pool[(size_t)k];
-				size_t at = st.variants.size();
-				st.variants.insert(st.variants.end(), part[(size_t)k].begin(), part[(size_t)k].end());
-				for (size_t i = at; i < st.variants.size(); i++) st.variants[i].off += base;
-				st.iSNV += cnt[(size_t)k].snv; st.iInsertion += cnt[(size_t)k].ins; st.iDeletion += cnt[(size_t)k].del;
-			}
+			auto lo = [&](int k) { return v0 + nv * k / nch; };
+			parallel_chunks(nch, st.threads, [&](int k) { VarCounts none; at[(size_t)k + 1] = records_to_variants<false>(ix, seq, r, chr_idx, lo(k), lo(k + 1), nullptr, nullptr, 0, none); });
+			for (int k = 0; k < nch; k++) at[(size_t)k + 1] += at[(size_t)k];
+			const size_t abase = st.alleles.size();
+			Variant *vout = st.variants.grow((size_t)nv);
+			char *pool = st.alleles.grow(at[(size_t)nch]);
+			if (!vout || !pool) { fprintf(stderr, "out of memory while collecting the variants\n"); return; }
+			pool -= abase;                                     // offsets count from the start of the allele array
+			parallel_chunks(nch, st.threads, [&](int k) { records_to_variants<true>(ix, seq, r, chr_idx, lo(k), lo(k + 1), vout + (lo(k) - v0), pool, abase + at[(size_t)k], cnt[(size_t)k]); });
+			for (int k = 0; k < nch; k++) { st.iSNV += cnt[(size_t)k].snv; st.iInsertion += cnt[(size_t)k].ins; st.iDeletion += cnt[(size_t)k].del; }
 			continue;
 		}
 		// fragments are independent: big blocks are scanned by several threads and their records appended in fragment order,
@@ -687,14 +691,20 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 		parallel_chunks(nch, st.threads, [&](int k) {
 			scan_fragments(ix, seq, r, chr_idx, b.frag_beg + nf * k / nch, b.frag_beg + nf * (k + 1) / nch, part[(size_t)k], pool[(size_t)k], cnt[(size_t)k]);
 		});
-		for (int k = 0; k < nch; k++) {
-			const uint64_t base = st.alleles.size();
-			st.alleles += pool[(size_t)k];
-			size_t at = st.variants.size();
-			st.variants.insert(st.variants.end(), part[(size_t)k].begin(), part[(size_t)k].end());
-			for (size_t i = at; i < st.variants.size(); i++) st.variants[i].off += base;
-			st.iSNV += cnt[(size_t)k].snv; st.iInsertion += cnt[(size_t)k].ins; st.iDeletion += cnt[(size_t)k].del;
-		}
+		// the parts move to their places at the end of the two arrays, every thread its own
+		std::vector<size_t> vat((size_t)nch + 1, 0), aat((size_t)nch + 1, 0);
+		for (int k = 0; k < nch; k++) { vat[(size_t)k + 1] = vat[(size_t)k] + part[(size_t)k].size(); aat[(size_t)k + 1] = aat[(size_t)k] + pool[(size_t)k].size(); }
+		const size_t abase = st.alleles.size();
+		Variant *vout = st.variants.grow(vat[(size_t)nch]);
+		char *aout = st.alleles.grow(aat[(size_t)nch]);
+		if ((!vout && vat[(size_t)nch]) || (!aout && aat[(size_t)nch])) { fprintf(stderr, "out of memory while collecting the variants\n"); return; }
+		parallel_chunks(nch, st.threads, [&](int k) {
+			if (!pool[(size_t)k].empty()) memcpy(aout + aat[(size_t)k], pool[(size_t)k].data(), pool[(size_t)k].size());
+			Variant *o = vout + vat[(size_t)k];
+			const uint64_t base = abase + aat[(size_t)k];
+			for (const Variant &v : part[(size_t)k]) { *o = v; o->off += base; o++; }
+		});
+		for (int k = 0; k < nch; k++) { st.iSNV += cnt[(size_t)k].snv; st.iInsertion += cnt[(size_t)k].ins; st.iDeletion += cnt[(size_t)k].del; }
 	}
 }
 

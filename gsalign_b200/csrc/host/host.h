@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../../include/gsalign_b200.h"
@@ -79,11 +80,36 @@ struct ContigResult {
 	void assign_variants(const gsa_variant_list &v);
 };
 
+// A growing array of plain records whose new elements are NOT initialised: grow() hands out room that the caller's threads
+// fill (and first touch) themselves.  A human-size pair collects 33 M variant records (1 GB): value-initialising and then
+// copying them on one thread cost more than finding them.  realloc() of a large block is a remap, not a copy.
+template <typename T> struct RawArray {
+	T *p = nullptr; size_t n = 0, cap = 0;
+	RawArray() {}
+	RawArray(const RawArray &) = delete;
+	RawArray &operator=(const RawArray &) = delete;
+	~RawArray() { free(p); }
+	T *grow(size_t k)                // room for k more elements at the end; nullptr when memory is out (size unchanged)
+	{
+		if (n + k > cap) {
+			size_t want = cap + cap / 2; if (want < n + k) want = n + k; if (want < 4096) want = 4096;
+			T *q = (T *)realloc(p, want * sizeof(T));
+			if (!q) return nullptr;
+			p = q; cap = want;
+		}
+		T *r = p + n; n += k; return r;
+	}
+	size_t size() const { return n; }
+	const T *data() const { return p; }
+	T &operator[](size_t i) { return p[i]; }
+	const T &operator[](size_t i) const { return p[i]; }
+};
+
 struct EmitState {                 // running totals of GenomeComparison (src/GSAlign.cpp:14-15)
 	int64_t total_aln_len = 0, total_matches = 0, local_aln_num = 0, dup_num = 0;
 	int iSNV = 0, iInsertion = 0, iDeletion = 0;
-	std::vector<Variant> variants;   // in the order VariantIdentification pushes them (the input order of the final unstable sort)
-	std::string alleles;
+	RawArray<Variant> variants;      // in the order VariantIdentification pushes them (the input order of the final unstable sort)
+	RawArray<char> alleles;
 	int threads = 1;                 // -t: host threads the emitters may use (row assembly, variant scan, VCF formatting)
 };
 

@@ -46,6 +46,39 @@ static int sort_mode(char **argv, int pattern)
 	return 0;
 }
 
+// GSA_HARNESS_VARS=1: the variant records gsa_variants() would deliver (include/gsalign_b200.h, gsa_variant_kind) are derived
+// from the rows here, on the host, and handed to the emitters the way bin/GSAlign hands them the device's list -- so that
+// the allele fetch of that path (records_to_variants) is checked against the row scan without a GPU.
+static int nt4_of(char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } }
+static void derive_variant_records(const HostIndex &ix, ContigResult &r, std::vector<gsa_variant> &vars, std::vector<int64_t> &first, std::vector<int64_t> &count)
+{
+	auto push = [&](int kind, int64_t rPos, int qPos, int len) {
+		gsa_variant v; v.rPos = rPos; v.qPos = qPos; v.gPos = gen_coordinate(ix, rPos).gPos; v.len = len; v.kind = kind; vars.push_back(v);
+	};
+	for (const gsa_block &b : r.blocks) {
+		first.push_back((int64_t)vars.size());
+		for (int64_t t = b.frag_beg; t < b.frag_beg + b.n_frags; t++) {
+			const gsa_frag &f = r.frags[(size_t)t];
+			if (f.bSeed || (f.qLen == 0 && f.rLen == 0)) continue;
+			if (f.qLen == 0) push(GSA_VAR_FRAG_DEL, f.rPos - 1, f.qPos - 1, f.rLen);
+			else if (f.rLen == 0) push(GSA_VAR_FRAG_INS, f.rPos - 1, f.qPos - 1, f.qLen);
+			else if (f.qLen == 1 && f.rLen == 1) {
+				char c1 = r.aln1[(size_t)f.aln_off], c2 = r.aln2[(size_t)f.aln_off];
+				if (nt4_of(c1) != nt4_of(c2) && nt4_of(c2) != 4) push(GSA_VAR_SNV, f.rPos, f.qPos, 1);
+			} else {
+				const char *a1 = r.aln1.data() + f.aln_off, *a2 = r.aln2.data() + f.aln_off;
+				int qpos = f.qPos; int64_t rpos = f.rPos;
+				for (int i = 0; i < f.aln_len; i++) {
+					if (a1[i] == '-') { int ind = 1; while (i + ind < f.aln_len && a1[i + ind] == '-') ind++; push(GSA_VAR_INS, rpos - 1, qpos - 1, ind); qpos += ind; i += ind - 1; }
+					else if (a2[i] == '-') { int ind = 1; while (i + ind < f.aln_len && a2[i + ind] == '-') ind++; push(GSA_VAR_DEL, rpos - 1, qpos - 1, ind); rpos += ind; i += ind - 1; }
+					else { if (nt4_of(a1[i]) != nt4_of(a2[i]) && nt4_of(a2[i]) != 4) push(GSA_VAR_SNV, rpos, qpos, 1); rpos++; qpos++; }
+				}
+			}
+		}
+		count.push_back((int64_t)vars.size() - first.back());
+	}
+}
+
 // GSA_TIMING=1: wall clock per stage on stderr (tools/emit_rig.cpp makes human-scale inputs for this)
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -85,6 +118,12 @@ int main(int argc, char **argv)
 		double t2 = now_s();
 		if (o.out_format == 1) output_maf(o, ix, query, qi, r);
 		if (o.out_format == 2) output_aln(o, ix, query, qi, r);
+		if (getenv("GSA_HARNESS_VARS")) { // (after the writer: iExtension has trimmed the last seed by now, as in bin/GSAlign's order of effects)
+			std::vector<gsa_variant> vars; std::vector<int64_t> first, count;
+			derive_variant_records(ix, r, vars, first, count);
+			gsa_variant_list vl; vl.n_variants = (int64_t)vars.size(); vl.variants = vars.data(); vl.block_first = first.data(); vl.block_count = count.data();
+			r.assign_variants(vl);
+		}
 		double t3 = now_s();
 		variant_identification(ix, query, qi, r, st);
 		t_read += t2 - t1; t_maf += t3 - t2; t_var += now_s() - t3;

@@ -50,9 +50,14 @@ def harness(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("fmt,threads,prm,flags", [(1, 1, {}, []), (1, 5, {}, []), (2, 3, {}, ["-fmt", "2"]),
-                                                   (1, 4, dict(min_seed_len=10, sensitive=1, min_block_score=50), ["-sen"])])
-def test_emitters_match_reference_cli(workdir, harness, fmt, threads, prm, flags):
+@pytest.mark.parametrize("fmt,threads,prm,flags,dev_vars", [(1, 1, {}, [], False), (1, 5, {}, [], False), (2, 3, {}, ["-fmt", "2"], False),
+                                                            (1, 4, dict(min_seed_len=10, sensitive=1, min_block_score=50), ["-sen"], False),
+                                                            (1, 1, {}, [], True), (1, 6, {}, [], True),
+                                                            (1, 3, dict(min_seed_len=10, sensitive=1, min_block_score=50), ["-sen"], True)])
+def test_emitters_match_reference_cli(workdir, harness, fmt, threads, prm, flags, dev_vars):
+    """dev_vars: the harness derives the variant records gsa_variants() delivers (rule of include/gsalign_b200.h) and the
+    emitters take the single-GPU CLI's route (alleles fetched per record, written in place by all threads) instead of
+    scanning the rows."""
     from conftest import build_index
     from test_gpu_pipeline import make_rearranged, run_reference
     exe = os.path.join(orc.REF_DIR, "GSAlign")
@@ -61,7 +66,7 @@ def test_emitters_match_reference_cli(workdir, harness, fmt, threads, prm, flags
     d = make_rearranged(workdir)
     prefix, qry = os.path.join(d, "ref"), os.path.join(d, "qry.fa")
     build_index(os.path.join(d, "ref.fa"), prefix)
-    tag = f"{fmt}_{threads}_{'sen' if prm else 'def'}"
+    tag = f"{fmt}_{threads}_{'sen' if prm else 'def'}_{int(dev_vars)}"
     ref = run_reference(prefix, qry, os.path.join(d, f"emit_ref_{tag}.pkl"), **prm)
     rec = os.path.join(d, f"records_{tag}.bin")
     with open(rec, "wb") as f:
@@ -69,6 +74,8 @@ def test_emitters_match_reference_cli(workdir, harness, fmt, threads, prm, flags
             f.write(_records(c))
     ours, theirs = os.path.join(d, f"emit_ours_{tag}"), os.path.join(d, f"emit_ref_{tag}")
     env = dict(os.environ, GSA_EMIT_CHUNK="40")   # small chunks: the blocks here have a few thousand fragments, the threads must all get some
+    if dev_vars:
+        env["GSA_HARNESS_VARS"] = "1"
     subprocess.run([harness, prefix, qry, rec, ours, str(fmt), str(threads)], check=True, stderr=subprocess.DEVNULL, env=env)
     subprocess.run([exe, "-t", "1", "-i", prefix, "-q", qry, "-o", theirs] + flags, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     ext = ".maf" if fmt == 1 else ".aln"
