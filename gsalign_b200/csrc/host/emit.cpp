@@ -141,8 +141,9 @@ struct MappedOut {
 	{
 		OutWriter &w = OutWriter::get();
 		path = name;
-		long long known = truncate ? -1 : w.known_end(path);
-		if (known < 0) w.drain();               // nothing of an earlier writer may land after a truncation / before the size is read
+		long long known = w.known_end(path);    // >= 0: this process has written the file before (writes may still be queued)
+		if (truncate && known >= 0) w.drain();  // nothing of an earlier writer may land after the truncation
+		if (truncate) known = -1;
 		fd = open(name, O_RDWR | O_CREAT | (truncate ? O_TRUNC : 0), 0644);
 		if (fd < 0) return false;
 		struct stat sb;
@@ -677,7 +678,11 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 			char *pool = st.alleles.grow(at[(size_t)nch]);
 			if (!vout || !pool) { fprintf(stderr, "out of memory while collecting the variants\n"); return; }
 			pool -= abase;                                     // offsets count from the start of the allele array
-			parallel_chunks(nch, st.threads, [&](int k) { records_to_variants<true>(ix, seq, r, chr_idx, lo(k), lo(k + 1), vout + (lo(k) - v0), pool, abase + at[(size_t)k], cnt[(size_t)k]); });
+			parallel_chunks(nch, st.threads, [&](int k) {
+				VarCounts mine;                                 // (not cnt[k] itself: neighbouring counters share a cache line)
+				records_to_variants<true>(ix, seq, r, chr_idx, lo(k), lo(k + 1), vout + (lo(k) - v0), pool, abase + at[(size_t)k], mine);
+				cnt[(size_t)k] = mine;
+			});
 			for (int k = 0; k < nch; k++) { st.iSNV += cnt[(size_t)k].snv; st.iInsertion += cnt[(size_t)k].ins; st.iDeletion += cnt[(size_t)k].del; }
 			continue;
 		}
@@ -689,7 +694,17 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 		std::vector<std::string> pool((size_t)nch);
 		std::vector<VarCounts> cnt((size_t)nch);
 		parallel_chunks(nch, st.threads, [&](int k) {
-			scan_fragments(ix, seq, r, chr_idx, b.frag_beg + nf * k / nch, b.frag_beg + nf * (k + 1) / nch, part[(size_t)k], pool[(size_t)k], cnt[(size_t)k]);
+			const int64_t t0 = b.frag_beg + nf * k / nch, t1 = b.frag_beg + nf * (k + 1) / nch;
+			// a gap fragment yields at most one record per column and three allele bytes per column: reserved once, the vectors
+			// never move while they fill (a move of a large vector is an unmap, and an unmap interrupts every thread)
+			size_t cols = 0;
+			for (int64_t t = t0; t < t1; t++) if (!r.frags[(size_t)t].bSeed) cols += (size_t)std::max(1, r.frags[(size_t)t].aln_len);
+			// (the thread fills objects of its own: the headers of part[k], pool[k], cnt[k] share cache lines with their neighbours',
+			// and every push writes the header)
+			std::vector<Variant> my_part; std::string my_pool; VarCounts mine;
+			my_part.reserve(cols); my_pool.reserve(3 * cols + 16);
+			scan_fragments(ix, seq, r, chr_idx, t0, t1, my_part, my_pool, mine);
+			part[(size_t)k].swap(my_part); pool[(size_t)k].swap(my_pool); cnt[(size_t)k] = mine;
 		});
 		// the parts move to their places at the end of the two arrays, every thread its own
 		std::vector<size_t> vat((size_t)nch + 1, 0), aat((size_t)nch + 1, 0);
