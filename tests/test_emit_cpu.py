@@ -105,3 +105,25 @@ def test_threaded_partition_swaps_like_std_sort(harness, n, distinct, threads, p
     for seed in (1, 2):
         out = subprocess.run([harness, "sort", str(n), str(distinct), str(threads), str(seed), str(pattern)], capture_output=True, text=True, env=env)
         assert out.returncode == 0 and out.stdout.strip() == "same", (out.stdout, seed)
+
+
+def test_fabricated_contigs_threads_and_variant_routes_same_bytes(harness, tmp_path):
+    """tools/emit_rig.cpp fabricates the records of contig pairs at the BASELINE rates (one block of ~185 000 fragments per
+    10 Mbp contig, indels included): the files must not depend on the thread count, nor on whether the variants come from
+    the row scan or from derived device-style records -- at chunk sizes that give every thread several stretches."""
+    rig = str(tmp_path / "emit_rig")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", rig, os.path.join(ROOT, "tools", "emit_rig.cpp")], check=True)
+    d = str(tmp_path)
+    subprocess.run([rig, d, "3", "10000000", "0.01", "0.001", "9"], check=True, stderr=subprocess.DEVNULL)
+    outs = []
+    for tag, threads, env in (("t1", 1, {}), ("t8", 8, {"GSA_EMIT_CHUNK": "3000"}), ("t5v", 5, {"GSA_EMIT_CHUNK": "3000", "GSA_HARNESS_VARS": "1"}),
+                              ("t16v", 16, {"GSA_HARNESS_VARS": "1"})):
+        out = os.path.join(d, tag)
+        subprocess.run([harness, os.path.join(d, "ref"), os.path.join(d, "qry.fa"), os.path.join(d, "records.bin"), out, "1", str(threads)],
+                       check=True, stderr=subprocess.DEVNULL, env=dict(os.environ, **env))
+        outs.append(out)
+    for e in (".maf", ".vcf"):
+        want = open(outs[0] + e, "rb").read()
+        assert len(want) > 10_000_000
+        for o in outs[1:]:
+            assert open(o + e, "rb").read() == want, (o, e)
