@@ -127,38 +127,66 @@ bool check_input_file(const char *path)
 	return !s.empty() && s[0] == '>';
 }
 
-// One record of the query FASTA: [beg, end) starts at a '>' header line.  Same acceptance rules as LoadQueryFile /
-// CheckQuerySeq (src/main.cpp:66-114): header trimmed by TrimChromosomeName, empty lines skipped, a trailing '\r' dropped,
-// every other character must be a letter.  Returns the offending line in *bad_line on failure.
-static bool parse_record(const char *beg, const char *end, QueryChr &qc, std::string *bad_line)
+// The query FASTA is parsed in PIECES: a record (from its '>' header line to the next one) is cut, at line starts, into
+// stretches of a few megabytes, so that one long contig keeps every core busy just like many short ones.  Same acceptance
+// rules as LoadQueryFile / CheckQuerySeq (src/main.cpp:66-114): header trimmed by TrimChromosomeName, empty lines skipped, a
+// trailing '\r' dropped, every other character must be a letter.
+struct FastaPiece {
+	const char *beg, *end;   // whole lines of the record's body (the header line belongs to no piece)
+	size_t rec;              // index of the record
+	size_t len = 0, at = 0;  // sequence letters in the piece; where they go in the record's string
+	std::string bad;         // the first offending line
+	bool is_bad = false;
+};
+
+// pass 0 (copy = nullptr) validates the lines of a piece and counts their letters; pass 1 copies them to `copy`
+static size_t walk_piece(FastaPiece &pc, char *copy)
 {
-	const char *p = beg;
-	bool header = true;
-	size_t total = 0;
-	for (int pass = 0; pass < 2; pass++) { // pass 0 validates and sizes, pass 1 copies
-		p = beg; header = true;
-		if (pass == 1) qc.seq.resize(total);
-		size_t at = 0;
-		while (p < end) {
-			const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-			const char *le = nl ? nl : end;
-			size_t len = (size_t)(le - p);
-			if (len > 0) {
-				if (header) { if (pass == 0) qc.name = trim_chromosome_name(std::string(p + 1, len - 1)); header = false; }
-				else {
-					if (p[len - 1] == '\r') len--;
-					if (pass == 0) {
-						unsigned bad = 0;
-						for (size_t i = 0; i < len; i++) bad |= (unsigned)((unsigned char)((p[i] | 0x20) - 'a') >= 26); // !isalpha, C locale
-						if (bad) { bad_line->assign(p, len); return false; }
-						total += len;
-					} else { memcpy(&qc.seq[at], p, len); at += len; }
-				}
-			}
-			p = nl ? nl + 1 : end;
+	size_t at = 0;
+	for (const char *p = pc.beg; p < pc.end;) {
+		const char *nl = (const char *)memchr(p, '\n', (size_t)(pc.end - p));
+		const char *le = nl ? nl : pc.end;
+		size_t len = (size_t)(le - p);
+		if (len > 0) {
+			if (p[len - 1] == '\r') len--;
+			if (!copy) {
+				unsigned bad = 0;
+				for (size_t i = 0; i < len; i++) bad |= (unsigned)((unsigned char)((p[i] | 0x20) - 'a') >= 26); // !isalpha, C locale
+				if (bad) { pc.bad.assign(p, len); pc.is_bad = true; return at; }
+			} else memcpy(copy + at, p, len);
+			at += len;
 		}
+		p = nl ? nl + 1 : pc.end;
 	}
-	return true;
+	return at;
+}
+
+// gives the string its final length.  Built as C++23 the letters are left for the copying threads to write (and their pages to
+// first touch): a 125 Mbp contig is 125 MB that resize() would zero on one thread first.
+static void size_string(std::string &s, size_t n)
+{
+#if defined(__cpp_lib_string_resize_and_overwrite)
+	s.resize_and_overwrite(n, [](char *, size_t k) { return k; });
+#else
+	s.resize(n);
+#endif
+}
+
+static size_t fasta_piece_bytes()
+{ // GSA_FASTA_PIECE shrinks the pieces so that tests put their borders everywhere in small files
+	static const size_t v = [] { const char *e = getenv("GSA_FASTA_PIECE"); long long x = e ? atoll(e) : 0; return x > 0 ? (size_t)x : (size_t)4 << 20; }();
+	return v;
+}
+
+// runs fn(i) for i in [0, n) on up to nth threads (dynamic: items are of uneven size)
+template <typename F> static void for_each_item(size_t n, size_t nth, F fn)
+{
+	std::atomic<size_t> next(0);
+	auto work = [&] { for (size_t i; (i = next++) < n;) fn(i); };
+	std::vector<std::thread> th;
+	for (size_t t = 1; t < std::min(nth, n); t++) th.emplace_back(work);
+	work();
+	for (auto &t : th) t.join();
 }
 
 bool load_query_file(const char *path, std::vector<QueryChr> &out)
@@ -209,22 +237,43 @@ bool load_query_file(const char *path, std::vector<QueryChr> &out)
 	}
 	if (ok) {
 		out.resize(starts.size());
-		std::vector<std::string> bad(starts.size());
-		std::vector<char> good(starts.size(), 1);
 		unsigned hw = std::thread::hardware_concurrency();
-		size_t nth = std::max<size_t>(1, std::min<size_t>(starts.size(), hw ? hw : 4));
-		std::vector<std::thread> th;
-		std::atomic<size_t> next(0);
-		auto work = [&] { for (size_t i; (i = next++) < starts.size();) good[i] = parse_record(starts[i], i + 1 < starts.size() ? starts[i + 1] : end, out[i], &bad[i]); };
-		for (size_t t = 1; t < nth; t++) th.emplace_back(work);
-		work();
-		for (auto &t : th) t.join();
-		for (size_t i = 0; i < starts.size() && ok; i++)
-			if (!good[i]) { // the first bad line in file order, like the serial reader
-				printf("%s\n", bad[i].c_str());
+		const size_t nth = std::max<size_t>(1, hw ? hw : 4);
+		// the pieces of every record: the header line is taken here, the body is cut at the first line start at or after every
+		// multiple of the piece size
+		std::vector<FastaPiece> pieces;
+		std::vector<size_t> first_piece(starts.size() + 1, 0);
+		const size_t want = fasta_piece_bytes();
+		for (size_t i = 0; i < starts.size(); i++) {
+			const char *rb = starts[i], *re = i + 1 < starts.size() ? starts[i + 1] : end;
+			const char *nl = (const char *)memchr(rb, '\n', (size_t)(re - rb));
+			const char *he = nl ? nl : re;
+			out[i].name = trim_chromosome_name(std::string(rb + 1, (size_t)(he - rb) - 1));
+			first_piece[i] = pieces.size();
+			for (const char *b = nl ? nl + 1 : re; b < re;) {
+				const char *e = re;
+				if ((size_t)(re - b) > want) { const char *c = (const char *)memchr(b + want - 1, '\n', (size_t)(re - (b + want - 1))); if (c) e = c + 1; }
+				FastaPiece pc; pc.beg = b; pc.end = e; pc.rec = i;
+				pieces.push_back(pc);
+				b = e;
+			}
+		}
+		first_piece[starts.size()] = pieces.size();
+		for_each_item(pieces.size(), nth, [&](size_t k) { pieces[k].len = walk_piece(pieces[k], nullptr); });
+		for (size_t k = 0; k < pieces.size() && ok; k++)
+			if (pieces[k].is_bad) { // the first bad line in file order, like the serial reader
+				printf("%s\n", pieces[k].bad.c_str());
 				fprintf(stderr, "The query sequence contains non-alphabet characters!\n");
 				ok = false;
 			}
+		if (ok) {
+			for_each_item(starts.size(), nth, [&](size_t i) { // (the string's pages are first touched by whoever sizes it)
+				size_t total = 0;
+				for (size_t k = first_piece[i]; k < first_piece[i + 1]; k++) { pieces[k].at = total; total += pieces[k].len; }
+				size_string(out[i].seq, total);
+			});
+			for_each_item(pieces.size(), nth, [&](size_t k) { if (pieces[k].len) walk_piece(pieces[k], &out[pieces[k].rec].seq[pieces[k].at]); });
+		}
 	}
 	if (size) munmap((void *)buf, size);
 	if (!ok) return false;

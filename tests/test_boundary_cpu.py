@@ -186,20 +186,24 @@ int main(int argc, char **argv)
 '''
 
 
-def test_query_fasta_reader_edge_cases(tmp_path):
+@pytest.mark.parametrize("std,piece", [("c++17", None), ("c++23", None), ("c++23", "7"), ("c++17", "1")])
+def test_query_fasta_reader_edge_cases(tmp_path, std, piece):
     """the CLI's parallel, memory-mapped FASTA reader keeps LoadQueryFile's rules (reference src/main.cpp:35-114): header
-    trimming, CR stripping, empty lines and records, no trailing newline, sequence before a header, non-letters"""
+    trimming, CR stripping, empty lines and records, no trailing newline, sequence before a header, non-letters.
+    The reader cuts records into pieces at line starts (GSA_FASTA_PIECE = bytes per piece: tiny values put a border after
+    every line) and, built as C++23 like bin/GSAlign, leaves the strings' letters to the copying threads."""
     import subprocess
     host = os.path.join(ROOT, "gsalign_b200", "csrc", "host")
     src = tmp_path / "ld.cpp"
     src.write_text(_LOADER_HARNESS)
     exe = str(tmp_path / "ld")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-I", host, "-o", exe, str(src), os.path.join(host, "io.cpp"), "-lpthread"], check=True)
+    subprocess.run(["g++", "-O1", f"-std={std}", "-I", host, "-o", exe, str(src), os.path.join(host, "io.cpp"), "-lpthread"], check=True)
+    env = dict(os.environ, **({"GSA_FASTA_PIECE": piece} if piece else {}))
 
     def run(text: bytes):
         f = tmp_path / "q.fa"
         f.write_bytes(text)
-        r = subprocess.run([exe, str(f)], capture_output=True, text=True)
+        r = subprocess.run([exe, str(f)], capture_output=True, text=True, env=env)
         return r.stdout.splitlines(), r.stderr
 
     out, _ = run(b"\n\n>chr1 some comment\nACGTNNacgt\r\n\nGGGG\n>chr2|x:1\nTTTT\n>empty\n>last\nAC")
@@ -210,6 +214,12 @@ def test_query_fasta_reader_edge_cases(tmp_path):
     assert out[0] == "AC1GT" and "ok=0" in out[1] and "non-alphabet" in err
     out, err = run(b">c\nACGT\n>d\nAC>GT\n")                 # '>' inside a sequence line is a non-letter too
     assert out[0] == "AC>GT" and "ok=0" in out[1]
+    out, err = run(b">c\nACGT\nAC-T\nAAAA\nA.A\n>d\nA*\n")       # several bad lines: the first one in file order is the one echoed
+    assert out[0] == "AC-T" and "ok=0" in out[1]
+    out, _ = run(b">only header")
+    assert out == ["ok=1 n=1", "[only] 0 "]
+    out, _ = run(b">x\r\nAC\r\n\r\nGT\r\n")                   # CR LF line ends: the header keeps its '\r' like the reference's getline does
+    assert out == ["ok=1 n=1", "[x", "] 4 ACGT"]           # (splitlines() cuts at the name's '\r')
     big = b">a\n" + b"ACGT" * 50_000 + b"\n" + b"".join(b">s%d\n%s\n" % (i, b"GATTACA" * (i + 1)) for i in range(40))
     out, _ = run(big)
     assert out[0] == "ok=1 n=41" and out[1].startswith("[a] 200000 ACGTACGT") and out[41] == "[s39] 280 " + "GATTACA" * 40
@@ -232,8 +242,9 @@ def test_query_fasta_reader_edge_cases(tmp_path):
     src2.write_text(_LOADER_HARNESS.replace('printf("[%s] %zu %s\\n", c.name.c_str(), c.seq.size(), c.seq.c_str());',
                                             '{ unsigned long long h = 1469598103934665603ull; for (char ch : c.seq) h = (h ^ (unsigned char)ch) * 1099511628211ull; printf("[%s] %zu %llx\\n", c.name.c_str(), c.seq.size(), h); }'))
     exe2 = str(tmp_path / "ld2")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I", host, "-o", exe2, str(src2), os.path.join(host, "io.cpp"), "-lpthread"], check=True)
-    got = subprocess.run([exe2, str(f)], capture_output=True, text=True).stdout.splitlines()
+    subprocess.run(["g++", "-O2", f"-std={std}", "-I", host, "-o", exe2, str(src2), os.path.join(host, "io.cpp"), "-lpthread"], check=True)
+    env2 = dict(os.environ, **({"GSA_FASTA_PIECE": "100003"} if piece else {}))
+    got = subprocess.run([exe2, str(f)], capture_output=True, text=True, env=env2).stdout.splitlines()
 
     def fnv(b):
         h = 1469598103934665603
