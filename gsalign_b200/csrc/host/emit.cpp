@@ -675,9 +675,12 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 			for (int k = 0; k < nch; k++) at[(size_t)k + 1] += at[(size_t)k];
 			const size_t abase = st.alleles.size();
 			Variant *vout = st.variants.grow((size_t)nv);
-			char *pool = st.alleles.grow(at[(size_t)nch]);
-			if (!vout || !pool) { fprintf(stderr, "out of memory while collecting the variants\n"); return; }
-			pool -= abase;                                     // offsets count from the start of the allele array
+			if (!vout || !st.alleles.grow(at[(size_t)nch])) { // (the arrays stay consistent: the block's records are dropped)
+				if (vout) st.variants.n -= (size_t)nv;
+				fprintf(stderr, "out of memory while collecting the variants\n");
+				return;
+			}
+			char *pool = &st.alleles[0];                       // offsets count from the start of the allele array
 			parallel_chunks(nch, st.threads, [&](int k) {
 				VarCounts mine;                                 // (not cnt[k] itself: neighbouring counters share a cache line)
 				records_to_variants<true>(ix, seq, r, chr_idx, lo(k), lo(k + 1), vout + (lo(k) - v0), pool, abase + at[(size_t)k], mine);
@@ -712,7 +715,11 @@ void variant_identification(const HostIndex &ix, const std::vector<QueryChr> &q,
 		const size_t abase = st.alleles.size();
 		Variant *vout = st.variants.grow(vat[(size_t)nch]);
 		char *aout = st.alleles.grow(aat[(size_t)nch]);
-		if ((!vout && vat[(size_t)nch]) || (!aout && aat[(size_t)nch])) { fprintf(stderr, "out of memory while collecting the variants\n"); return; }
+		if ((!vout && vat[(size_t)nch]) || (!aout && aat[(size_t)nch])) {
+			if (vout) st.variants.n -= vat[(size_t)nch];
+			fprintf(stderr, "out of memory while collecting the variants\n");
+			return;
+		}
 		parallel_chunks(nch, st.threads, [&](int k) {
 			if (!pool[(size_t)k].empty()) memcpy(aout + aat[(size_t)k], pool[(size_t)k].data(), pool[(size_t)k].size());
 			Variant *o = vout + vat[(size_t)k];
