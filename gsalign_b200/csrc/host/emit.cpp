@@ -64,7 +64,9 @@ public:
 			const size_t want = (n + n / 4 + 4095) & ~(size_t)4095;
 			void *m = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
 			if (m == MAP_FAILED) { mem[s] = nullptr; cap[s] = 0; lk.lock(); busy[s] = false; failed = true; cv.notify_all(); return -1; }
-			madvise(m, want, MADV_HUGEPAGE);
+			// (no MADV_HUGEPAGE: measured neutral here -- the two buffers are faulted in once per process by all threads -- and with
+			// defrag=madvise a huge-page fault compacts memory synchronously, which on a box whose memory is full of freshly
+			// written page cache can stall for longer than all the 4 KB faults together)
 			mem[s] = (char *)m; cap[s] = want;
 		}
 		return s;
