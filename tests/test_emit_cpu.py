@@ -107,14 +107,17 @@ def test_threaded_partition_swaps_like_std_sort(harness, n, distinct, threads, p
         assert out.returncode == 0 and out.stdout.strip() == "same", (out.stdout, seed)
 
 
-def test_fabricated_contigs_threads_and_variant_routes_same_bytes(harness, tmp_path):
+@pytest.mark.parametrize("contigs,bp,snv,indel,min_bytes", [(3, 10_000_000, "0.01", "0.001", 10_000_000), (2, 3_000_000, "0.05", "0.03", 5_000_000),
+                                                             (2, 4_000_000, "0.10", "0", 5_000_000)])
+def test_fabricated_contigs_threads_and_variant_routes_same_bytes(harness, tmp_path, contigs, bp, snv, indel, min_bytes):
     """tools/emit_rig.cpp fabricates the records of contig pairs at the BASELINE rates (one block of ~185 000 fragments per
-    10 Mbp contig, indels included): the files must not depend on the thread count, nor on whether the variants come from
+    10 Mbp contig, indels included), at an indel-dense setting (neighbouring events merge into long gapped fragments) and at
+    C5's divergence: the files must not depend on the thread count, nor on whether the variants come from
     the row scan or from derived device-style records -- at chunk sizes that give every thread several stretches."""
     rig = str(tmp_path / "emit_rig")
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", rig, os.path.join(ROOT, "tools", "emit_rig.cpp")], check=True)
     d = str(tmp_path)
-    subprocess.run([rig, d, "3", "10000000", "0.01", "0.001", "9"], check=True, stderr=subprocess.DEVNULL)
+    subprocess.run([rig, d, str(contigs), str(bp), snv, indel, "9"], check=True, stderr=subprocess.DEVNULL)
     outs = []
     for tag, threads, env in (("t1", 1, {}), ("t8", 8, {"GSA_EMIT_CHUNK": "3000"}), ("t5v", 5, {"GSA_EMIT_CHUNK": "3000", "GSA_HARNESS_VARS": "1"}),
                               ("t16v", 16, {"GSA_HARNESS_VARS": "1"})):
@@ -124,6 +127,6 @@ def test_fabricated_contigs_threads_and_variant_routes_same_bytes(harness, tmp_p
         outs.append(out)
     for e in (".maf", ".vcf"):
         want = open(outs[0] + e, "rb").read()
-        assert len(want) > 10_000_000
+        assert len(want) > min_bytes
         for o in outs[1:]:
             assert open(o + e, "rb").read() == want, (o, e)

@@ -2,7 +2,7 @@
 // CLI's emitters (gsalign_b200/csrc/host/emit.cpp, through tests/emit_harness.cpp) can be timed at the size of a C4 contig
 // on a machine without a GPU.  The records are NOT an aligner's output: a reference contig is drawn at random, SNVs and
 // indels are placed at the workload's rates, every exact stretch of >= 15 bases becomes a seed fragment and what lies between
-// two seeds becomes one gap fragment whose rows are the true alignment.  One block per contig, like the real output of the
+// two seeds becomes one gap fragment whose rows are the true alignment (ungapped where the reference would copy ungapped).  One block per contig, like the real output of the
 // synthetic BASELINE pairs.
 //   emit_rig <dir> <contigs> <bp per contig> <p_snv> <p_indel> [seed]
 // writes <dir>/ref.{pac,ann,amb,bwt,sa} (bwt/sa are header-only stubs: the emitters never read them), <dir>/qry.fa and
@@ -42,6 +42,17 @@ int main(int argc, char **argv)
 		int64_t g_r = 0, g_q = 0, score = 0, cols = 0;
 		auto flush_gap = [&] {
 			if (g1.empty()) return;
+			{ // GenerateFragAlignment's rule (src/ProcessCandidateAlignment.cpp:290-351): a fragment of equal lengths whose ungapped
+			  // comparison shows at most 5 mismatches is copied ungapped -- in particular a 1 x 1 fragment is always one column
+				std::string r1, r2;
+				for (char ch : g1) if (ch != '-') r1 += ch;
+				for (char ch : g2) if (ch != '-') r2 += ch;
+				if (r1.size() == r2.size() && r1.size() != g1.size()) {
+					int mis = 0;
+					for (size_t i = 0; i < r1.size(); i++) mis += r1[i] != r2[i];
+					if (mis <= 5) { g1 = r1; g2 = r2; }
+				}
+			}
 			gsa_frag f; memset(&f, 0, sizeof(f));
 			f.rPos = (int64_t)c * L + g_r; f.qPos = (int32_t)g_q; f.bSeed = 0; f.aln_off = (int64_t)a1.size(); f.aln_len = (int32_t)g1.size();
 			for (size_t i = 0; i < g1.size(); i++) { f.rLen += g1[i] != '-'; f.qLen += g2[i] != '-'; score += g1[i] == g2[i]; }
