@@ -334,10 +334,16 @@ static int count_gaps(const char *aln, int i, int stop)
 // assembles the two rows of a block (src/tools.cpp:169-184): inside seeds BOTH rows are copied from the query.
 // Fragments are independent once their offsets are known, so big blocks are assembled by several threads; the number of
 // gap characters of each row (needed for the "size" column) is counted on the way: only gap fragments hold any.
+static void build_rows(const QueryChr &qc, const ContigResult &r, const gsa_block &b, char *a1, char *a2, int threads, int64_t &gaps1, int64_t &gaps2);
 static void build_rows(const QueryChr &qc, const ContigResult &r, const gsa_block &b, std::vector<char> &a1, std::vector<char> &a2, int threads,
                        int64_t &gaps1, int64_t &gaps2)
 {
 	a1.resize((size_t)b.aln_len + 1); a2.resize((size_t)b.aln_len + 1);
+	build_rows(qc, r, b, a1.data(), a2.data(), threads, gaps1, gaps2);
+}
+// (rows of b.aln_len + 1 bytes each, NUL-terminated; the memory may be uninitialised: every byte is written here)
+static void build_rows(const QueryChr &qc, const ContigResult &r, const gsa_block &b, char *a1, char *a2, int threads, int64_t &gaps1, int64_t &gaps2)
+{
 	a1[(size_t)b.aln_len] = a2[(size_t)b.aln_len] = '\0';
 	const int64_t nf = b.n_frags;
 	int nch = (int)std::max<int64_t>(1, std::min<int64_t>(threads, nf / emit_chunk()));
@@ -353,13 +359,13 @@ static void build_rows(const QueryChr &qc, const ContigResult &r, const gsa_bloc
 		for (int64_t t = chunk_beg(k); t < chunk_beg(k + 1); t++) {
 			const gsa_frag &f = r.frags[(size_t)t];
 			if (f.bSeed) {
-				memcpy(a1.data() + pos, qc.seq.data() + f.qPos, (size_t)f.qLen);
-				memcpy(a2.data() + pos, qc.seq.data() + f.qPos, (size_t)f.qLen);
+				memcpy(a1 + pos, qc.seq.data() + f.qPos, (size_t)f.qLen);
+				memcpy(a2 + pos, qc.seq.data() + f.qPos, (size_t)f.qLen);
 				pos += (size_t)f.qLen;
 			} else {
 				const char *s1 = r.aln1.data() + f.aln_off, *s2 = r.aln2.data() + f.aln_off;
-				memcpy(a1.data() + pos, s1, (size_t)f.aln_len);
-				memcpy(a2.data() + pos, s2, (size_t)f.aln_len);
+				memcpy(a1 + pos, s1, (size_t)f.aln_len);
+				memcpy(a2 + pos, s2, (size_t)f.aln_len);
 				for (int i = 0; i < f.aln_len; i++) { c1 += s1[i] == '-'; c2 += s2[i] == '-'; }
 				pos += (size_t)f.aln_len;
 			}
@@ -371,7 +377,7 @@ static void build_rows(const QueryChr &qc, const ContigResult &r, const gsa_bloc
 }
 
 // iExtension (src/tools.cpp:192-202): a block whose last seed runs past the end of its contig is trimmed in place
-static void trim_extension(const HostIndex &ix, const Coordinate &coor, ContigResult &r, gsa_block &b, std::vector<char> &a1, std::vector<char> &a2)
+template <typename Rows> static void trim_extension(const HostIndex &ix, const Coordinate &coor, ContigResult &r, gsa_block &b, Rows &a1, Rows &a2)
 {
 	gsa_frag &last = r.frags[(size_t)(b.frag_beg + b.n_frags - 1)];
 	int idx = coor.ChromosomeIdx;
@@ -528,32 +534,91 @@ void output_maf(const Options &o, const HostIndex &ix, const std::vector<QueryCh
 	out.close_file();
 }
 
+// "%12lld" / "%12d" of a number of at most twelve characters: right-aligned in 12 columns
+static inline char *put_padded_int(char *p, long long v)
+{
+	char tmp[24]; int n = 0;
+	unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+	do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+	if (v < 0) tmp[n++] = '-';
+	for (int k = n; k < 12; k++) *p++ = ' ';
+	while (n) *p++ = tmp[--n];
+	return p;
+}
+
 void output_aln(const Options &o, const HostIndex &ix, const std::vector<QueryChr> &q, int qidx, ContigResult &r)
-{ // OutputAlignment, src/tools.cpp:222-286
-	FILE *out = fopen(o.aln.c_str(), qidx == 0 ? "w" : "a");
-	if (!out) return;
+{ // OutputAlignment, src/tools.cpp:222-286.  The 80-column windows of a block are independent once the running positions at
+  // their starts are known (prefix sums of the non-gap counts), so they are formatted by all threads straight into the output
+  // buffer: a counting pass, the offsets, a writing pass -- the same bytes the fprintf loop produces, "%.80s" stopping at the NUL
+  // that iExtension may have put into a row included.
+	MappedOut out;
+	if (!out.open_file(o.aln.c_str(), qidx == 0)) return;
 	const QueryChr &qc = q[(size_t)qidx];
-	std::vector<char> a1, a2;
+	struct Rows { // the two rows of a block; grown without initialising: build_rows writes every byte, on all threads
+		char *p = nullptr; size_t cap = 0;
+		~Rows() { free(p); }
+		bool fit(size_t n) { if (n <= cap) return true; free(p); p = (char *)malloc(n); cap = p ? n : 0; return p != nullptr; }
+		char &operator[](size_t i) { return p[i]; }
+	} a1, a2;
 	std::string qname, rname;
+	const int nth = std::max(1, o.threads);
 	for (gsa_block &b : r.blocks) {
 		if (!o.allow_dup && b.bDup) continue;
 		int64_t gaps1 = 0, gaps2 = 0;
-		build_rows(qc, r, b, a1, a2, o.threads, gaps1, gaps2);
-		uint32_t aln_len = (uint32_t)b.aln_len; // rows were assembled at the untrimmed length
+		if (!a1.fit((size_t)b.aln_len + 1) || !a2.fit((size_t)b.aln_len + 1)) { fprintf(stderr, "out of memory while writing the alignments\n"); break; }
+		build_rows(qc, r, b, a1.p, a2.p, o.threads, gaps1, gaps2);
+		const uint32_t aln_len = (uint32_t)b.aln_len; // rows were assembled at the untrimmed length
 		Coordinate coor = gen_coordinate(ix, r.frags[(size_t)b.frag_beg].rPos);
 		padded_names(ix, qc, coor.ChromosomeIdx, qname, rname);
 		trim_extension(ix, coor, r, b, a1, a2);
-		fprintf(out, "#Identity = %d / %d (%.2f%%) Orientation = %s\n\n", b.score, b.aln_len, (int)(1000 * (1.0 * b.score / b.aln_len)) / 10.0, coor.bDir ? "Forward" : "Reverse");
-		uint32_t pos = 0; int qpos = r.frags[(size_t)b.frag_beg].qPos + 1; long long rpos = coor.gPos;
-		while (pos < aln_len) {
-			int stop = (int)(pos + 80 > aln_len ? aln_len : pos + 80);
-			int p = 80 - count_gaps(a1.data(), (int)pos, stop), qq = 80 - count_gaps(a2.data(), (int)pos, stop);
-			fprintf(out, "ref.%s\t%12lld\t%.80s\nqry.%s\t%12d\t%.80s\n\n", rname.c_str(), rpos, a1.data() + pos, qname.c_str(), qpos, a2.data() + pos);
-			pos += 80; rpos += coor.bDir ? p : -p; qpos += qq;
-		}
-		fprintf(out, "%s\n", std::string(100, '*').c_str());
+		char head[256];
+		const int nh = snprintf(head, sizeof(head), "#Identity = %d / %d (%.2f%%) Orientation = %s\n\n", b.score, b.aln_len, (int)(1000 * (1.0 * b.score / b.aln_len)) / 10.0, coor.bDir ? "Forward" : "Reverse");
+		const size_t nw = ((size_t)aln_len + 79) / 80;                       // windows of the fprintf loop (pos < aln_len)
+		const int nch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nth, nw / (size_t)std::max<int64_t>(1, emit_chunk() / 16)));   // 4 096 windows per thread at least
+		auto w_beg = [&](int k) { return nw * (size_t)k / (size_t)nch; };
+		// non-gap counts of a window as the loop adds them: 80 minus the '-' of [pos, stop), for a short last window too
+		auto steps = [&](size_t w, int &p, int &qq) {
+			const int pos = (int)(w * 80), stop = (int)std::min<size_t>((size_t)aln_len, w * 80 + 80);
+			p = 80 - count_gaps(a1.p, pos, stop); qq = 80 - count_gaps(a2.p, pos, stop);
+		};
+		// The two numbers of a window are printed "%12lld" / "%12d": twelve columns as long as they have at most twelve
+		// characters, which positions inside a genome always do (|rpos| < 2^31 + 2^32).  A window's size is then known without
+		// its running positions, and one pass counts both the bytes and the steps of a chunk.
+		const size_t fixed = 4 + rname.size() + 1 + 12 + 1 + 1 + 4 + qname.size() + 1 + 12 + 1 + 2;   // everything of a window but the two rows
+		std::vector<long long> rsum((size_t)nch + 1, 0), qsum((size_t)nch + 1, 0);
+		std::vector<size_t> at((size_t)nch + 1, 0);
+		parallel_chunks(nch, nth, [&](int k) {
+			long long sr = 0, sq = 0; size_t bytes = 0;
+			for (size_t w = w_beg(k); w < w_beg(k + 1); w++) {
+				int p, qq; steps(w, p, qq); sr += p; sq += qq;
+				bytes += fixed + strnlen(a1.p + w * 80, 80) + strnlen(a2.p + w * 80, 80);
+			}
+			rsum[(size_t)k + 1] = sr; qsum[(size_t)k + 1] = sq; at[(size_t)k + 1] = bytes;
+		});
+		for (int k = 0; k < nch; k++) { rsum[(size_t)k + 1] += rsum[(size_t)k]; qsum[(size_t)k + 1] += qsum[(size_t)k]; at[(size_t)k + 1] += at[(size_t)k]; }
+		const long long rpos0 = coor.gPos, rdir = coor.bDir ? 1 : -1;
+		const int qpos0 = r.frags[(size_t)b.frag_beg].qPos + 1;
+		char *base = out.reserve((size_t)nh + at[(size_t)nch] + 101);
+		if (!base) break;
+		memcpy(base, head, (size_t)nh);
+		parallel_chunks(nch, nth, [&](int k) {
+			long long rpos = rpos0 + rdir * rsum[(size_t)k]; int qpos = qpos0 + (int)qsum[(size_t)k];
+			char *p = base + nh + at[(size_t)k];
+			for (size_t w = w_beg(k); w < w_beg(k + 1); w++) {
+				const size_t pos = w * 80;
+				const size_t l1 = strnlen(a1.p + pos, 80), l2 = strnlen(a2.p + pos, 80);
+				memcpy(p, "ref.", 4); p += 4; memcpy(p, rname.data(), rname.size()); p += rname.size(); *p++ = '\t';
+				p = put_padded_int(p, rpos); *p++ = '\t'; memcpy(p, a1.p + pos, l1); p += l1; *p++ = '\n';
+				memcpy(p, "qry.", 4); p += 4; memcpy(p, qname.data(), qname.size()); p += qname.size(); *p++ = '\t';
+				p = put_padded_int(p, qpos); *p++ = '\t'; memcpy(p, a2.p + pos, l2); p += l2; *p++ = '\n'; *p++ = '\n';
+				int pp, qq; steps(w, pp, qq);
+				rpos += rdir * pp; qpos += qq;
+			}
+		});
+		memset(base + nh + at[(size_t)nch], '*', 100);
+		base[(size_t)nh + at[(size_t)nch] + 100] = '\n';
 	}
-	fclose(out);
+	out.close_file();
 }
 
 // VariantIdentification (src/SeqVariant.cpp:12-119) over fragments [t_beg, t_end) of one block: records go to `out` in

@@ -4,7 +4,8 @@
 // indels are placed at the workload's rates, every exact stretch of >= 15 bases becomes a seed fragment and what lies between
 // two seeds becomes one gap fragment whose rows are the true alignment (ungapped where the reference would copy ungapped).  One block per contig, like the real output of the
 // synthetic BASELINE pairs.
-//   emit_rig <dir> <contigs> <bp per contig> <p_snv> <p_indel> [seed]
+//   emit_rig <dir> <contigs> <bp per contig> <p_snv> <p_indel> [seed [ext]]      (ext > 0: every block but the last runs ext
+//                                                                                 bases past the end of its reference contig)
 // writes <dir>/ref.{pac,ann,amb,bwt,sa} (bwt/sa are header-only stubs: the emitters never read them), <dir>/qry.fa and
 // <dir>/records.bin (the stream tests/emit_harness.cpp reads).
 #include <math.h>
@@ -23,19 +24,25 @@ static inline double rnd01() { return (double)(rnd() >> 11) * (1.0 / 90071992547
 
 int main(int argc, char **argv)
 {
-	if (argc < 6) { fprintf(stderr, "usage: emit_rig dir contigs bp p_snv p_indel [seed]\n"); return 2; }
+	if (argc < 6) { fprintf(stderr, "usage: emit_rig dir contigs bp p_snv p_indel [seed [ext]]\n"); return 2; }
 	const std::string dir = argv[1];
 	const int K = atoi(argv[2]); const int64_t L = atoll(argv[3]);
 	const double p_snv = atof(argv[4]), p_indel = atof(argv[5]), p_ev = p_snv + p_indel;
 	if (argc > 6) rng_state ^= (uint64_t)atoll(argv[6]) * 0x9E3779B97F4A7C15ull;
+	const int ext = argc > 7 ? atoi(argv[7]) : 0;
 	const int64_t l_pac = (int64_t)K * L;
 	std::vector<uint8_t> pac((size_t)(l_pac / 4 + 2), 0);
 	FILE *fq = fopen((dir + "/qry.fa").c_str(), "wb"), *fr = fopen((dir + "/records.bin").c_str(), "wb");
 	if (!fq || !fr) return 1;
 	static const char ACGT[] = "ACGT";
+	std::vector<std::string> refs((size_t)K);
 	for (int c = 0; c < K; c++) {
-		std::string ref((size_t)L, 'A'), qry, a1, a2;
-		for (int64_t i = 0; i < L; i++) { int b = (int)(rnd() >> 62); ref[(size_t)i] = ACGT[b]; int64_t g = (int64_t)c * L + i; pac[(size_t)(g >> 2)] |= (uint8_t)(b << ((~g & 3) << 1)); }
+		refs[(size_t)c].assign((size_t)L, 'A');
+		for (int64_t i = 0; i < L; i++) { int b = (int)(rnd() >> 62); refs[(size_t)c][(size_t)i] = ACGT[b]; int64_t g = (int64_t)c * L + i; pac[(size_t)(g >> 2)] |= (uint8_t)(b << ((~g & 3) << 1)); }
+	}
+	for (int c = 0; c < K; c++) {
+		const std::string &ref = refs[(size_t)c];
+		std::string qry, a1, a2;
 		qry.reserve((size_t)(L + L / 50));
 		std::vector<gsa_frag> frags;
 		std::string g1, g2;                       // rows of the gap fragment being collected
@@ -92,6 +99,10 @@ int main(int argc, char **argv)
 		}
 		flush_gap();
 		if (!frags.back().bSeed) { fprintf(stderr, "rig: contig ends in a gap fragment (harmless)\n"); }
+		else if (ext > 0 && c + 1 < K) { // the last seed runs `ext` bases into the next reference contig: what iExtension trims
+			frags.back().qLen += ext; frags.back().rLen += ext; frags.back().aln_len += ext;
+			qry.append(refs[(size_t)c + 1], 0, (size_t)ext); score += ext; cols += ext;
+		}
 		gsa_block b; memset(&b, 0, sizeof(b));
 		b.score = (int32_t)score; b.aln_len = (int32_t)cols; b.n_frags = (int32_t)frags.size(); b.frag_beg = 0;
 		int32_t nb = 1; int64_t nf = (int64_t)frags.size(), ab = (int64_t)a1.size();
